@@ -1,0 +1,93 @@
+"""Build libcellmapper_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m cellmapper_b200.build [--force] [--verbose]
+
+The shared library exports the C ABI declared in include/cellmapper_b200.h and is loaded with
+ctypes by cellmapper_b200._lib.  It lives at cellmapper_b200/lib/libcellmapper_b200.so (git-ignored,
+but it travels to the GPU box with the repo snapshot).
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIBPATH = os.path.join(LIBDIR, "libcellmapper_b200.so")
+STAMP = os.path.join(LIBDIR, "build.stamp")
+
+SOURCES = ["cabi.cu", "knn_exact.cu", "knn_mma.cu", "graph_kernel.cu", "transfer.cu", "jaccard.cu"]
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-O3",
+    "-lineinfo",
+    "-std=c++17",
+    "--expt-relaxed-constexpr",
+    "--extended-lambda",
+    "-Xcompiler",
+    "-fPIC",
+    "-Xptxas",
+    "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(root, name), "rb") as f:
+                    h.update(name.encode())
+                    h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def sources() -> list[str]:
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    fp = _fingerprint()
+    if not force and os.path.exists(LIBPATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == fp:
+        return LIBPATH
+    objs = []
+    logs = []
+    for src in sources():
+        obj = os.path.join(LIBDIR, os.path.basename(src).replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        objs.append(obj)
+    cmd = [_nvcc(), "-shared", "-o", LIBPATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+        f.write("\n".join(logs))
+    with open(STAMP, "w") as f:
+        f.write(fp)
+    if verbose:
+        print("\n".join(logs))
+    return LIBPATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

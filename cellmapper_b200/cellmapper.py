@@ -1,0 +1,487 @@
+"""Drop-in ``CellMapper`` for the k-NN mapping hot path, backed by libcellmapper_b200 (sm_100a).
+
+Mirrors the public surface of the reference class (``src/cellmapper/model/cellmapper.py``):
+``compute_neighbors`` -> ``compute_mapping_matrix`` -> ``map_obs`` / ``map_obsm`` / ``map_layers`` /
+``map``, the ``mapping_matrix`` property + setter, ``query_imputed``, ``load_precomputed_distances``
+and ``estimate_presence_score`` (``evaluate.py:426-480``).  Same keyword names, side effects on the
+AnnData objects, host-visible types and exception types; the neighbour method is ``"b200"``.
+
+Everything is computed on the GPU and stays there between steps; host objects (numpy / scipy CSR /
+pandas) are produced only where the reference's contract exposes them.  Out of scope (SURVEY.md
+§2): joint-embedding fall-backs (``use_rep=None``), evaluation metrics and plots.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Literal
+
+import numpy as np
+import pandas as pd
+import torch
+from scipy.sparse import coo_matrix, csc_matrix, csr_matrix, issparse
+
+from . import _lib, device
+from ._anndata import AnnData
+from .knn import Neighbors, NeighborsResults, _to_device
+from .logging import logger
+
+__all__ = ["CellMapper", "PackageConstants", "get_n_comps", "sorted_category_codes"]
+
+KERNEL_METHODS = ("gaussian", "scarches", "inverse_distance", "random", "equal")
+
+
+class PackageConstants:
+    n_comps = 50  # reference: constants.py:4
+
+
+def get_n_comps(n_comps: int | None, n_vars: int) -> int:
+    """reference: utils.py:223-227."""
+    if n_comps is None:
+        return min(n_vars, PackageConstants.n_comps)
+    return min(n_comps, n_vars)
+
+
+def sorted_category_codes(values: pd.Series):
+    """Class codes in the category order ``OneHotEncoder`` uses at cellmapper.py:591-594: the
+    lexicographically sorted unique values PRESENT in the column (not the pandas category order).
+    Returns (categories ndarray, codes int32 ndarray)."""
+    if isinstance(values.dtype, pd.CategoricalDtype):
+        cat = values.cat
+        present = np.unique(cat.codes.to_numpy())
+        present = present[present >= 0]
+        names = np.asarray(cat.categories.to_numpy(), dtype=object)[present]
+        order = np.argsort(names, kind="stable")  # few categories: host sort of the names only
+        cats = names[order]
+        lut = np.full(len(cat.categories) + 1, -1, dtype=np.int32)
+        lut[present[order]] = np.arange(len(order), dtype=np.int32)
+        codes = lut[cat.codes.to_numpy()]
+        if (codes < 0).any():
+            raise ValueError("missing values in a categorical obs column are not supported by method='b200'")
+        return cats, codes
+    cats, codes = np.unique(np.asarray(values.to_numpy(), dtype=object), return_inverse=True)
+    return cats, codes.astype(np.int32)
+
+
+class _DeviceCSR:
+    """The mapping matrix on the device: indptr int32 (n_q+1), cols int32, vals float32."""
+
+    def __init__(self, indptr, cols, vals, shape):
+        self.indptr, self.cols, self.vals, self.shape = indptr, cols, vals, tuple(shape)
+        self._host: csr_matrix | None = None
+
+    def to_scipy(self) -> csr_matrix:
+        if self._host is None:
+            ip = self.indptr.cpu().numpy()
+            nnz = int(ip[-1])
+            m = csr_matrix((self.vals[:nnz].cpu().numpy(), self.cols[:nnz].cpu().numpy(), ip), shape=self.shape)
+            m.has_sorted_indices = True
+            self._host = m
+        return self._host
+
+
+class CellMapper:
+    """Mapping of labels, embeddings, and expression values between reference and query datasets."""
+
+    def __init__(self, query: AnnData, reference: AnnData | None = None, *, allreduce=None) -> None:
+        """``allreduce`` (keyword-only, not in the reference): in-place SUM over ranks for the kernel
+        bandwidth statistics when the query cells are sharded over several GPUs
+        (``cellmapper_b200.dist.allreduce_sum``); ``None`` for a single process."""
+        self._allreduce = allreduce
+        self.query = query
+        self.reference = reference if reference is not None else query  # cellmapper.py:37-38
+        self._is_self_mapping = reference is None
+        if self._is_self_mapping:
+            logger.info("Initialized CellMapper for self-mapping with %d cells.", query.n_obs)
+        else:
+            logger.info(
+                "Initialized CellMapper with %d query cells and %d reference cells.", query.n_obs, self.reference.n_obs
+            )
+        self.knn: Neighbors | None = None
+        self._mapping: _DeviceCSR | None = None
+        self.label_transfer_metrics: dict[str, Any] | None = None
+        self.label_transfer_report: pd.DataFrame | None = None
+        self.prediction_postfix: str | None = None
+        self.confidence_postfix: str | None = None
+        self.only_yx: bool | None = None
+        self._query_imputed: AnnData | None = None
+        self.expression_transfer_metrics: dict[str, Any] | None = None
+        #: last imputed layer as device CSR / dense tensor (kept for callers that stay on the GPU)
+        self.imputed_device = None
+
+    def __repr__(self):
+        query_summary = f"AnnData(n_obs={self.query.n_obs:,}, n_vars={self.query.n_vars:,})"
+        if self._is_self_mapping:
+            return f"CellMapper(self-mapping, data={query_summary}, "
+        reference_summary = f"AnnData(n_obs={self.reference.n_obs:,}, n_vars={self.reference.n_vars:,})"
+        return f"CellMapper(query={query_summary}, reference={reference_summary}"
+
+    # ------------------------------------------------------------------------------------------
+    # mapping matrix property (cellmapper.py:71-137)
+    # ------------------------------------------------------------------------------------------
+    @property
+    def mapping_matrix(self) -> csr_matrix | None:
+        """scipy CSR float32 (n_query, n_reference), rows summing to 1 (materialised lazily)."""
+        return None if self._mapping is None else self._mapping.to_scipy()
+
+    @mapping_matrix.setter
+    def mapping_matrix(self, value):
+        if value is None:
+            self._mapping = None
+            return
+        self._mapping = self._validate_and_normalize_mapping_matrix(value)
+
+    @property
+    def mapping_matrix_device(self) -> _DeviceCSR | None:
+        return self._mapping
+
+    def _validate_and_normalize_mapping_matrix(self, m: csr_matrix | coo_matrix | csc_matrix) -> _DeviceCSR:
+        """reference: cellmapper.py:99-137 -- shape check, float64 row sums, multiply by the
+        reciprocal, float32 CSR.  The normalisation runs on the device."""
+        expected = (self.query.n_obs, self.reference.n_obs)
+        if tuple(m.shape) != expected:
+            raise ValueError(f"Mapping matrix shape mismatch: expected ({expected[0]}, {expected[1]}), but got {m.shape}.")
+        if not issparse(m):
+            m = csr_matrix(np.asarray(m))
+        m = m.tocsr()
+        m.sum_duplicates()
+        m.sort_indices()
+        indptr = _to_device(m.indptr, torch.int32)
+        cols = _to_device(m.indices, torch.int32)
+        vals64 = _to_device(m.data, torch.float64)
+        vals, zero = device.csr_row_normalize(indptr, vals64)
+        if int(zero.item()) > 0:
+            logger.warning("Some rows in the mapping matrix have a sum of zero. These rows will be left unchanged.")
+        return _DeviceCSR(indptr, cols, vals, expected)
+
+    # ------------------------------------------------------------------------------------------
+    # neighbours (cellmapper.py:139-251)
+    # ------------------------------------------------------------------------------------------
+    def compute_neighbors(
+        self,
+        n_neighbors: int = 30,
+        use_rep: str | None = None,
+        n_comps: int | None = None,
+        method: Literal["b200"] = "b200",
+        metric: str = "euclidean",
+        only_yx: bool = False,
+        fallback_representation: Literal["fast_cca", "joint_pca"] = "fast_cca",
+        fallback_kwargs: dict[str, Any] | None = None,
+    ) -> None:
+        self.only_yx = only_yx
+        if use_rep is None:
+            # cellmapper.py:211-235 computes PCA / fast-CCA here; outside this package's scope
+            raise NotImplementedError(
+                "method='b200' needs a precomputed joint representation: pass use_rep='<key in .obsm>' (or 'X'). "
+                "The embedding fall-backs of quadbio/cellmapper are not part of this package."
+            )
+        if use_rep == "X":
+            xrep, yrep = self.reference.X, self.query.X
+        else:
+            xrep, yrep = self.reference.obsm[use_rep], self.query.obsm[use_rep]
+        if issparse(xrep) or issparse(yrep):
+            raise ValueError("the representation must be dense (got a sparse matrix)")
+        n_comps = get_n_comps(n_comps, n_vars=xrep.shape[1])
+        xrep = np.ascontiguousarray(np.asarray(xrep)[:, :n_comps])
+        yrep = np.ascontiguousarray(np.asarray(yrep)[:, :n_comps])
+        # cellmapper.py:250 always passes both arrays; in self-mapping they are the same object here so
+        # the embedding is uploaded once
+        self.knn = Neighbors(xrep, xrep if self._is_self_mapping else yrep)
+        self.knn.compute_neighbors(n_neighbors=n_neighbors, method=method, metric=metric, only_yx=only_yx)
+        self._mapping = None
+
+    def load_precomputed_distances(self, distances_key: str = "distances", include_self: bool | None = None) -> None:
+        """reference: cellmapper.py:493-532 (self-mapping only)."""
+        if not self._is_self_mapping:
+            raise ValueError("load_precomputed_distances is only available in self-mapping mode.")
+        distances_matrix = self.query.obsp[distances_key]
+        self.knn = Neighbors.from_distances(distances_matrix, include_self=include_self)
+        logger.info(
+            "Loaded precomputed distances from '%s' with %d cells and %d neighbors per cell.",
+            distances_key,
+            distances_matrix.shape[0],
+            self.knn.xx.n_neighbors,
+        )
+
+    # ------------------------------------------------------------------------------------------
+    # mapping matrix (cellmapper.py:253-305)
+    # ------------------------------------------------------------------------------------------
+    def compute_mapping_matrix(
+        self,
+        method: Literal["jaccard", "gaussian", "scarches", "inverse_distance", "random", "hnoca", "equal"] = "gaussian",
+        allreduce=None,
+    ) -> None:
+        if self.knn is None:
+            raise ValueError("Neighbors have not been computed. Call compute_neighbors() first.")
+        logger.info("Computing mapping matrix using method '%s'.", method)
+        if method in ("jaccard", "hnoca"):
+            if self.only_yx:
+                raise ValueError(
+                    "Jaccard and HNOCa methods require both x and y neighbors to be computed. Set only_yx=False."
+                )
+            if self.knn.xx is None or self.knn.yy is None or self.knn.xy is None or self.knn.yx is None:
+                raise ValueError("Neighbors must be computed before accessing adjacency matrices.")
+            from .jaccard import jaccard_mapping_device
+
+            indptr, cols, vals = jaccard_mapping_device(self.knn, hnoca=(method == "hnoca"))
+            self._mapping = _DeviceCSR(indptr, cols, vals, (self.query.n_obs, self.reference.n_obs))
+        elif method in KERNEL_METHODS:
+            yx: NeighborsResults = self.knn.yx
+            expected = (self.query.n_obs, self.reference.n_obs)
+            if yx.shape != expected:
+                raise ValueError(
+                    f"Mapping matrix shape mismatch: expected ({expected[0]}, {expected[1]}), but got {yx.shape}."
+                )
+            indptr, cols, vals = yx.connectivities_device(
+                method, normalize=True, allreduce=allreduce if allreduce is not None else self._allreduce
+            )
+            self._mapping = _DeviceCSR(indptr, cols, vals, expected)
+        else:
+            raise NotImplementedError(f"Method '{method}' is not implemented.")
+
+    # ------------------------------------------------------------------------------------------
+    # transfers
+    # ------------------------------------------------------------------------------------------
+    def _require_mapping(self) -> _DeviceCSR:
+        if self._mapping is None:
+            raise ValueError("Mapping matrix has not been computed. Call compute_mapping_matrix() first.")
+        return self._mapping
+
+    def map_obsm(self, key: str, prediction_postfix: str = "pred") -> None:
+        """reference: cellmapper.py:307-344."""
+        m = self._require_mapping()
+        logger.info("Mapping embeddings for key '%s'.", key)
+        emb = np.asarray(self.reference.obsm[key])
+        out = device.spmm(m.indptr, m.cols, m.vals, _to_device(emb))
+        output_key = f"{key}_{prediction_postfix}"
+        self.query.obsm[output_key] = out.cpu().numpy()
+        logger.info("Embeddings mapped and stored in query.obsm['%s'].", output_key)
+
+    def map_layers(self, key: str) -> None:
+        """reference: cellmapper.py:346-383.  Sparse layers go through the CSR x CSR kernel, dense
+        layers through the k-sparse x dense kernel."""
+        m = self._require_mapping()
+        logger.info("Mapping layer for key '%s'.", key)
+        layer = self.reference.X if key == "X" else self.reference.layers[key]
+        if issparse(layer):
+            x = layer.tocsr()
+            if not x.has_sorted_indices:
+                x = x.sorted_indices()
+            n_genes = x.shape[1]
+            if n_genes > _lib.SPGEMM_MAX_COLS:
+                raise NotImplementedError(
+                    f"sparse layers with more than {_lib.SPGEMM_MAX_COLS} columns are not supported yet (got {n_genes})"
+                )
+            if x.dtype != np.float32:
+                logger.warning("sparse layer of dtype %s is transferred in float32 by method='b200'.", x.dtype)
+            oip, ocols, ovals = device.spgemm(
+                m.indptr, m.cols, m.vals, _to_device(x.indptr), _to_device(x.indices), _to_device(x.data), n_genes
+            )
+            self.imputed_device = (oip, ocols, ovals)
+            ip = oip.cpu().numpy()
+            if ip[-1] < np.iinfo(np.int32).max:
+                ip = ip.astype(np.int32)
+            out = csr_matrix((ovals.cpu().numpy(), ocols.cpu().numpy(), ip), shape=(self.query.n_obs, n_genes))
+            out.has_sorted_indices = True
+        else:
+            dense = device.spmm(m.indptr, m.cols, m.vals, _to_device(np.asarray(layer)))
+            self.imputed_device = dense
+            out = dense.cpu().numpy()
+        self.query_imputed = out
+        message = f"Expression for layer '{key}' mapped and stored in query_imputed.X."
+        if not self._is_self_mapping:
+            message += (
+                f"\nNote: The feature space matches the reference (n_vars={self.reference.n_vars}), "
+                f"not the query (n_vars={self.query.n_vars})."
+            )
+        logger.info(message)
+
+    @property
+    def query_imputed(self) -> AnnData | None:
+        return self._query_imputed
+
+    @query_imputed.setter
+    def query_imputed(self, value) -> None:
+        """reference: cellmapper.py:397-424 -> utils.create_imputed_anndata (utils.py:15-126)."""
+        if value is None:
+            self._query_imputed = None
+            return
+        if isinstance(value, AnnData):
+            if value.n_obs != self.query.n_obs:
+                raise ValueError(
+                    f"Imputed AnnData has {value.n_obs} observations, but query has {self.query.n_obs} observations. "
+                    "They must have the same number of observations."
+                )
+            self._query_imputed = value
+            return
+        if isinstance(value, pd.DataFrame):
+            if len(value.index) != self.query.n_obs:
+                raise ValueError(
+                    f"DataFrame has {len(value.index)} rows, but query has {self.query.n_obs} observations. They must match."
+                )
+            if len(value.columns) != self.reference.n_vars:
+                raise ValueError(
+                    f"DataFrame has {len(value.columns)} columns, but reference has {self.reference.n_vars} features. "
+                    "They must match."
+                )
+            value = value.values
+        if not (isinstance(value, np.ndarray) or issparse(value)):
+            raise TypeError(
+                f"Unsupported type for expression_data: {type(value)}. "
+                "Must be AnnData, numpy array, sparse matrix, or pandas DataFrame."
+            )
+        expected = (self.query.n_obs, self.reference.n_vars)
+        if tuple(value.shape) != expected:
+            raise ValueError(
+                f"Expression data shape mismatch: expected {expected}, but got {value.shape}. "
+                "Should be (n_query_cells, n_reference_genes)."
+            )
+        self._query_imputed = AnnData(
+            X=value,
+            obs=self.query.obs,
+            var=self.reference.var,
+            uns=dict(self.query.uns),
+            obsm=self.query.obsm,
+            varm=getattr(self.reference, "varm", None),
+        )
+
+    def map_obs(self, key: str, prediction_postfix: str = "pred", confidence_postfix: str = "conf") -> None:
+        """reference: cellmapper.py:534-587."""
+        self._require_mapping()
+        if key not in self.reference.obs.columns:
+            raise KeyError(f"Key '{key}' not found in reference.obs")
+        self.prediction_postfix = prediction_postfix
+        self.confidence_postfix = confidence_postfix
+        reference_data = self.reference.obs[key]
+        is_categorical = (
+            isinstance(reference_data.dtype, pd.CategoricalDtype)
+            or pd.api.types.is_object_dtype(reference_data)
+            or pd.api.types.is_string_dtype(reference_data)
+        )
+        if is_categorical:
+            logger.info("Mapping categorical data for key '%s' using one-hot encoding.", key)
+            self._map_obs_categorical(key, prediction_postfix, confidence_postfix)
+        else:
+            logger.info("Mapping numerical data for key '%s' using direct matrix multiplication.", key)
+            self._map_obs_numerical(key, prediction_postfix)
+
+    def _map_obs_categorical(self, key: str, prediction_postfix: str, confidence_postfix: str) -> None:
+        """reference: cellmapper.py:589-623 (weighted vote + argmax on the device)."""
+        m = self._require_mapping()
+        ref_col = self.reference.obs[key]
+        cats, codes = sorted_category_codes(ref_col)
+        code_dev, conf_dev = device.vote_argmax(m.indptr, m.cols, m.vals, _to_device(codes), len(cats))
+        pred_codes = code_dev.cpu().numpy()
+        conf = conf_dev.cpu().numpy()
+        if isinstance(ref_col.dtype, pd.CategoricalDtype):
+            # same values as `pd.Series(cats[pred_codes], dtype=ref dtype)` without building n strings
+            to_orig = ref_col.cat.categories.get_indexer(pd.Index(cats))
+            pred = pd.Series(
+                pd.Categorical.from_codes(to_orig[pred_codes], dtype=ref_col.dtype), index=self.query.obs_names
+            )
+        else:
+            pred = pd.Series(data=np.array(cats)[pred_codes], index=self.query.obs_names, dtype=ref_col.dtype)
+        self.query.obs[f"{key}_{prediction_postfix}"] = pred
+        self.query.obs[f"{key}_{confidence_postfix}"] = pd.Series(conf, index=self.query.obs_names)
+        if f"{key}_colors" in self.reference.uns:  # cellmapper.py:611-617
+            color_lookup = dict(zip(self.reference.obs[key].cat.categories, self.reference.uns[f"{key}_colors"], strict=True))
+            self.query.uns[f"{key}_{prediction_postfix}_colors"] = [
+                color_lookup.get(cat, "#383838") for cat in pred.cat.categories
+            ]
+        logger.info("Categorical data mapped and stored in query.obs['%s'].", f"{key}_{prediction_postfix}")
+
+    def _map_obs_numerical(self, key: str, prediction_postfix: str) -> None:
+        """reference: cellmapper.py:625-637."""
+        m = self._require_mapping()
+        values = np.array(self.reference.obs[key])
+        out = device.spmm(m.indptr, m.cols, m.vals, _to_device(values))
+        self.query.obs[f"{key}_{prediction_postfix}"] = pd.Series(data=out.cpu().numpy().ravel(), index=self.query.obs_names)
+        logger.info("Numerical data mapped and stored in query.obs['%s'].", f"{key}_{prediction_postfix}")
+
+    def map(
+        self,
+        obs_keys: str | list[str] | None = None,
+        obsm_keys: str | list[str] | None = None,
+        layer_key: str | None = None,
+        n_neighbors: int = 30,
+        use_rep: str | None = None,
+        knn_method: Literal["b200"] = "b200",
+        metric: str = "euclidean",
+        only_yx: bool = False,
+        mapping_method: Literal["jaccard", "gaussian", "scarches", "inverse_distance", "random", "hnoca", "equal"] = "gaussian",
+        prediction_postfix: str = "pred",
+    ) -> "CellMapper":
+        """reference: cellmapper.py:426-491."""
+        self.compute_neighbors(n_neighbors=n_neighbors, use_rep=use_rep, method=knn_method, metric=metric, only_yx=only_yx)
+        self.compute_mapping_matrix(method=mapping_method)
+        if obs_keys is not None:
+            for obs_key in [obs_keys] if isinstance(obs_keys, str) else obs_keys:
+                self.map_obs(key=obs_key, prediction_postfix=prediction_postfix)
+        if obsm_keys is not None:
+            for obsm_key in [obsm_keys] if isinstance(obsm_keys, str) else obsm_keys:
+                self.map_obsm(key=obsm_key, prediction_postfix=prediction_postfix)
+        if layer_key is not None:
+            self.map_layers(key=layer_key)
+        if obs_keys is None and obsm_keys is None and layer_key is None:
+            logger.warning(
+                "Neither ``obs_keys``, ``obsm_keys`` or ``layer_key`` provided. No labels, embeddings or layers were transferred. "
+                "Please provide at least one of ``obs_keys``, ``obsm_keys`` or ``layer_key``."
+            )
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    # presence score (evaluate.py:426-521) -- "next" row f1 of the scope table
+    # ------------------------------------------------------------------------------------------
+    def estimate_presence_score(
+        self,
+        groupby: str | None = None,
+        key_added: str = "presence_score",
+        log: bool = False,
+        percentile: tuple[float, float] = (1, 99),
+    ):
+        if self.knn is None or self.knn.yx is None:
+            raise ValueError("Neighbors must be computed before estimating presence scores.")
+        yx = self.knn.yx
+        indptr, cols, vals = yx.connectivities_device("gaussian", normalize=False)
+        n_ref = self.reference.n_obs
+        scores_all = device.csr_col_sums(indptr, cols, vals, n_ref).cpu().numpy()
+        df_all = pd.DataFrame({"all": scores_all}, index=self.reference.obs_names)
+        self.reference.obs[key_added] = process_presence_scores(df_all, log=log, percentile=percentile)["all"]
+        logger.info("Presence score across all query cells computed and stored in `reference.obs['%s']`", key_added)
+        if groupby is not None:
+            group_labels = self.query.obs[groupby]
+            groups = group_labels.unique()
+            score_matrix = np.zeros((n_ref, len(groups)), dtype=np.float32)
+            ip_host = indptr.cpu().numpy().astype(np.int64)
+            for gi, group in enumerate(groups):
+                rows = np.flatnonzero((group_labels == group).values)
+                # row-slice of the device CSR: gather the rows' edges into a compact CSR
+                lens = ip_host[rows + 1] - ip_host[rows]
+                sub_ip = np.zeros(len(rows) + 1, dtype=np.int32)
+                np.cumsum(lens, out=sub_ip[1:])
+                take = np.concatenate([np.arange(ip_host[r], ip_host[r + 1]) for r in rows]) if len(rows) else np.zeros(0, dtype=np.int64)
+                take_dev = _to_device(take, torch.int64)
+                sub = device.csr_col_sums(_to_device(sub_ip, torch.int32), cols[take_dev].contiguous(), vals[take_dev].contiguous(), n_ref)
+                score_matrix[:, gi] = sub.cpu().numpy()
+            df_groups = pd.DataFrame(score_matrix, index=self.reference.obs_names, columns=groups)
+            self.reference.obsm[key_added] = process_presence_scores(df_groups, log=log, percentile=percentile)
+            logger.info(
+                "Presence scores per group defined in `query.obs['%s']` computed and stored in `reference.obsm['%s']`",
+                groupby,
+                key_added,
+            )
+
+
+def process_presence_scores(scores: pd.DataFrame, log: bool = False, percentile: tuple[float, float] = (1, 99)) -> pd.DataFrame:
+    """log1p / percentile clip / min-max of presence scores (reference: evaluate.py:483-521).
+    Post-processing of one float per reference cell; host side like the reference."""
+    if log:
+        scores = np.log1p(scores)
+    if tuple(percentile) != (0, 100):
+        low, high = percentile
+        scores = scores.apply(lambda x: np.clip(x, np.percentile(x, low), np.percentile(x, high)), axis=0)
+
+    def minmax(x):
+        min_val, max_val = np.min(x), np.max(x)
+        return (x - min_val) / (max_val - min_val) if max_val > min_val else np.zeros_like(x)
+
+    return scores.apply(minmax, axis=0)

@@ -1,0 +1,369 @@
+// P2: graph kernel over the (n_q, k) edge list -> CSR -> row-normalised float32 mapping matrix.
+// Replaces NeighborsResults._compute_kernel_values / _create_sparse_matrix (knn.py:79-111,166-226)
+// and CellMapper._validate_and_normalize_mapping_matrix (cellmapper.py:99-137).  HBM-bound: every
+// edge is read once (16 B) and written once (8 B).
+#include "common.cuh"
+
+namespace cm {
+namespace {
+
+__device__ __forceinline__ bool edge_valid(double d, int64_t i) { return i != -1 && isfinite(d); }
+
+// ------------------------------------------------------------------------------------------------
+// deterministic statistics: fixed grid, per-block partials, last block folds them in index order
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatsBlocks = 592;  // 4 per SM
+constexpr int kStatsThreads = 256;
+
+struct StatsScratch {
+  double part[kStatsBlocks][3];
+  unsigned int ticket;
+};
+
+__global__ void __launch_bounds__(kStatsThreads)
+edge_stats_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n, const double* mean_in,
+                  double* out3, StatsScratch* scratch) {
+  __shared__ double sh[3][kStatsThreads / 32];
+  __shared__ bool last;
+  const double mean = mean_in ? *mean_in : 0.0;
+  double s = 0.0, m2 = 0.0, c = 0.0;
+  // contiguous slab per block, strided inside the block: a fixed summation tree for a given n
+  const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per_block;
+  const int64_t hi = lo + per_block < n ? lo + per_block : n;
+  for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+    const double dv = dist[e];
+    if (edge_valid(dv, idx[e])) {
+      s += dv;
+      const double t = dv - mean;
+      m2 = fma(t, t, m2);
+      c += 1.0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = m2; sh[2][warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, cc = 0;
+    for (int w = 0; w < kStatsThreads / 32; ++w) { a += sh[0][w]; b += sh[1][w]; cc += sh[2][w]; }
+    scratch->part[blockIdx.x][0] = a;
+    scratch->part[blockIdx.x][1] = b;
+    scratch->part[blockIdx.x][2] = cc;
+    __threadfence();
+    last = atomicAdd(&scratch->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0, b = 0, cc = 0;
+    for (unsigned w = 0; w < gridDim.x; ++w) {
+      a += scratch->part[w][0];
+      b += scratch->part[w][1];
+      cc += scratch->part[w][2];
+    }
+    out3[0] = a;
+    out3[1] = b;
+    out3[2] = cc;
+    scratch->ticket = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// numpy's float64 summation order for `np.add.reduceat` (scipy CSR row sums, _compressed.py:507):
+// first element + pairwise_sum(rest), where pairwise_sum is numpy's 8-accumulator / recursive-halving
+// routine (probed, pinned by tests/test_oracle_golden.py through the golden mapping matrices).
+// ------------------------------------------------------------------------------------------------
+template <class Load>
+__device__ double numpy_pairwise(Load a, int off, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res += a(off + i);
+    return res;
+  }
+  if (n <= 128) {
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a(off + j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] += a(off + i + j);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a(off + i);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return numpy_pairwise(a, off, n2) + numpy_pairwise(a, off + n2, n - n2);
+}
+template <class Load>
+__device__ double numpy_row_sum(Load a, int n) {
+  if (n == 0) return 0.0;
+  return a(0) + numpy_pairwise(a, 1, n - 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge list -> CSR.  One warp per query row; the row lives in the warp's shared-memory slab.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowWarps = 8;
+
+__device__ __forceinline__ double kernel_value(int kernel, double d, double p0) {
+  switch (kernel) {
+    case CM_KERNEL_GAUSSIAN: return exp(-((d * d) / p0));   // p0 = 2*sigma^2      (knn.py:198)
+    case CM_KERNEL_SCARCHES: return exp((-d) / p0);         // p0 = (2/std)^2      (knn.py:207-209)
+    case CM_KERNEL_INVERSE_DISTANCE: return 1.0 / (d + p0); // p0 = epsilon = 1e-8 (knn.py:219)
+    default: return 1.0;                                    // equal               (knn.py:202)
+  }
+}
+
+__device__ __forceinline__ double kernel_param(int kernel, const double* stats3) {
+  const double sum = stats3[0], m2 = stats3[1], cnt = stats3[2];
+  if (kernel == CM_KERNEL_GAUSSIAN) {
+    const double sigma = sum / cnt;  // np.mean
+    return 2.0 * (sigma * sigma);
+  }
+  if (kernel == CM_KERNEL_SCARCHES) {
+    const double sd = sqrt(m2 / cnt);  // np.std, population
+    const double t = 2.0 / sd;
+    return t * t;
+  }
+  return 1e-8;
+}
+
+__global__ void count_valid_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n_q, int k,
+                                   int32_t* __restrict__ indptr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) indptr[0] = 0;
+  for (int64_t row = warp0; row < n_q; row += nwarps) {
+    int c = 0;
+    for (int e = lane; e < k; e += 32) c += edge_valid(dist[row * k + e], idx[row * k + e]) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) indptr[row + 1] = c;
+  }
+}
+
+// in-place inclusive scan of a[0..n) (int32), three kernels, block sums kept in `scratch`
+constexpr int kScanBlock = 1024;
+__global__ void scan_local_kernel(int32_t* a, int64_t n, int32_t* block_sums) {
+  __shared__ int32_t sh[kScanBlock];
+  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  sh[threadIdx.x] = i < n ? a[i] : 0;
+  __syncthreads();
+  for (int o = 1; o < kScanBlock; o <<= 1) {
+    int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  if (i < n) a[i] = sh[threadIdx.x];
+  if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void scan_sums_kernel(int32_t* block_sums, int64_t nb) {
+  __shared__ int32_t sh[kScanBlock];
+  int32_t carry = 0;
+  for (int64_t base = 0; base < nb; base += kScanBlock) {
+    const int64_t i = base + threadIdx.x;
+    sh[threadIdx.x] = i < nb ? block_sums[i] : 0;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+      int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (i < nb) block_sums[i] = sh[threadIdx.x] + carry;
+    carry += sh[kScanBlock - 1];
+    __syncthreads();
+  }
+}
+__global__ void scan_add_kernel(int32_t* a, int64_t n, const int32_t* block_sums) {
+  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  if (blockIdx.x > 0 && i < n) a[i] += block_sums[blockIdx.x - 1];
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+edge_to_csr_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n_q, int k, int np,
+                   int kernel, const double* __restrict__ stats3, int normalize, const int32_t* __restrict__ indptr,
+                   int32_t* __restrict__ cols, float* __restrict__ vals_f32, double* __restrict__ vals_f64) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wv = reinterpret_cast<double*>(smem_raw) + (size_t)warp * np;
+  int32_t* cv = reinterpret_cast<int32_t*>(smem_raw + (size_t)kRowWarps * np * sizeof(double)) + (size_t)warp * np;
+  const double p0 = kernel_param(kernel, stats3);
+
+  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < n_q; row += (int64_t)gridDim.x * kRowWarps) {
+    for (int e = lane; e < np; e += 32) {
+      double w = 0.0;
+      int32_t c = INT32_MAX;
+      if (e < k) {
+        const double dv = dist[row * k + e];
+        const int64_t iv = idx[row * k + e];
+        if (edge_valid(dv, iv)) {
+          w = kernel_value(kernel, dv, p0);
+          c = (int32_t)iv;
+        }
+      }
+      wv[e] = w;
+      cv[e] = c;
+    }
+    __syncwarp();
+    // sort the row by column (invalid edges sink to the end)
+    for (int size = 2; size <= np; size <<= 1) {
+      const int half = size >> 1;
+      for (int t = lane; t < (np >> 1); t += 32) {
+        const int blk = t / half, off = t - blk * half;
+        const int i = blk * size + off, j = blk * size + size - 1 - off;
+        if (cv[j] < cv[i]) {
+          int32_t ci = cv[i]; cv[i] = cv[j]; cv[j] = ci;
+          double wi = wv[i]; wv[i] = wv[j]; wv[j] = wi;
+        }
+      }
+      __syncwarp();
+      for (int stride = size >> 2; stride >= 1; stride >>= 1) {
+        for (int t = lane; t < (np >> 1); t += 32) {
+          const int i = 2 * stride * (t / stride) + (t % stride), j = i + stride;
+          if (cv[j] < cv[i]) {
+            int32_t ci = cv[i]; cv[i] = cv[j]; cv[j] = ci;
+            double wi = wv[i]; wv[i] = wv[j]; wv[j] = wi;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    const int32_t start = indptr[row];
+    const int n_valid = indptr[row + 1] - start;
+    double inv = 1.0;
+    if (normalize) {
+      double rs = 0.0;
+      if (lane == 0) rs = numpy_row_sum([&](int i) { return wv[i]; }, n_valid);
+      rs = __shfl_sync(0xffffffffu, rs, 0);
+      if (rs == 0.0) rs = 1.0;  // zero rows are left unchanged (cellmapper.py:127-129)
+      inv = 1.0 / rs;
+    }
+    for (int e = lane; e < n_valid; e += 32) {
+      cols[start + e] = cv[e];
+      if (vals_f32) vals_f32[start + e] = (float)(wv[e] * inv);
+      if (vals_f64) vals_f64[start + e] = wv[e] * inv;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void csr_row_normalize_kernel(const int32_t* __restrict__ indptr, const double* __restrict__ vals_in,
+                                         int64_t n_rows, float* __restrict__ vals_out, unsigned long long* zero_rows) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t lo = indptr[row], hi = indptr[row + 1];
+    double rs = numpy_row_sum([&](int i) { return vals_in[lo + i]; }, hi - lo);
+    if (rs == 0.0) {
+      rs = 1.0;
+      if (zero_rows) atomicAdd(zero_rows, 1ULL);
+    }
+    const double inv = 1.0 / rs;
+    for (int32_t e = lo; e < hi; ++e) vals_out[e] = (float)(vals_in[e] * inv);
+  }
+}
+
+__global__ void csr_col_sums_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols,
+                                    const double* __restrict__ vals, int64_t n_rows, double* __restrict__ out) {
+  const int64_t nnz = indptr[n_rows];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&out[cols[e]], vals[e]);
+}
+
+}  // namespace
+}  // namespace cm
+
+using namespace cm;
+
+extern "C" int cm_edge_stats(const double* dist, const int64_t* idx, int64_t n_edges, const double* mean_in,
+                             double* out3, void* workspace, size_t workspace_bytes, void* stream) {
+  CM_REQUIRE(n_edges >= 0 && out3 && workspace, "bad edge_stats arguments");
+  CM_REQUIRE(workspace_bytes >= sizeof(StatsScratch) && sizeof(StatsScratch) <= CM_EDGE_STATS_WORKSPACE_BYTES,
+             "edge_stats workspace too small (%zu < %zu)", workspace_bytes, sizeof(StatsScratch));
+  cudaStream_t st = (cudaStream_t)stream;
+  StatsScratch* sc = static_cast<StatsScratch*>(workspace);
+  CM_CUDA_CHECK(cudaMemsetAsync(&sc->ticket, 0, sizeof(unsigned int), st));
+  edge_stats_kernel<<<kStatsBlocks, kStatsThreads, 0, st>>>(dist, idx, n_edges, mean_in, out3, sc);
+  CM_LAUNCH_CHECK("edge_stats_kernel");
+  return CM_OK;
+}
+
+extern "C" int cm_edge_kernel_to_csr(const double* dist, const int64_t* idx, int64_t n_q, int k, int kernel,
+                                     const double* stats3, int normalize, int32_t* indptr, int32_t* cols,
+                                     float* vals_f32, double* vals_f64, void* stream) {
+  CM_REQUIRE(n_q >= 0 && k >= 1, "bad edge list shape");
+  CM_REQUIRE(kernel >= 0 && kernel <= 3, "unknown kernel code %d", kernel);
+  CM_REQUIRE(vals_f32 || vals_f64, "one of vals_f32 / vals_f64 must be given");
+  CM_REQUIRE(n_q * (int64_t)k < (int64_t)INT32_MAX, "nnz must fit int32 (scipy CSR index type)");
+  int np = 32;
+  while (np < k) np <<= 1;
+  CM_REQUIRE(np <= 1024, "k = %d too large for the edge kernel (max 1024)", k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_q == 0) {
+    CM_CUDA_CHECK(cudaMemsetAsync(indptr, 0, sizeof(int32_t), st));
+    return CM_OK;
+  }
+  {
+    int64_t blocks = ceil_div(n_q * 32, 256);
+    int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
+    count_valid_kernel<<<grid, 256, 0, st>>>(dist, idx, n_q, k, indptr);
+    CM_LAUNCH_CHECK("count_valid_kernel");
+  }
+  {
+    // inclusive scan of indptr[1..n_q]; block sums live at the head of `cols` until it is filled
+    const int64_t nb = ceil_div(n_q, kScanBlock);
+    CM_REQUIRE(nb <= n_q * (int64_t)k, "scratch too small");
+    scan_local_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(indptr + 1, n_q, cols);
+    CM_LAUNCH_CHECK("scan_local_kernel");
+    if (nb > 1) {
+      scan_sums_kernel<<<1, kScanBlock, 0, st>>>(cols, nb);
+      CM_LAUNCH_CHECK("scan_sums_kernel");
+      scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(indptr + 1, n_q, cols);
+      CM_LAUNCH_CHECK("scan_add_kernel");
+    }
+  }
+  {
+    size_t smem = (size_t)kRowWarps * np * (sizeof(double) + sizeof(int32_t));
+    CM_CUDA_CHECK(cudaFuncSetAttribute(edge_to_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = ceil_div(n_q, kRowWarps);
+    int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
+    edge_to_csr_kernel<<<grid, kRowWarps * 32, smem, st>>>(dist, idx, n_q, k, np, kernel, stats3, normalize, indptr,
+                                                          cols, vals_f32, vals_f64);
+    CM_LAUNCH_CHECK("edge_to_csr_kernel");
+  }
+  return CM_OK;
+}
+
+extern "C" int cm_csr_row_normalize(const int32_t* indptr, const double* vals_in, int64_t n_rows, float* vals_out,
+                                    int64_t* zero_rows_out, void* stream) {
+  CM_REQUIRE(n_rows >= 0, "bad row count");
+  if (n_rows == 0) return CM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_rows_out) CM_CUDA_CHECK(cudaMemsetAsync(zero_rows_out, 0, sizeof(int64_t), st));
+  int64_t blocks = ceil_div(n_rows, 128);
+  int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  csr_row_normalize_kernel<<<grid, 128, 0, st>>>(indptr, vals_in, n_rows, vals_out,
+                                                reinterpret_cast<unsigned long long*>(zero_rows_out));
+  CM_LAUNCH_CHECK("csr_row_normalize_kernel");
+  return CM_OK;
+}
+
+extern "C" int cm_csr_col_sums(const int32_t* indptr, const int32_t* cols, const double* vals, int64_t n_rows,
+                               double* out, void* stream) {
+  CM_REQUIRE(n_rows >= 0, "bad row count");
+  if (n_rows == 0) return CM_OK;
+  csr_col_sums_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(indptr, cols, vals, n_rows, out);
+  CM_LAUNCH_CHECK("csr_col_sums_kernel");
+  return CM_OK;
+}

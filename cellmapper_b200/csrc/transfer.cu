@@ -1,0 +1,264 @@
+// P3: transfers through the row-normalised mapping matrix M (CSR float32, int32 sorted columns).
+//   vote   : OneHotEncoder + M @ xtab + argmax / max            (cellmapper.py:591-605)
+//   spmm   : M @ dense (obsm, numeric obs, dense layers)        (cellmapper.py:338,373,628)
+//   spgemm : M @ CSR expression matrix                          (cellmapper.py:372-373)
+// All HBM/L2-bound gathers.  Summation order follows scipy's csr_matmat / csr_matvecs: per output
+// element, terms are added in ascending reference index, multiply and add rounded separately.
+#include "common.cuh"
+
+namespace cm {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// label vote: one warp per query row; lane L owns classes c with c % 32 == L
+// ------------------------------------------------------------------------------------------------
+constexpr int kVoteWarps = 4;
+
+__global__ void __launch_bounds__(kVoteWarps * 32)
+vote_argmax_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols, const float* __restrict__ vals,
+                   int64_t n_q, const int32_t* __restrict__ codes, int n_classes, int32_t* __restrict__ out_code,
+                   float* __restrict__ out_conf, float* __restrict__ out_probs) {
+  extern __shared__ float vote_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sums = vote_smem + (size_t)warp * n_classes;
+  for (int64_t row = (int64_t)blockIdx.x * kVoteWarps + warp; row < n_q; row += (int64_t)gridDim.x * kVoteWarps) {
+    for (int c = lane; c < n_classes; c += 32) sums[c] = 0.f;
+    __syncwarp();
+    const int32_t lo = indptr[row], hi = indptr[row + 1];
+    for (int32_t base = lo; base < hi; base += 32) {
+      const int32_t e = base + lane;
+      int cls = -1;
+      float w = 0.f;
+      if (e < hi) {
+        cls = codes[cols[e]];
+        w = vals[e];
+      }
+      const int n_here = min(32, hi - base);
+      for (int t = 0; t < n_here; ++t) {  // ascending column order
+        const int c_t = __shfl_sync(0xffffffffu, cls, t);
+        const float w_t = __shfl_sync(0xffffffffu, w, t);
+        if ((c_t & 31) == lane) sums[c_t] = __fadd_rn(sums[c_t], w_t);  // w * 1.0f == w
+      }
+    }
+    __syncwarp();
+    float best = 0.f;
+    int best_c = INT32_MAX;
+    bool any = false;
+    for (int c = lane; c < n_classes; c += 32) {
+      const float s = sums[c];
+      if (out_probs) out_probs[row * n_classes + c] = s;
+      if (!any || s > best) { best = s; best_c = c; any = true; }
+    }
+    if (!any) { best = -CUDART_INF_F; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+      if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+    }
+    if (lane == 0) {
+      if (hi == lo) { best_c = 0; best = 0.f; }  // empty row: scipy argmax -> 0, max -> 0
+      out_code[row] = best_c;
+      out_conf[row] = best;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-sparse x dense: one thread per output element
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols,
+                            const float* __restrict__ vals, int64_t n_q, const T* __restrict__ B, int64_t ldb, int m,
+                            T* __restrict__ out, int64_t ldo) {
+  const int64_t total = n_q * (int64_t)m;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / m;
+    const int c = (int)(t - row * m);
+    const int32_t lo = indptr[row], hi = indptr[row + 1];
+    T acc = (T)0;
+    for (int32_t e = lo; e < hi; ++e) {
+      const T a = (T)vals[e];
+      const T b = B[(int64_t)cols[e] * ldb + c];
+      if constexpr (sizeof(T) == 4)
+        acc = __fadd_rn(acc, __fmul_rn(a, b));
+      else
+        acc = __dadd_rn(acc, __dmul_rn(a, b));
+    }
+    out[row * ldo + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR x CSR row gather/accumulate: one CTA per query row, dense accumulator + touched-bitmap in smem
+// ------------------------------------------------------------------------------------------------
+constexpr int kSpgemmThreads = 512;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+  // exclusive scan of one int per thread across the block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int ws = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+    int winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (int)(blockDim.x >> 5)) warp_sums[lane] = winc - ws;
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  return warp_sums[warp] + inc - v;
+}
+
+template <bool kFill>
+__global__ void __launch_bounds__(kSpgemmThreads)
+spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_cols, const float* __restrict__ m_vals,
+              int64_t n_q, const int64_t* __restrict__ x_indptr, const int32_t* __restrict__ x_cols,
+              const float* __restrict__ x_vals, int32_t n_genes, int32_t* __restrict__ out_row_nnz,
+              const int64_t* __restrict__ out_indptr, int32_t* __restrict__ out_cols, float* __restrict__ out_vals) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n_words = (n_genes + 31) >> 5;
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw);
+  float* acc = reinterpret_cast<float*>(smem_raw + (size_t)n_words * 4);
+  __shared__ int warp_sums[32];
+  __shared__ int total_sh;
+
+  for (int w = threadIdx.x; w < n_words; w += blockDim.x) bitmap[w] = 0u;
+  if (kFill)
+    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) acc[g] = 0.f;
+  __syncthreads();
+
+  for (int64_t row = blockIdx.x; row < n_q; row += gridDim.x) {
+    const int32_t lo = m_indptr[row], hi = m_indptr[row + 1];
+    for (int32_t e = lo; e < hi; ++e) {  // ascending reference index == scipy's accumulation order
+      const int64_t r = m_cols[e];
+      const int64_t xs = x_indptr[r], xe = x_indptr[r + 1];
+      float w = 0.f;
+      if (kFill) w = m_vals[e];
+      for (int64_t p = xs + threadIdx.x; p < xe; p += blockDim.x) {
+        const int32_t g = x_cols[p];
+        atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+        if (kFill) acc[g] = __fadd_rn(acc[g], __fmul_rn(w, x_vals[p]));  // columns are unique inside one X row
+      }
+      if (kFill) __syncthreads();  // next neighbour may touch the same genes from other threads
+    }
+    __syncthreads();
+    // emit in ascending gene order: rank of every set bit by a block-wide scan over bitmap words
+    int base_rank = 0;
+    for (int w0 = 0; w0 < n_words; w0 += blockDim.x) {
+      const int w = w0 + threadIdx.x;
+      const uint32_t bits = w < n_words ? bitmap[w] : 0u;
+      const int pc = __popc(bits);
+      int total;
+      const int ex = block_exclusive_scan(pc, warp_sums, &total_sh);
+      total = total_sh;
+      if (kFill && bits) {
+        int64_t o = out_indptr[row] + base_rank + ex;
+        uint32_t b = bits;
+        while (b) {
+          const int bit = __ffs(b) - 1;
+          b &= b - 1;
+          const int g = (w << 5) + bit;
+          out_cols[o] = g;
+          out_vals[o] = acc[g];
+          acc[g] = 0.f;
+          ++o;
+        }
+      }
+      if (w < n_words) bitmap[w] = 0u;
+      base_rank += total;
+      __syncthreads();
+    }
+    if (!kFill && threadIdx.x == 0) out_row_nnz[row] = base_rank;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace cm
+
+using namespace cm;
+
+extern "C" int cm_vote_argmax(const int32_t* indptr, const int32_t* cols, const float* vals, int64_t n_q,
+                              const int32_t* codes, int n_classes, int32_t* out_code, float* out_conf,
+                              float* out_probs, void* stream) {
+  CM_REQUIRE(n_q >= 0 && n_classes >= 1, "bad vote arguments");
+  CM_REQUIRE(n_classes <= 12288, "n_classes = %d too large (max 12288)", n_classes);
+  if (n_q == 0) return CM_OK;
+  size_t smem = (size_t)kVoteWarps * n_classes * sizeof(float);
+  CM_CUDA_CHECK(cudaFuncSetAttribute(vote_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = ceil_div(n_q, kVoteWarps);
+  int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  vote_argmax_kernel<<<grid, kVoteWarps * 32, smem, (cudaStream_t)stream>>>(indptr, cols, vals, n_q, codes, n_classes,
+                                                                           out_code, out_conf, out_probs);
+  CM_LAUNCH_CHECK("vote_argmax_kernel");
+  return CM_OK;
+}
+
+extern "C" int cm_spmm_csr_dense(const int32_t* indptr, const int32_t* cols, const float* vals, int64_t n_q,
+                                 const void* B, int64_t ldb, int m, int dtype, void* out, int64_t ldo, void* stream) {
+  CM_REQUIRE(n_q >= 0 && m >= 1 && ldb >= m && ldo >= m, "bad spmm arguments");
+  CM_REQUIRE(dtype == CM_F32 || dtype == CM_F64, "bad dtype code %d", dtype);
+  if (n_q == 0) return CM_OK;
+  int64_t blocks = ceil_div(n_q * (int64_t)m, 256);
+  int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  if (dtype == CM_F32)
+    spmm_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, cols, vals, n_q, (const float*)B, ldb, m,
+                                                              (float*)out, ldo);
+  else
+    spmm_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(indptr, cols, vals, n_q, (const double*)B, ldb, m,
+                                                               (double*)out, ldo);
+  CM_LAUNCH_CHECK("spmm_kernel");
+  return CM_OK;
+}
+
+static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
+                         const int64_t* x_indptr, const int32_t* x_cols, const float* x_vals, int32_t n_genes,
+                         int32_t* out_row_nnz, const int64_t* out_indptr, int32_t* out_cols, float* out_vals,
+                         cudaStream_t st) {
+  CM_REQUIRE(n_q >= 0 && n_genes >= 1 && n_genes <= CM_SPGEMM_MAX_COLS, "n_genes = %d outside 1..%d", n_genes,
+             CM_SPGEMM_MAX_COLS);
+  if (n_q == 0) return CM_OK;
+  const int n_words = (n_genes + 31) >> 5;
+  size_t smem = (size_t)n_words * 4 + (fill ? (size_t)n_genes * 4 : 0);
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int64_t want = (int64_t)kNumSMs * per_sm;
+  int grid = (int)(n_q < want ? n_q : want);
+  if (fill) {
+    CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spgemm_kernel<true><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals,
+                                                           n_genes, out_row_nnz, out_indptr, out_cols, out_vals);
+  } else {
+    CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spgemm_kernel<false><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals,
+                                                            n_genes, out_row_nnz, out_indptr, out_cols, out_vals);
+  }
+  CM_LAUNCH_CHECK("spgemm_kernel");
+  return CM_OK;
+}
+
+extern "C" int cm_spgemm_count(const int32_t* m_indptr, const int32_t* m_cols, int64_t n_q, const int64_t* x_indptr,
+                               const int32_t* x_cols, int32_t n_genes, int32_t* out_row_nnz, void* stream) {
+  return spgemm_launch(false, m_indptr, m_cols, nullptr, n_q, x_indptr, x_cols, nullptr, n_genes, out_row_nnz, nullptr,
+                       nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cm_spgemm_fill(const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
+                              const int64_t* x_indptr, const int32_t* x_cols, const float* x_vals, int32_t n_genes,
+                              const int64_t* out_indptr, int32_t* out_cols, float* out_vals, void* stream) {
+  return spgemm_launch(true, m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, n_genes, nullptr, out_indptr,
+                       out_cols, out_vals, (cudaStream_t)stream);
+}

@@ -1,0 +1,121 @@
+"""Multi-GPU decomposition of the mapping path: one process per GPU,
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) for the few exchange steps the path has.
+
+* query-sharded (default): every rank holds the whole reference, owns a contiguous block of query
+  rows and runs search -> kernel -> transfers on it.  The only coupling is the kernel bandwidth,
+  ONE statistic over all edges (knn.py:196,206): an all-reduce of 3 float64 per pass.
+* reference-sharded (reference does not fit / presence score over a 10M-cell atlas): every rank
+  searches its block of the reference for ALL queries, the per-rank top-k lists are all-gathered
+  and merged (``cm_knn_merge_topk``).
+
+The compute callables are injected so that the collective plumbing can be exercised on CPU with
+world_size 2 over gloo.
+"""
+
+from __future__ import annotations
+
+import os
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+__all__ = [
+    "init_from_env",
+    "world",
+    "shard_bounds",
+    "allreduce_sum",
+    "reference_sharded_search",
+    "gather_rows",
+]
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun).
+    Returns (rank, world_size, local_rank). A single process without those variables is world 1."""
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world_size, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world_size)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    return rank, world_size, local_rank
+
+
+def world() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous balanced blocks: the first ``n % world`` ranks get one extra row."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum(t: torch.Tensor) -> None:
+    """In-place SUM over ranks (no-op for a single process).  Used for the bandwidth statistics."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def reference_sharded_search(
+    q: torch.Tensor,
+    r_local: torch.Tensor,
+    r_offset: int,
+    k: int,
+    search: Callable[[torch.Tensor, torch.Tensor, int, int], tuple[torch.Tensor, torch.Tensor]],
+    merge: Callable[[torch.Tensor, torch.Tensor, int], tuple[torch.Tensor, torch.Tensor]],
+):
+    """Top-k of every query over a reference that is sharded by rows across ranks.
+
+    ``search(q, r_local, k_local, r_offset)`` -> (dist (n_q,k_local) f64, idx (n_q,k_local) i64 with
+    GLOBAL indices); ``merge(cand_dist (L,n_q,k), cand_idx, k)`` -> merged (dist, idx).
+    Exchange: one all-gather of n_q*k*(8+8) bytes per rank.
+    """
+    rank, ws = world()
+    k_local = min(k, r_local.shape[0])
+    d, i = search(q, r_local, k_local, r_offset)
+    if k_local < k:  # a shard smaller than k: pad with (+inf, -1)
+        pad = k - k_local
+        d = torch.cat([d, torch.full((d.shape[0], pad), float("inf"), dtype=d.dtype, device=d.device)], 1)
+        i = torch.cat([i, torch.full((i.shape[0], pad), -1, dtype=i.dtype, device=i.device)], 1)
+    d = d.contiguous()
+    i = i.contiguous()
+    if ws == 1:
+        return merge(d[None], i[None], k)
+    n_q = d.shape[0]
+    all_d = torch.empty((ws * n_q, k), dtype=d.dtype, device=d.device)  # rank-major concatenation
+    all_i = torch.empty((ws * n_q, k), dtype=i.dtype, device=i.device)
+    dist.all_gather_into_tensor(all_d, d)
+    dist.all_gather_into_tensor(all_i, i)
+    return merge(all_d.view(ws, n_q, k), all_i.view(ws, n_q, k), k)
+
+
+def gather_rows(t: torch.Tensor, counts: list[int] | None = None) -> torch.Tensor | None:
+    """Concatenate row blocks of all ranks on every rank (blocks may differ in length by one)."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(ws)]
+    dist.all_gather(sizes, n_local)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    padded = t
+    if t.shape[0] < m:
+        padded = torch.cat([t, torch.zeros((m - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)])
+    out = [torch.empty_like(padded) for _ in range(ws)]
+    dist.all_gather(out, padded.contiguous())
+    return torch.cat([o[:s] for o, s in zip(out, sizes)])

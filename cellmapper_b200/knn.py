@@ -1,0 +1,321 @@
+"""Host-side mirror of the reference's k-NN layer (``src/cellmapper/model/knn.py``) for method="b200".
+
+Same class and method names, argument meaning and error behaviour as the reference so that the
+parity tests read like the reference's own tests; the arithmetic runs in libcellmapper_b200 (CUDA,
+sm_100a).  Results live on the device and are materialised as numpy / scipy objects lazily, only
+when the host-visible attribute is read.
+"""
+
+from __future__ import annotations
+
+from typing import Literal
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix, issparse
+
+from . import _lib, device
+from .logging import logger
+
+__all__ = ["NeighborsResults", "Neighbors", "sklearn_like_dist_mode"]
+
+
+def _current_device() -> torch.device:
+    _lib.require_device(torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(a, dtype=None) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        t = a if a.is_cuda else a.to(_current_device(), non_blocking=True)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(_current_device(), non_blocking=True)
+    return t if dtype is None or t.dtype == dtype else t.to(dtype)
+
+
+def sklearn_like_dist_mode(dtype, n_features: int, n_neighbors: int, n_samples_fit: int) -> int:
+    """Rounding of the returned distance that reproduces the reference's sklearn path bit for bit:
+    brute force (d > 15 or k >= n_fit // 2, ``sklearn/neighbors/_base.py:615-648``) on float32 input
+    goes through float32 (``sqrtf((float)d2)``), everything else is ``sqrt`` in float64."""
+    brute = n_features > 15 or n_neighbors >= n_samples_fit // 2
+    return _lib.DIST_SKLEARN_F32 if (brute and np.dtype(dtype) == np.float32) else _lib.DIST_SQRT_F64
+
+
+class NeighborsResults:
+    """Nearest-neighbour result store: ``distances`` / ``indices`` of shape (n_samples, n_neighbors)
+    and the graph builders on top of them (reference: knn.py:14-266).  Accepts numpy arrays or CUDA
+    tensors; padding entries are ``index == -1`` / ``distance == inf`` (knn.py:68-77)."""
+
+    def __init__(self, distances, indices, n_targets: int | None = None):
+        if tuple(indices.shape) != tuple(distances.shape):
+            raise ValueError("Indices and distances must have the same shape.")  # knn.py:46-47
+        self._dist_host = self._idx_host = None
+        self._dist_dev = self._idx_dev = None
+        if isinstance(distances, torch.Tensor):
+            self._dist_dev = distances
+        else:
+            self._dist_host = np.asarray(distances)
+        if isinstance(indices, torch.Tensor):
+            self._idx_dev = indices
+        else:
+            self._idx_host = np.asarray(indices)
+        self._shape2 = tuple(int(s) for s in indices.shape)
+        self.n_targets = int(n_targets) if n_targets is not None else self._shape2[0]  # knn.py:49-51
+        self._cache: dict = {}
+
+    # -- host views (lazy device -> host) ------------------------------------------------------
+    @property
+    def distances(self) -> np.ndarray:
+        if self._dist_host is None:
+            self._dist_host = self._dist_dev.cpu().numpy()
+        return self._dist_host
+
+    @property
+    def indices(self) -> np.ndarray:
+        if self._idx_host is None:
+            self._idx_host = self._idx_dev.cpu().numpy()
+        return self._idx_host
+
+    # -- device views --------------------------------------------------------------------------
+    @property
+    def distances_device(self) -> torch.Tensor:
+        if self._dist_dev is None:
+            self._dist_dev = _to_device(self._dist_host, torch.float64)
+        return self._dist_dev
+
+    @property
+    def indices_device(self) -> torch.Tensor:
+        if self._idx_dev is None:
+            self._idx_dev = _to_device(self._idx_host, torch.int64)
+        return self._idx_dev
+
+    @property
+    def n_samples(self) -> int:
+        return self._shape2[0]
+
+    @property
+    def n_neighbors(self) -> int:
+        return self._shape2[1]
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return (self.n_samples, self.n_targets or self.n_samples)
+
+    def _get_valid_entries_mask(self) -> np.ndarray:
+        return (self.indices != -1) & np.isfinite(self.distances)  # knn.py:77
+
+    # -- graphs --------------------------------------------------------------------------------
+    def _csr_from_device(self, indptr, cols, vals, dtype) -> csr_matrix:
+        ip = indptr.cpu().numpy()
+        nnz = int(ip[-1])
+        m = csr_matrix(
+            (vals[:nnz].cpu().numpy().astype(dtype, copy=False), cols[:nnz].cpu().numpy(), ip), shape=self.shape
+        )
+        m.has_sorted_indices = True
+        return m
+
+    def connectivities_device(self, kernel: str = "gaussian", normalize: bool = False, allreduce=None):
+        """Device CSR (indptr, cols, vals) of the kernel graph; float64 raw weights, or the
+        row-normalised float32 mapping matrix when ``normalize``."""
+        d, i = self.distances_device, self.indices_device
+        stats = device.edge_stats(d, i, allreduce=allreduce)
+        if float(stats[2].item()) == 0.0:
+            raise ValueError("No finite distances found in the neighborhood graph")  # knn.py:191-192
+        if kernel == "random":  # knn.py:211-213 -- unseeded, for testing purposes only
+            indptr, cols, vals = device.edge_kernel_to_csr(d, i, "equal", stats, normalize=False)
+            vals = vals * torch.rand_like(vals)
+            if normalize:
+                vals, _ = device.csr_row_normalize(indptr, vals)
+            return indptr, cols, vals
+        return device.edge_kernel_to_csr(d, i, kernel, stats, normalize=normalize)
+
+    @property
+    def knn_graph_distances(self) -> csr_matrix:
+        """Sparse matrix of distances (knn.py:113-132)."""
+        if "dist_graph" not in self._cache:
+            mask = self._get_valid_entries_mask()
+            n, k = self._shape2
+            rows = np.repeat(np.arange(n), k)[mask.ravel()]
+            self._cache["dist_graph"] = csr_matrix(
+                (self.distances.ravel()[mask.ravel()].astype(np.float64), (rows, self.indices.ravel()[mask.ravel()])),
+                shape=self.shape,
+            )
+        return self._cache["dist_graph"]
+
+    def knn_graph_connectivities(
+        self,
+        kernel: Literal["gaussian", "scarches", "random", "inverse_distance", "equal"] = "gaussian",
+        dtype=np.float64,
+        **kwargs,
+    ) -> csr_matrix:
+        """Connectivities with the given kernel as scipy CSR (knn.py:134-164), computed on the device."""
+        if kernel not in ("gaussian", "scarches", "random", "inverse_distance", "equal"):
+            raise ValueError(
+                f"Unknown kernel: {kernel}. Supported kernels are: 'gaussian', 'scarches', 'random', 'inverse_distance', 'equal'."
+            )
+        if kwargs.get("epsilon", 1e-8) != 1e-8:
+            raise NotImplementedError("only the default epsilon=1e-8 is supported by the b200 kernel")
+        indptr, cols, vals = self.connectivities_device(kernel, normalize=False)
+        return self._csr_from_device(indptr, cols, vals, dtype)
+
+    def boolean_adjacency(self, dtype=np.float64, set_diag: bool | None = None) -> csr_matrix:
+        """0/1 adjacency from the neighbour indices (knn.py:228-266); container glue, host side."""
+        idx = self.indices
+        mask = idx != -1
+        n, k = self._shape2
+        rows = np.repeat(np.arange(n), k)[mask.ravel()]
+        adj = csr_matrix((np.ones(rows.shape[0], dtype=dtype), (rows, idx.ravel()[mask.ravel()])), shape=self.shape)
+        if set_diag is not None:
+            if self.shape[0] != self.shape[1]:
+                raise ValueError(
+                    "The set_diag parameter can only be used with square matrices "
+                    f"(got shape {self.shape[0]} x {self.shape[1]})."
+                )
+            adj.setdiag(1.0 if set_diag else 0.0)
+        return adj
+
+
+def extract_neighbors_from_distances(distances_matrix, include_self: bool | None = None):
+    """Neighbour lists from a sparse distance matrix (reference: utils.py:129-219), vectorised.
+
+    Ragged rows are padded with index -1 / distance +inf; rows are sorted by distance when they are
+    not already.  Returns (indices int64, distances float64)."""
+    if not issparse(distances_matrix):
+        raise TypeError("Distances matrix must be a sparse matrix")
+    if distances_matrix.shape[0] != distances_matrix.shape[1]:
+        raise ValueError(f"Square distance matrix required (got {distances_matrix.shape})")
+    dm = distances_matrix.tocsr()
+    n = dm.shape[0]
+    indptr = dm.indptr.astype(np.int64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    cols = dm.indices.astype(np.int64)
+    data = dm.data.astype(np.float64)
+    is_self = cols == rows
+    if include_self is False:
+        keep = ~is_self
+        rows, cols, data = rows[keep], cols[keep], data[keep]
+    elif include_self is True:
+        has_self = np.zeros(n, dtype=bool)
+        has_self[rows[is_self]] = True
+        add = np.flatnonzero(~has_self)
+        # the reference appends self with distance 0 at the END of the row (utils.py:197-199)
+        pos = np.concatenate([np.arange(rows.shape[0], dtype=np.float64), indptr[add + 1] - 0.5])
+        order = np.argsort(pos, kind="stable")
+        rows = np.concatenate([rows, add])[order]
+        cols = np.concatenate([cols, add])[order]
+        data = np.concatenate([data, np.zeros(add.shape[0])])[order]
+    counts = np.bincount(rows, minlength=n)
+    starts = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=starts[1:])
+    # rows that are not already ascending get a (non-stable, like np.argsort default) distance sort
+    pos_in_row = np.arange(rows.shape[0]) - starts[rows]
+    desc = np.zeros(n, dtype=bool)
+    if rows.shape[0] > 1:
+        same = rows[1:] == rows[:-1]
+        bad = same & (data[1:] < data[:-1])
+        desc[rows[1:][bad]] = True
+    if desc.any():
+        for i in np.flatnonzero(desc):
+            s, e = starts[i], starts[i + 1]
+            o = np.argsort(data[s:e])
+            cols[s:e] = cols[s:e][o]
+            data[s:e] = data[s:e][o]
+    width = int(counts.max()) if n else 0
+    indices = np.full((n, width), -1, dtype=np.int64)
+    distances = np.full((n, width), np.inf, dtype=np.float64)
+    indices[rows, pos_in_row] = cols
+    distances[rows, pos_in_row] = data
+    return indices, distances
+
+
+class Neighbors:
+    """Compute and store nearest neighbours (reference: knn.py:269-492) with the B200 back-end."""
+
+    def __init__(self, xrep, yrep=None):
+        self.xrep = xrep
+        self.yrep = yrep if yrep is not None else xrep
+        self.xx: NeighborsResults | None = None
+        self.yy: NeighborsResults | None = None
+        self.xy: NeighborsResults | None = None
+        self.yx: NeighborsResults | None = None
+        self._is_self_mapping = yrep is None
+        self.search_stats: dict = {}
+
+    @classmethod
+    def from_distances(cls, distances_matrix, include_self: bool | None = None) -> "Neighbors":
+        """reference: knn.py:296-337."""
+        indices, distances = extract_neighbors_from_distances(distances_matrix, include_self=include_self)
+        n_cells = distances_matrix.shape[0]
+        neighbors = cls(xrep=np.zeros((n_cells, 1)))
+        result = NeighborsResults(distances=distances, indices=indices)
+        neighbors.xx = neighbors.yy = neighbors.xy = neighbors.yx = result
+        neighbors._is_self_mapping = True
+        logger.info("Created Neighbors object from distances matrix with %d cells", n_cells)
+        return neighbors
+
+    def compute_neighbors(
+        self,
+        n_neighbors: int = 30,
+        method: Literal["b200"] = "b200",
+        metric: str = "euclidean",
+        random_state: int = 0,
+        only_yx: bool = False,
+        algo: int = _lib.KNN_AUTO,
+    ):
+        """Exact k-NN on the GPU.  Mirrors knn.py:339-465: ``only_yx`` computes the single
+        query->reference search, otherwise xx, yy, xy, yx.  Distances are Euclidean (not squared),
+        float64; indices int64; rows ascending."""
+        if method != "b200":
+            raise ValueError(
+                f"Unknown method: {method}. This package implements method='b200' only; "
+                "use quadbio/cellmapper for 'sklearn', 'pynndescent', 'rapids' and 'faiss'."
+            )
+        if metric != "euclidean":
+            raise ValueError(f"method='b200' supports metric='euclidean' only (got {metric!r}).")
+        logger.info("Using %s to compute %d neighbors.", method, n_neighbors)
+        x = _to_device(self.xrep)
+        y = x if self.yrep is self.xrep else _to_device(self.yrep)
+        np_dtype = np.result_type(
+            np.float32 if x.dtype == torch.float32 else np.float64, np.float32 if y.dtype == torch.float32 else np.float64
+        )
+
+        def search(q, r):
+            mode = sklearn_like_dist_mode(np_dtype, r.shape[1], n_neighbors, r.shape[0])
+            d, i, st = device.knn_search(q, r, n_neighbors, dist_mode=mode, algo=algo, return_stats=True)
+            return d, i, st
+
+        d, i, st = search(y, x)
+        self.search_stats["yx"] = st
+        yx = NeighborsResults(d, i, n_targets=x.shape[0])
+        if only_yx:
+            self.yx = yx
+            return
+        d, i, st = search(x, x)
+        self.search_stats["xx"] = st
+        self.xx = NeighborsResults(d, i, n_targets=None)
+        d, i, st = search(y, y)
+        self.search_stats["yy"] = st
+        self.yy = NeighborsResults(d, i, n_targets=None)
+        d, i, st = search(x, y)
+        self.search_stats["xy"] = st
+        self.xy = NeighborsResults(d, i, n_targets=y.shape[0])
+        self.yx = yx
+
+    def get_adjacency_matrices(self):
+        """reference: knn.py:467-483."""
+        if self.xx is None or self.yy is None or self.xy is None or self.yx is None:
+            raise ValueError("Neighbors must be computed before accessing adjacency matrices.")
+        return (
+            self.xx.boolean_adjacency(),
+            self.yy.boolean_adjacency(),
+            self.xy.boolean_adjacency(),
+            self.yx.boolean_adjacency(),
+        )
+
+    def __repr__(self):
+        return (
+            f"Neighbors(xrep_shape={tuple(self.xrep.shape)}, yrep_shape={tuple(self.yrep.shape)}, "
+            f"xx={self.xx is not None}, yy={self.yy is not None}, "
+            f"xy={self.xy is not None}, yx={self.yx is not None}, "
+            f"self_mapping={self._is_self_mapping})"
+        )

@@ -1,0 +1,166 @@
+/*
+ * cellmapper_b200.h -- C ABI of the B200-native k-NN mapping path (libcellmapper_b200.so).
+ *
+ * The reference (quadbio/cellmapper) is pure Python and has no FFI of its own: on this path it
+ * calls scikit-learn / numpy / scipy.  Each entry point below therefore replaces one *library call
+ * site* of the reference; the citation next to it is the reference line a maintainer would swap.
+ * INTEGRATION.md shows the ctypes stub for each.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (torch CUDA tensors on the host
+ *     side) unless the name ends in _host; sizes are element counts; row-major; no ownership moves;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     the host unless stated;
+ *   - return value: 0 = ok, non-zero = error (CM_ERR_*); cm_last_error() returns a message for the
+ *     last failing call of the calling thread;
+ *   - no torch, no C++ types in any signature.
+ */
+#ifndef CELLMAPPER_B200_H
+#define CELLMAPPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_ABI_VERSION 1
+
+enum cm_status {
+  CM_OK = 0,
+  CM_ERR_ARG = 1,      /* bad argument (shape, dtype code, k > n_r, ...) */
+  CM_ERR_CUDA = 2,     /* a CUDA runtime call failed */
+  CM_ERR_DEVICE = 3,   /* device is not sm_100 (B200) */
+  CM_ERR_WORKSPACE = 4 /* workspace too small */
+};
+
+enum cm_dtype { CM_F32 = 0, CM_F64 = 1 };
+
+/* graph kernels of NeighborsResults._compute_kernel_values (knn.py:166-226) */
+enum cm_kernel { CM_KERNEL_GAUSSIAN = 0, CM_KERNEL_SCARCHES = 1, CM_KERNEL_INVERSE_DISTANCE = 2, CM_KERNEL_EQUAL = 3 };
+
+/* how the float64 squared distance becomes the returned distance (oracle behaviour) */
+enum cm_dist_mode {
+  CM_DIST_SQRT_F64 = 0,    /* sqrt(d2) in float64: sklearn KD-tree path / float64 input        */
+  CM_DIST_SKLEARN_F32 = 1, /* (double)sqrtf((float)d2): sklearn brute force on float32 input    */
+  CM_DIST_SQUARED = 2      /* d2 itself: what the reference's faiss branch returns (knn.py:416) */
+};
+
+/* search algorithm selector for cm_knn_search */
+enum cm_knn_algo {
+  CM_KNN_AUTO = 0,     /* tcgen05 split-fp16 GEMM + exact re-rank, exact f64 fallback per row    */
+  CM_KNN_EXACT_F64 = 1 /* SIMT float64 brute force only (ground truth / fallback kernel)         */
+};
+
+int cm_abi_version(void);
+const char* cm_last_error(void);
+/* 0 if `device` is a compute-capability 10.x GPU this library was built for, CM_ERR_DEVICE otherwise */
+int cm_device_check(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * P1  exact Euclidean k-NN.
+ * Replaces: sklearn.neighbors.NearestNeighbors(k).fit(R).kneighbors(Q)   (knn.py:428-440)
+ *           and the faiss / cuML branches                                  (knn.py:379-426)
+ * Q (n_q, d) and R (n_r, d): row-major with leading dimensions ldq / ldr (elements), dtype cm_dtype.
+ * out_dist (n_q, k) float64, out_idx (n_q, k) int64, rows ascending by (distance, index).
+ * r_index_offset is added to every emitted index (reference-sharded search).
+ * stats_out (device, 4 x int64, may be NULL): [0] rows re-done by the exact fallback,
+ *   [1] rows whose certificate failed even there (duplicate-distance ties; result still valid
+ *   under the tie rule), [2] candidates examined by the re-rank, [3] reserved.
+ * ------------------------------------------------------------------------------------------- */
+size_t cm_knn_workspace_bytes(int64_t n_q, int64_t n_r, int d, int k, int algo);
+int cm_knn_search(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d, int dtype,
+                  int k, int64_t r_index_offset, int dist_mode, int algo, double* out_dist, int64_t* out_idx,
+                  void* workspace, size_t workspace_bytes, int64_t* stats_out, void* stream);
+
+/* merge n_lists per-shard candidate lists (each (n_q, k), ascending) into the global top-k.
+ * Replaces nothing in the reference (it has no sharded search); used after the NCCL all-gather. */
+int cm_knn_merge_topk(const double* cand_dist, const int64_t* cand_idx, int n_lists, int64_t n_q, int k,
+                      double* out_dist, int64_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * P2  graph kernel -> CSR -> row-normalised float32 mapping matrix.
+ * ------------------------------------------------------------------------------------------- */
+/* Statistics over valid edges (idx != -1 and finite d) -- the inputs of np.mean / np.std at
+ * knn.py:196,206.  out3 (3 float64, device): [0] sum d, [1] sum (d - m)^2, [2] count, where
+ * m = *mean_in (device) or 0 when mean_in is NULL.  Deterministic (fixed reduction tree).  The host
+ * calls it once for (sum, count), all-reduces across GPUs, then again with the global mean for the
+ * centred second moment that np.std computes (two-pass, like numpy). */
+int cm_edge_stats(const double* dist, const int64_t* idx, int64_t n_edges, const double* mean_in, double* out3,
+                  void* workspace, size_t workspace_bytes, void* stream);
+#define CM_EDGE_STATS_WORKSPACE_BYTES 32768
+
+/* Edge list (n_q, k) -> CSR with columns sorted inside each row.
+ * Replaces: _compute_kernel_values + _create_sparse_matrix (knn.py:79-111,166-226) and, when
+ * `normalize` != 0, CellMapper._validate_and_normalize_mapping_matrix (cellmapper.py:99-137):
+ *   w = kernel(d) in float64, row sum in float64 in ascending-column order, w * (1/rowsum), round
+ *   to float32.  stats3 = the (all-reduced) output of cm_edge_stats (device pointer).
+ * indptr (n_q+1) int32, cols (n_q*k) int32, vals_f32 (n_q*k) float32 [normalize] or vals_f64
+ * (n_q*k) float64 [raw connectivities, e.g. for the presence score]; pass NULL for the unused one.
+ * Invalid edges are dropped, so rows may be shorter than k (ragged / precomputed graphs). */
+int cm_edge_kernel_to_csr(const double* dist, const int64_t* idx, int64_t n_q, int k, int kernel, const double* stats3,
+                          int normalize, int32_t* indptr, int32_t* cols, float* vals_f32, double* vals_f64,
+                          void* stream);
+/* stats3 layout: the reduced [sum d, sum (d-mean)^2, count] of cm_edge_stats. */
+
+/* Row-normalise an arbitrary CSR (user-supplied mapping matrix / jaccard counts), float64 in,
+ * float32 out: cellmapper.py:126-135. zero_rows_out (device int64, may be NULL) counts zero rows. */
+int cm_csr_row_normalize(const int32_t* indptr, const double* vals_in, int64_t n_rows, float* vals_out,
+                         int64_t* zero_rows_out, void* stream);
+
+/* column sums of a float64 CSR: presence score, evaluate.py:457 (`conn.sum(axis=0)`). out (n_cols)
+ * float64 must be zeroed by the caller (it is accumulated into, so shards can share it). */
+int cm_csr_col_sums(const int32_t* indptr, const int32_t* cols, const double* vals, int64_t n_rows, double* out,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * P3  transfers through the mapping matrix M (CSR float32, int32 indices, sorted columns).
+ * ------------------------------------------------------------------------------------------- */
+/* categorical obs: replaces OneHotEncoder + `M @ xtab` + argmax/max (cellmapper.py:591-605).
+ * codes (n_r) int32 class of each reference cell in *sorted-category* order; per query the class
+ * sums are accumulated in float32 in ascending column order; ties -> lowest class.
+ * out_probs (n_q, n_classes) float32 may be NULL. */
+int cm_vote_argmax(const int32_t* indptr, const int32_t* cols, const float* vals, int64_t n_q, const int32_t* codes,
+                   int n_classes, int32_t* out_code, float* out_conf, float* out_probs, void* stream);
+
+/* dense right-hand side: `M @ reference.obsm[key]`, `M @ values.reshape(-1,1)`, `M @ dense layer`
+ * (cellmapper.py:338,373,628).  B (n_r, m) row-major ldb, dtype cm_dtype; out (n_q, m) same dtype. */
+int cm_spmm_csr_dense(const int32_t* indptr, const int32_t* cols, const float* vals, int64_t n_q, const void* B,
+                      int64_t ldb, int m, int dtype, void* out, int64_t ldo, void* stream);
+
+/* sparse right-hand side: `M @ reference.X` with CSR X (cellmapper.py:372-373), two passes.
+ * count: out_row_nnz (n_q) int32 = structural nnz of each output row (union of the gathered rows'
+ *        columns; values that sum to exactly 0 are kept as explicit zeros).
+ * fill : out_indptr (n_q+1) int64 is the exclusive scan of out_row_nnz (caller computes it);
+ *        writes sorted columns + float32 values.  n_genes <= CM_SPGEMM_MAX_COLS. */
+#define CM_SPGEMM_MAX_COLS 49152
+int cm_spgemm_count(const int32_t* m_indptr, const int32_t* m_cols, int64_t n_q, const int64_t* x_indptr,
+                    const int32_t* x_cols, int32_t n_genes, int32_t* out_row_nnz, void* stream);
+int cm_spgemm_fill(const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
+                   const int64_t* x_indptr, const int32_t* x_cols, const float* x_vals, int32_t n_genes,
+                   const int64_t* out_indptr, int32_t* out_cols, float* out_vals, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * measurement hooks (bench.py)
+ * ------------------------------------------------------------------------------------------- */
+/* number of kernels this library has launched in the calling process so far */
+int64_t cm_launch_count(void);
+/* when enabled, cm_knn_search brackets its phases with CUDA events on the caller's stream */
+int cm_profile_enable(int on);
+/* HOST pointer out4: milliseconds of [rowstats+prep, mma_topk, rerank, exact fallback] of the last
+ * profiled cm_knn_search of the calling thread; synchronises on those events. */
+int cm_profile_last_knn_ms(float* out4_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * debug / self-test hooks (used by tests/ only)
+ * ------------------------------------------------------------------------------------------- */
+/* one 128 x 128 tile of the split-fp16 tcgen05 product: out[i*128+j] = ||r_j||^2 - 2 q_i.r_j in the
+ * kernel's scaled units, scale_out (1 float) = the power-of-two scale. Needs n_q,n_r <= 128. */
+int cm_debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
+                      float* scale_out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLMAPPER_B200_H */

@@ -1,0 +1,423 @@
+"""Parity of the CUDA path against the oracle / golden vectors.  All tests need a B200 (`-m gpu`)
+and call through the C ABI (cellmapper_b200.device -> libcellmapper_b200.so)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from conftest import assert_csr_equal, golden_csr, load_golden, neighbours_match
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["gaussian", "scarches", "inverse_distance", "equal"]
+Q2R = ["q2r_d30", "q2r_d10_kdtree", "q2r_d50"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    from cellmapper_b200 import _lib
+
+    _lib.require_device(0)
+    return torch
+
+
+def dev(torch, a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def scipy_from_device(indptr, cols, vals, shape):
+    from scipy.sparse import csr_matrix
+
+    ip = indptr.cpu().numpy()
+    nnz = int(ip[-1])
+    return csr_matrix((vals[:nnz].cpu().numpy(), cols[:nnz].cpu().numpy(), ip), shape=shape)
+
+
+def ulp_diff_f32(a, b):
+    ai = np.asarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    bi = np.asarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+# --------------------------------------------------------------------------------------------
+# P1 search
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,n_q,n_r", [(30, 200, 300), (50, 128, 128), (8, 77, 500), (52, 130, 257)])
+def test_tensor_core_products_match_float64(torch_cuda, d, n_q, n_r):
+    """Raw tcgen05 split-fp16 accumulators against the float64 value of ||r'||^2 - 2 q'.r'."""
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    rng = np.random.default_rng(d)
+    q = (rng.standard_normal((n_q, d)) * 3 + 1).astype(np.float32)
+    r = (rng.standard_normal((n_r, d)) * 3 + 1).astype(np.float32)
+    out, scale = device.debug_mma_tile(dev(torch, q), dev(torch, r))
+    out = out.cpu().numpy().astype(np.float64)[:n_q, :n_r]
+    s = float(scale.item())
+    amax = max(np.abs(q).max(), np.abs(r).max())
+    assert 32 <= amax * s < 64 and np.log2(s) == np.round(np.log2(s))
+    q64, r64 = q.astype(np.float64) * s, r.astype(np.float64) * s
+    want = (r64 * r64).sum(1)[None, :] - 2.0 * q64 @ r64.T
+    bound = 2.0**-18 * ((q64 * q64).sum(1)[:, None] + (r64 * r64).sum(1)[None, :])
+    err = np.abs(out - want)
+    assert (err <= bound).all(), f"max err/bound = {(err / bound).max():.3f}, max err = {err.max():.3e}"
+
+
+@pytest.mark.parametrize("name", Q2R)
+@pytest.mark.parametrize("algo", ["exact", "auto"])
+def test_search_matches_reference_golden(torch_cuda, name, algo):
+    torch = torch_cuda
+    from cellmapper_b200 import _lib, device
+    from cellmapper_b200.knn import sklearn_like_dist_mode
+
+    g = load_golden(name)
+    xr, xq, k = g["xr"], g["xq"], int(g["k"])
+    mode = sklearn_like_dist_mode(xr.dtype, xr.shape[1], k, xr.shape[0])
+    d, i, st = device.knn_search(
+        dev(torch, xq), dev(torch, xr), k, dist_mode=mode,
+        algo=_lib.KNN_EXACT_F64 if algo == "exact" else _lib.KNN_AUTO, return_stats=True,
+    )  # fmt: skip
+    d, i = d.cpu().numpy(), i.cpu().numpy()
+    assert d.dtype == np.float64 and i.dtype == np.int64
+    assert neighbours_match(i, d, g["indices"], g["distances"]) == 0
+    same = i == g["indices"]
+    assert same.mean() > 0.999
+    if mode == _lib.DIST_SKLEARN_F32:
+        np.testing.assert_array_equal(d[same], g["distances"][same])  # bit-exact incl. sklearn's float32 rounding
+    else:
+        np.testing.assert_allclose(d[same], g["distances"][same], rtol=1e-14)
+    assert (np.diff(d, axis=1) >= 0).all()
+
+
+@pytest.mark.parametrize("n_q,n_r,d,k", [(5000, 5000, 30, 30), (3000, 20000, 50, 30), (1000, 4000, 16, 5), (513, 1000, 50, 40)])
+def test_search_matches_sklearn_live(torch_cuda, n_q, n_r, d, k):
+    """BASELINE config 1 (5k x 5k x 30) and friends against sklearn run on the box's CPU."""
+    torch = torch_cuda
+    from cellmapper_b200 import device, synth
+    from cellmapper_b200.knn import sklearn_like_dist_mode
+    from oracle import cellmapper_oracle as orc
+
+    centres = synth.mixture_centres(8, d)
+    xr, _ = synth.mixture_embedding(n_r, centres, seed=1)
+    xq, _ = synth.mixture_embedding(n_q, centres, seed=2)
+    ref_d, ref_i = orc.search_sklearn(xr, xq, k)
+    mode = sklearn_like_dist_mode(xr.dtype, d, k, n_r)
+    dd, ii, st = device.knn_search(dev(torch, xq), dev(torch, xr), k, dist_mode=mode, return_stats=True)
+    dd, ii, st = dd.cpu().numpy(), ii.cpu().numpy(), st.cpu().numpy()
+    assert neighbours_match(ii, dd, ref_i, ref_d) == 0
+    same = ii == ref_i
+    assert same.mean() > 0.9999
+    np.testing.assert_array_equal(dd[same], ref_d[same])
+    assert st[0] <= 0.01 * n_q, f"{st[0]} of {n_q} rows needed the exact fallback"
+
+
+def test_search_float64_input_and_self_mapping(torch_cuda):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+    from oracle import cellmapper_oracle as orc
+
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((1500, 20))
+    ref_d, ref_i = orc.search_sklearn(x, x, 10)
+    dd, ii = device.knn_search(dev(torch, x), dev(torch, x), 10)
+    dd, ii = dd.cpu().numpy(), ii.cpu().numpy()
+    assert neighbours_match(ii, dd, ref_i, ref_d) == 0
+    assert (ii[:, 0] == np.arange(1500)).all() and (dd[:, 0] == 0).all()
+    np.testing.assert_allclose(dd[:, 1:], ref_d[:, 1:], rtol=1e-9)
+
+
+def test_search_duplicates_and_ties(torch_cuda):
+    """Many exactly-equal distances: results must still be a valid exact answer (tie rule)."""
+    torch = torch_cuda
+    from cellmapper_b200 import device
+    from oracle import cellmapper_oracle as orc
+
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((50, 24)).astype(np.float32)
+    xr = np.repeat(base, 40, axis=0)  # every point 40 times
+    xq = base[:20] + 0.01
+    dd, ii = device.knn_search(dev(torch, xq), dev(torch, xr), 30)
+    dd, ii = dd.cpu().numpy(), ii.cpu().numpy()
+    ref_d, _ = orc.bruteforce_knn_f64(xr, xq, 30)
+    np.testing.assert_allclose(dd, ref_d, rtol=1e-12)
+    for row in range(20):
+        assert len(set(ii[row].tolist())) == 30
+        np.testing.assert_allclose(np.sqrt(((xr[ii[row]].astype(np.float64) - xq[row]) ** 2).sum(1)), dd[row], rtol=1e-12)
+
+
+def test_search_errors(torch_cuda):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    x = dev(torch, np.zeros((10, 4), dtype=np.float32))
+    with pytest.raises(ValueError, match="n_neighbors <= n_samples_fit"):
+        device.knn_search(x, x, 11)
+
+
+def test_merge_topk(torch_cuda):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    rng = np.random.default_rng(0)
+    xr = rng.standard_normal((4000, 32)).astype(np.float32)
+    xq = rng.standard_normal((300, 32)).astype(np.float32)
+    full_d, full_i = device.knn_search(dev(torch, xq), dev(torch, xr), 30)
+    parts_d, parts_i = [], []
+    bounds = [0, 900, 2100, 2101, 4000]
+    for s, e in zip(bounds[:-1], bounds[1:]):
+        kk = min(30, e - s)
+        d_, i_ = device.knn_search(dev(torch, xq), dev(torch, xr[s:e]), kk, r_index_offset=s)
+        if kk < 30:
+            d_ = torch.cat([d_, torch.full((300, 30 - kk), float("inf"), dtype=d_.dtype, device=d_.device)], 1)
+            i_ = torch.cat([i_, torch.full((300, 30 - kk), -1, dtype=i_.dtype, device=i_.device)], 1)
+        parts_d.append(d_)
+        parts_i.append(i_)
+    md, mi = device.knn_merge_topk(torch.stack(parts_d), torch.stack(parts_i), 30)
+    assert torch.equal(mi, full_i) and torch.equal(md, full_d)
+
+
+# --------------------------------------------------------------------------------------------
+# P2 graph kernel
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", Q2R)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_mapping_matrix_from_reference_distances(torch_cuda, name, kernel):
+    """Given the reference's own (distances, indices), the float32 mapping matrix must match to 1 ulp
+    (exp / summation-order differences; structure must be identical)."""
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    g = load_golden(name)
+    n_r = g["xr"].shape[0]
+    ip, cols, vals = device.edge_kernel_to_csr(dev(torch, g["distances"]), dev(torch, g["indices"]), kernel, normalize=True)
+    m = scipy_from_device(ip, cols, vals, (g["distances"].shape[0], n_r))
+    ref = golden_csr(g, f"mm_{kernel}")
+    np.testing.assert_array_equal(m.indptr, ref.indptr)
+    np.testing.assert_array_equal(m.indices, ref.indices)
+    assert m.data.dtype == np.float32 and m.indices.dtype == np.int32
+    ulps = ulp_diff_f32(m.data, ref.data)
+    assert ulps.max() <= 1, f"max ulp diff {ulps.max()}"
+    assert (ulps > 0).mean() < 1e-3
+
+
+def test_raw_connectivities_and_presence(torch_cuda):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    g = load_golden("q2r_d30")
+    n_r = g["xr"].shape[0]
+    ip, cols, vals = device.edge_kernel_to_csr(dev(torch, g["distances"]), dev(torch, g["indices"]), "gaussian", normalize=False)
+    m = scipy_from_device(ip, cols, vals, (g["distances"].shape[0], n_r))
+    ref = golden_csr(g, "conn_gaussian")
+    assert_csr_equal(m, ref, rtol=1e-14)
+    colsum = device.csr_col_sums(ip, cols, vals, n_r).cpu().numpy()
+    np.testing.assert_allclose(colsum, np.asarray(ref.sum(axis=0)).ravel(), rtol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["none", "true", "false"])
+def test_ragged_graph(torch_cuda, tag):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    g = load_golden("ragged_selfmap")
+    idx, dist = g[f"indices_{tag}"], g[f"distances_{tag}"]
+    ip, cols, vals = device.edge_kernel_to_csr(dev(torch, dist), dev(torch, idx), "gaussian", normalize=True)
+    m = scipy_from_device(ip, cols, vals, (idx.shape[0], idx.shape[0]))
+    ref = golden_csr(g, f"mm_{tag}")
+    np.testing.assert_array_equal(m.indptr, ref.indptr)
+    np.testing.assert_array_equal(m.indices, ref.indices)
+    assert ulp_diff_f32(m.data, ref.data).max() <= 1
+
+
+def test_edge_stats(torch_cuda):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    rng = np.random.default_rng(1)
+    d = rng.random((5000, 30)) * 10
+    i = rng.integers(0, 1000, (5000, 30))
+    d[::7, -3:] = np.inf
+    i[::7, -3:] = -1
+    st = device.edge_stats(dev(torch, d), dev(torch, i)).cpu().numpy()
+    ok = np.isfinite(d) & (i != -1)
+    np.testing.assert_allclose(st[0], d[ok].sum(), rtol=1e-14)
+    np.testing.assert_allclose(st[1] / st[2], np.var(d[ok]), rtol=1e-12)
+    assert st[2] == ok.sum()
+
+
+# --------------------------------------------------------------------------------------------
+# P3 transfers
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", Q2R)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_transfers_from_reference_matrix(torch_cuda, name, kernel):
+    """Given the reference's mapping matrix: labels bit-exact, conf / obsm / numeric / imputed values
+    bit-exact (same float32 summation order as scipy)."""
+    torch = torch_cuda
+    from cellmapper_b200 import device
+    from oracle import cellmapper_oracle as orc
+
+    g = load_golden(name)
+    m = golden_csr(g, f"mm_{kernel}")
+    ip, cols, vals = dev(torch, m.indptr, torch.int32), dev(torch, m.indices, torch.int32), dev(torch, m.data, torch.float32)
+    cats, codes = orc.onehot_sorted(g["labels"])
+    code, conf, probs = device.vote_argmax(ip, cols, vals, dev(torch, codes), len(cats), return_probs=True)
+    np.testing.assert_array_equal(cats[code.cpu().numpy()].astype(str), g[f"pred_{kernel}"])
+    np.testing.assert_array_equal(conf.cpu().numpy(), g[f"conf_{kernel}"])
+    np.testing.assert_array_equal(probs.cpu().numpy().max(1), g[f"conf_{kernel}"])
+    np.testing.assert_array_equal(device.spmm(ip, cols, vals, dev(torch, g["umap"])).cpu().numpy(), g[f"umap_{kernel}"])
+    np.testing.assert_array_equal(
+        device.spmm(ip, cols, vals, dev(torch, g["umap"].astype(np.float64))).cpu().numpy(), g[f"umap64_{kernel}"]
+    )
+    np.testing.assert_array_equal(device.spmm(ip, cols, vals, dev(torch, g["score"])).cpu().numpy(), g[f"score_{kernel}"])
+    np.testing.assert_array_equal(
+        device.spmm(ip, cols, vals, dev(torch, (g["score"] * 100).astype(np.int64))).cpu().numpy(), g[f"count_{kernel}"]
+    )
+    expr = golden_csr(g, "expr")
+    oip, ocols, ovals = device.spgemm(ip, cols, vals, dev(torch, expr.indptr), dev(torch, expr.indices), dev(torch, expr.data), expr.shape[1])
+    from scipy.sparse import csr_matrix
+
+    out = csr_matrix((ovals.cpu().numpy(), ocols.cpu().numpy(), oip.cpu().numpy()), shape=(m.shape[0], expr.shape[1]))
+    assert out.has_sorted_indices
+    ref = golden_csr(g, f"imputed_{kernel}")
+    out.eliminate_zeros()
+    ref.eliminate_zeros()
+    assert_csr_equal(out, ref)
+    if kernel == "gaussian":
+        dense = device.spmm(ip, cols, vals, dev(torch, np.asarray(expr.todense()))).cpu().numpy()
+        np.testing.assert_array_equal(dense, g["imputed_dense"])
+
+
+# --------------------------------------------------------------------------------------------
+# the drop-in surface end to end
+# --------------------------------------------------------------------------------------------
+def make_adatas(g, with_layers=True):
+    import pandas as pd
+    from scipy.sparse import csr_matrix
+
+    from cellmapper_b200._anndata import AnnData
+
+    n_r, n_q = g["xr"].shape[0], g["xq"].shape[0]
+    expr = golden_csr(g, "expr").astype(np.float32)
+    ref = AnnData(
+        X=expr,
+        obs=pd.DataFrame(
+            {
+                "celltype": pd.Categorical(g["labels"]),
+                "score": g["score"],
+                "score64": g["score"].astype(np.float64),
+                "count": (g["score"] * 100).astype(np.int64),
+            },
+            index=[f"r{i}" for i in range(n_r)],
+        ),
+        obsm={"X_joint": g["xr"], "X_umap": g["umap"], "X_umap64": g["umap"].astype(np.float64)},
+        layers={"dense": np.asarray(expr.todense())} if with_layers else {},
+        uns={"celltype_colors": [f"#{i:06x}" for i in range(len(np.unique(g["labels"])))]},
+    )
+    qry = AnnData(X=csr_matrix((n_q, 5), dtype=np.float32), obs=pd.DataFrame(index=[f"q{i}" for i in range(n_q)]), obsm={"X_joint": g["xq"]})
+    return qry, ref
+
+
+@pytest.mark.parametrize("name", Q2R)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cellmapper_map_matches_reference(torch_cuda, name, kernel):
+    from cellmapper_b200 import CellMapper
+
+    g = load_golden(name)
+    qry, ref = make_adatas(g)
+    cm = CellMapper(qry, ref).map(
+        use_rep="X_joint",
+        obs_keys=["celltype", "score", "score64", "count"],
+        obsm_keys=["X_umap", "X_umap64"],
+        layer_key="X",
+        n_neighbors=int(g["k"]),
+        only_yx=True,
+        mapping_method=kernel,
+    )
+    assert cm.knn.xx is None and cm.knn.yx is not None
+    assert neighbours_match(cm.knn.yx.indices, cm.knn.yx.distances, g["indices"], g["distances"]) == 0
+    mm = cm.mapping_matrix
+    refmm = golden_csr(g, f"mm_{kernel}")
+    assert mm.dtype == np.float32 and mm.shape == refmm.shape
+    if np.array_equal(cm.knn.yx.indices, g["indices"]):
+        np.testing.assert_array_equal(mm.indices, refmm.indices)
+        rt = 1e-3 if kernel == "inverse_distance" else 1e-6
+        np.testing.assert_allclose(mm.data, refmm.data, rtol=rt)
+        # transferred labels: bit-exact given equal neighbours
+        np.testing.assert_array_equal(qry.obs["celltype_pred"].to_numpy().astype(str), g[f"pred_{kernel}"])
+        np.testing.assert_allclose(qry.obs["celltype_conf"].to_numpy(), g[f"conf_{kernel}"], rtol=1e-5)
+        np.testing.assert_allclose(qry.obs["score_pred"].to_numpy(), g[f"score_{kernel}"], rtol=1e-5)
+        np.testing.assert_allclose(qry.obs["score64_pred"].to_numpy(), g[f"score64_{kernel}"], rtol=1e-5)
+        np.testing.assert_allclose(qry.obsm["X_umap_pred"], g[f"umap_{kernel}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(qry.obsm["X_umap64_pred"], g[f"umap64_{kernel}"], rtol=1e-5, atol=1e-6)
+        imp = cm.query_imputed.X
+        assert_csr_equal(imp, golden_csr(g, f"imputed_{kernel}"), rtol=1e-5, atol=1e-7, structure=False)
+    assert str(qry.obs["celltype_pred"].dtype) == "category"
+    assert qry.obs["celltype_conf"].dtype == np.float32
+    assert qry.obs["score_pred"].dtype == np.float32 and qry.obs["score64_pred"].dtype == np.float64
+    assert qry.obs["count_pred"].dtype == np.float64
+    assert qry.obsm["X_umap_pred"].dtype == np.float32 and qry.obsm["X_umap64_pred"].dtype == np.float64
+    assert "celltype_pred_colors" in qry.uns
+    np.testing.assert_allclose(np.asarray(mm.sum(1)).ravel(), 1.0, atol=1e-6)
+    cm.estimate_presence_score()
+    if kernel == "gaussian" and np.array_equal(cm.knn.yx.indices, g["indices"]):
+        np.testing.assert_allclose(ref.obs["presence_score"].to_numpy(), g["presence_score"], atol=1e-9)
+
+
+def test_cellmapper_errors_mirror_reference(torch_cuda):
+    from cellmapper_b200 import CellMapper
+
+    g = load_golden("q2r_d30")
+    qry, ref = make_adatas(g, with_layers=False)
+    cm = CellMapper(qry, ref)
+    with pytest.raises(ValueError, match="Neighbors have not been computed"):
+        cm.compute_mapping_matrix()
+    with pytest.raises(ValueError, match="Mapping matrix has not been computed"):
+        cm.map_obs("celltype")
+    cm.compute_neighbors(use_rep="X_joint", only_yx=True)
+    with pytest.raises(ValueError, match="Set only_yx=False"):
+        cm.compute_mapping_matrix("jaccard")
+    with pytest.raises(NotImplementedError):
+        cm.compute_mapping_matrix("nope")
+    cm.compute_mapping_matrix("gaussian")
+    with pytest.raises(KeyError):
+        cm.map_obs("missing")
+    with pytest.raises(ValueError, match="Unknown method"):
+        cm.compute_neighbors(use_rep="X_joint", method="sklearn")
+    from scipy.sparse import identity
+
+    with pytest.raises(ValueError, match="shape mismatch"):
+        cm.mapping_matrix = identity(3, format="csr")
+    # user-supplied matrix is re-normalised on the device (cellmapper.py:83-137)
+    user = (golden_csr(g, "mm_gaussian") * 3.0).tocoo()
+    cm.mapping_matrix = user
+    assert_csr_equal(cm.mapping_matrix, golden_csr(g, "mm_gaussian"), rtol=1e-6, structure=False)
+
+
+@pytest.mark.parametrize("tag,include_self", [("none", None), ("true", True), ("false", False)])
+def test_precomputed_ragged_selfmapping(torch_cuda, tag, include_self):
+    import pandas as pd
+    from scipy.sparse import csr_matrix
+
+    from cellmapper_b200 import CellMapper
+    from cellmapper_b200._anndata import AnnData
+
+    g = load_golden("ragged_selfmap")
+    graph = golden_csr(g, "graph")
+    n = graph.shape[0]
+    ad = AnnData(
+        X=csr_matrix((n, 3), dtype=np.float32),
+        obs=pd.DataFrame({"celltype": pd.Categorical(g["labels"])}, index=[f"c{i}" for i in range(n)]),
+        obsp={"distances": graph},
+    )
+    cm = CellMapper(ad)
+    cm.load_precomputed_distances("distances", include_self=include_self)
+    np.testing.assert_array_equal(cm.knn.yx.indices, g[f"indices_{tag}"])
+    np.testing.assert_array_equal(cm.knn.yx.distances, g[f"distances_{tag}"])
+    cm.compute_mapping_matrix("gaussian")
+    cm.map_obs("celltype")
+    np.testing.assert_array_equal(ad.obs["celltype_pred"].to_numpy().astype(str), g[f"pred_{tag}"])
+    np.testing.assert_allclose(ad.obs["celltype_conf"].to_numpy(), g[f"conf_{tag}"], rtol=1e-6)
