@@ -23,7 +23,13 @@ int launch_knn_exact(const void* Q, int64_t n_q, int64_t ldq, const void* R, int
 
 // tensor-core path limits
 constexpr int kMmaTile = 128;    // rows per operand tile (UMMA M and N)
-constexpr int kMmaMaxKp = 160;   // padded split-K columns: ceil((3d+3)/16)*16 <= 160  ->  d <= 52
+// Operand images (see knn_mma.cu): a segment holds the d embedding columns plus the 3 norm columns,
+// rounded up to 8-column chunks.  Query image: 3 segments (-2hi | -2hi | -2lo), reference image: 2
+// segments (hi+norms | lo); the third product (lo_q x hi_r) re-reads the reference's hi segment.
+constexpr int kMmaMaxSegChunks = 7;  // ceil((d+3)/8) <= 7  ->  d <= 53
+static inline int mma_seg_chunks(int d) { return (d + 3 + 7) / 8; }
+static inline int mma_kp_q(int d) { return 8 * ((3 * mma_seg_chunks(d) + 1) / 2 * 2); }  // even chunk count
+static inline int mma_kp_r(int d) { return 8 * 2 * mma_seg_chunks(d); }
 constexpr int kMmaMaxK = 40;     // neighbours supported by the candidate buffers
 constexpr int kCandCap = 96;     // per-row candidate slots in shared memory
 constexpr int kKeepLo = 44;      // after compaction a row keeps between kKeepLo ..
@@ -31,7 +37,6 @@ constexpr int kKeepHi = 60;      // .. and kKeepHi candidates
 constexpr int kCandOut = kKeepHi;
 constexpr int kMaxSplits = 8;
 
-static inline int mma_kp(int d) { return (int)((3 * d + 3 + 15) / 16 * 16); }
-static inline bool mma_supported(int d, int k) { return mma_kp(d) <= kMmaMaxKp && k <= kMmaMaxK; }
+static inline bool mma_supported(int d, int k) { return mma_seg_chunks(d) <= kMmaMaxSegChunks && k <= kMmaMaxK; }
 
 }  // namespace cm

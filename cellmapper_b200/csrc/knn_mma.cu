@@ -7,12 +7,14 @@
 //   prep       : scale by a power of two so max|x| in [32,64), split every value into fp16 hi + lo and
 //                write "operand images" -- the exact byte layout tcgen05.mma reads from shared
 //                memory (K-major, no swizzle, 8x16-byte core matrices) -- so a tile is ONE contiguous
-//                cp.async.bulk.  Columns: Q' = [-2hi | -2hi | -2lo | c c c], R' = [hi | lo | hi | n1 n2 n3]
-//                with c*(n1+n2+n3) = ||r'||^2, hence  Q'.R'^T = ||r'||^2 - 2 q'.r'  (rank-equivalent
-//                to the squared distance) with ~2^-22 relative accuracy from three fp16 products.
+//                cp.async.bulk.  Columns: Q' = [-2hi,c c c | -2hi | -2lo], R' = [hi,n1 n2 n3 | lo]; the
+//                K-steps of the third query segment re-read the reference's hi segment, so
+//                Q'.R'^T = c(n1+n2+n3) - 2(hi.hi + hi.lo + lo.hi) = ||r'||^2 - 2 q'.r'  (rank-equivalent
+//                to the squared distance) with ~2^-22 relative accuracy from three fp16 products,
+//                while the streamed reference tile carries only 2 of the 3 segments.
 //   mma_topk   : one CTA per (128-query tile, reference split).  Warp 0 streams reference tiles with
 //                bulk-async copies into a shared-memory ring, warp 1 issues tcgen05.mma (128x128xK')
-//                into double-buffered TMEM accumulators, warps 2-5 drain TMEM (tcgen05.ld, one query
+//                into four TMEM accumulator buffers, warps 2-5 drain TMEM (tcgen05.ld, one query
 //                row per thread) and keep a per-row threshold + candidate buffer in shared memory.
 //                The n_q x n_r distance matrix never exists.
 //   rerank     : per query, exact float64 direct-difference distances of the <= 60*splits candidates,
@@ -182,10 +184,13 @@ constexpr float kNormColumn = 256.f;  // the constant c in the three norm column
 
 // One thread per (row, 8-column chunk): one 16-byte store into the operand image.
 // image byte offset of (row, col) = (row/8) * (kp*16) + (col/8) * 128 + (row%8) * 16 + (col%8) * 2
+// Column meaning (dc = chunks per segment, cs = column inside the segment):
+//   query     seg0: -2*hi(x) for cs<d, c for d<=cs<d+3     seg1: -2*hi(x)     seg2: -2*lo(x)
+//   reference seg0:    hi(x) for cs<d, n1 n2 n3 at d..d+2   seg1:    lo(x)
 template <typename T>
-__global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int64_t n_pad, int d, int kp,
+__global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int64_t n_pad, int d, int kp, int dc,
                             const double* __restrict__ norms, const ScaleInfo* __restrict__ info, int is_query,
-                            uint4* __restrict__ img) {
+                            uint64_t perm_mul, uint4* __restrict__ img) {
   const int chunks = kp >> 3;
   const float scale = scale_from_absmax(info->absmax_bits);
   const int64_t total = n_pad * chunks;
@@ -194,35 +199,40 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
     const int64_t group = t / (8 * chunks);
     const int rem = (int)(t - group * 8 * chunks);
     const int chunk = rem >> 3, r8 = rem & 7;
-    const int64_t row = group * 8 + r8;
+    const int64_t pos = group * 8 + r8;
+    // image position -> source row: identity for queries, golden-ratio scramble for the reference
+    const int64_t row = perm_mul ? (int64_t)((perm_mul * (uint64_t)pos) % (uint64_t)n_pad) : pos;
+    const int seg = chunk / dc;
+    const int n_seg = is_query ? 3 : 2;
     __half h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int col = chunk * 8 + e;
+      const int cs = (chunk - seg * dc) * 8 + e;
       float out = 0.f;
-      if (row < n) {
-        if (col < 3 * d) {
-          const int seg = col / d, j = col - seg * d;
-          const float xs = (float)((double)X[row * ld + j] * (double)scale);
-          const __half hi = __float2half_rn(xs);
-          const float lo = xs - __half2float(hi);
-          if (is_query)
-            out = seg == 2 ? -2.f * __half2float(__float2half_rn(lo)) : -2.f * __half2float(hi);
-          else
-            out = seg == 1 ? __half2float(__float2half_rn(lo)) : __half2float(hi);
-        } else if (col < 3 * d + 3) {
-          if (is_query) {
-            out = kNormColumn;
-          } else {
-            const double nn = norms[row] * (double)scale * (double)scale / (double)kNormColumn;
-            const float n1 = __half2float(__float2half_rn((float)nn));
-            const float n2 = __half2float(__float2half_rn((float)(nn - (double)n1)));
-            const float n3 = __half2float(__float2half_rn((float)(nn - (double)n1 - (double)n2)));
-            out = col == 3 * d ? n1 : (col == 3 * d + 1 ? n2 : n3);
+      if (seg < n_seg) {
+        if (row < n) {
+          if (cs < d) {
+            const float xs = (float)((double)X[row * ld + cs] * (double)scale);
+            const __half hi = __float2half_rn(xs);
+            const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
+            if (is_query)
+              out = seg == 2 ? -2.f * lo : -2.f * __half2float(hi);
+            else
+              out = seg == 1 ? lo : __half2float(hi);
+          } else if (seg == 0 && cs < d + 3) {
+            if (is_query) {
+              out = kNormColumn;
+            } else {
+              const double nn = norms[row] * (double)scale * (double)scale / (double)kNormColumn;
+              const float n1 = __half2float(__float2half_rn((float)nn));
+              const float n2 = __half2float(__float2half_rn((float)(nn - (double)n1)));
+              const float n3 = __half2float(__float2half_rn((float)(nn - (double)n1 - (double)n2)));
+              out = cs == d ? n1 : (cs == d + 1 ? n2 : n3);
+            }
           }
+        } else if (!is_query && seg == 0 && cs == d) {
+          out = 65504.f;  // padded reference rows: "infinitely far"
         }
-      } else if (!is_query && col == 3 * d) {
-        out = 65504.f;  // padded reference rows: "infinitely far"
       }
       h[e] = __float2half_rn(out);
     }
@@ -237,52 +247,76 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
 
 // ------------------------------------------------------------------------------------------------
 // per-row candidate buffer in shared memory (one query row per epilogue thread)
-// layout inside a warp's region: keys[e][lane], idx[e][lane]  -> conflict-free 32-bit accesses
+// layout inside a warp's region: keys[e][lane], idx[e][lane] (4-byte cells) -> conflict-free.
+// All accesses go through explicit ld/st.shared on 32-bit shared addresses.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+constexpr uint32_t kCandStride = 32 * 4;  // bytes between consecutive entries of one row
+
 struct RowCand {
-  uint32_t* keys;  // ordered-uint image of the fp32 accumulator value
-  uint32_t* idx;   // reference row (local to the launch)
+  uint32_t keys;     // shared address of this row's key column (ordered-uint image of the fp32 value)
+  uint32_t idx;      // shared address of this row's index column
   int cnt;
   uint32_t thr_key;  // every element seen so far with key < thr_key is in the buffer
-  float thr;         // same threshold as a float (ordered_to_float(thr_key)); +inf at start
+  float thr;         // the same threshold as a float; +inf at start
 };
 
-__device__ __forceinline__ int count_below(const RowCand& rc, uint32_t piv) {
+// keys are stored as raw fp32 bit patterns (cheapest for the append path) and mapped to their
+// order-preserving uint image when the cold compaction code reads them
+__device__ __forceinline__ uint32_t lds_key(uint32_t addr) { return float_to_ordered(__uint_as_float(lds_u32(addr))); }
+
+__device__ __forceinline__ int count_below(uint32_t keys, int cnt, uint32_t piv) {
   int c = 0;
-  for (int e = 0; e < rc.cnt; ++e) c += (rc.keys[e * 32] < piv) ? 1 : 0;
+  int e = 0;
+  for (; e + 8 <= cnt; e += 8) {  // 8 independent loads in flight: one warp per scheduler, so ILP matters
+    uint32_t k0 = lds_key(keys + (e + 0) * kCandStride), k1 = lds_key(keys + (e + 1) * kCandStride);
+    uint32_t k2 = lds_key(keys + (e + 2) * kCandStride), k3 = lds_key(keys + (e + 3) * kCandStride);
+    uint32_t k4 = lds_key(keys + (e + 4) * kCandStride), k5 = lds_key(keys + (e + 5) * kCandStride);
+    uint32_t k6 = lds_key(keys + (e + 6) * kCandStride), k7 = lds_key(keys + (e + 7) * kCandStride);
+    c += (k0 < piv) + (k1 < piv) + (k2 < piv) + (k3 < piv) + (k4 < piv) + (k5 < piv) + (k6 < piv) + (k7 < piv);
+  }
+  for (; e < cnt; ++e) c += lds_key(keys + e * kCandStride) < piv;
   return c;
 }
 
-// Shrink the buffer to kKeepLo..kKeepHi entries and tighten the threshold.  Selection, not sorting:
-// bisection on the ordered-uint key until the count below the pivot lands in the window; ties that
-// straddle the window are cut arbitrarily and the threshold is set to the tied value (the row then
-// keeps fewer than kKeepLo strictly-below entries and, if it matters, fails its certificate later).
-__device__ __noinline__ void compact_row(RowCand& rc) {
-  if (rc.cnt <= kKeepHi) return;
+// Shrink the buffer to between keep_lo and keep_hi entries and tighten the threshold.  Selection,
+// not sorting: bisection on the ordered-uint key until the count below the pivot lands in the
+// window.  Ties that straddle the window are cut arbitrarily and the threshold is set to the tied
+// value (the row then keeps fewer strictly-below entries and, if it matters, fails its certificate).
+// Cold code, deliberately NOT inlined: the hot epilogue loop has to stay inside the instruction cache.
+// Returns (new count) | (new threshold key << 32).
+__device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint32_t idx, int cnt, uint32_t thr_key,
+                                                            int keep_lo, int keep_hi) {
+  if (cnt <= keep_hi) return (unsigned long long)(uint32_t)cnt | ((unsigned long long)thr_key << 32);
   uint32_t lo = 0xFFFFFFFFu, mx = 0u;
-  for (int e = 0; e < rc.cnt; ++e) {
-    const uint32_t kx = rc.keys[e * 32];
+  for (int e = 0; e < cnt; ++e) {
+    const uint32_t kx = lds_key(keys + e * kCandStride);
     lo = min(lo, kx);
     mx = max(mx, kx);
   }
-  // invariants: count(key < lo) < kKeepLo ; count(key < hi) > kKeepHi
-  uint32_t tl;
-  int c_tl;
+  // invariants of the bisection: count(key < lo) < keep_lo ; count(key < hi) > keep_hi
+  uint32_t tl = mx;
   bool tie = false;
-  int c = count_below(rc, mx);
-  if (c <= kKeepHi) {
-    tl = mx;
-    c_tl = c;
-    tie = c < kKeepLo;  // more than cnt - kKeepLo entries share the maximum
+  int c = count_below(keys, cnt, mx);
+  int c_tl = c;
+  if (c <= keep_hi) {
+    tie = c < keep_lo;  // more than cnt - keep_lo entries share the maximum
   } else {
     uint32_t hi = mx;
     bool found = false;
     while (hi - lo > 1u) {
       const uint32_t piv = lo + ((hi - lo) >> 1);
-      c = count_below(rc, piv);
-      if (c < kKeepLo) {
+      c = count_below(keys, cnt, piv);
+      if (c < keep_lo) {
         lo = piv;
-      } else if (c > kKeepHi) {
+      } else if (c > keep_hi) {
         hi = piv;
       } else {
         tl = piv;
@@ -293,42 +327,64 @@ __device__ __noinline__ void compact_row(RowCand& rc) {
     }
     if (!found) {  // keys equal to `lo` straddle the window
       tl = lo;
-      c_tl = count_below(rc, lo);
+      c_tl = count_below(keys, cnt, lo);
       tie = true;
     }
   }
-  int extra = tie ? kKeepHi - c_tl : 0;
+  int extra = tie ? keep_hi - c_tl : 0;
   int w = 0;
-  for (int e = 0; e < rc.cnt; ++e) {
-    const uint32_t kx = rc.keys[e * 32];
-    const uint32_t ix = rc.idx[e * 32];
+  for (int e = 0; e < cnt; ++e) {
+    const uint32_t raw = lds_u32(keys + e * kCandStride);
+    const uint32_t kx = float_to_ordered(__uint_as_float(raw));
+    const uint32_t ix = lds_u32(idx + e * kCandStride);
     bool keep = kx < tl;
     if (!keep && tie && kx == tl && extra > 0) {
       keep = true;
       --extra;
     }
     if (keep) {
-      rc.keys[w * 32] = kx;
-      rc.idx[w * 32] = ix;
+      sts_u32(keys + w * kCandStride, raw);
+      sts_u32(idx + w * kCandStride, ix);
       ++w;
     }
   }
-  rc.cnt = w;
-  rc.thr_key = tl;
-  rc.thr = ordered_to_float(tl);
+  return (unsigned long long)(uint32_t)w | ((unsigned long long)tl << 32);
+}
+
+__device__ __forceinline__ void compact_row(RowCand& rc, int keep_lo, int keep_hi) {
+  const unsigned long long r = compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, keep_lo, keep_hi);
+  rc.cnt = (int)(uint32_t)r;
+  rc.thr_key = (uint32_t)(r >> 32);
+  rc.thr = rc.thr_key == 0xFFFFFFFFu ? CUDART_INF_F : ordered_to_float(rc.thr_key);
+}
+
+// Adaptive keep window.  The reference rows are visited in a scrambled (golden-ratio stride) order,
+// so after a fraction f of a split has been seen the number of true top-k members among the seen
+// elements is Binomial(k, f).  Keeping k*f + 4.5 sigma + 8 candidates therefore loses a true
+// neighbour with probability ~1e-5 per row (caught by the certificate), while the threshold is as
+// tight as it can be from the very first tiles -- far fewer candidates pass than with a fixed window.
+__device__ __forceinline__ void keep_window(int k, float f, int& keep_lo, int& keep_hi) {
+  const float kf = (float)k * f;
+  int lo = (int)ceilf(kf + 4.5f * sqrtf(fmaxf(kf * (1.f - f), 0.f)) + 8.f);
+  int hi = min(lo + 14, kCandOut);
+  lo = min(lo, hi - 4);
+  keep_lo = lo;
+  keep_hi = hi;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the tensor-core kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kMmaThreads = 192;  // warp 0 producer, warp 1 MMA + TMEM owner, warps 2..5 epilogue
-constexpr int kTmemCols = 256;    // 2 accumulator buffers x 128 fp32 columns
+constexpr int kAccBufs = 4;       // TMEM accumulator buffers: the MMA warp runs up to 3 tiles ahead
+constexpr int kTmemCols = kAccBufs * kMmaTile;  // 512 fp32 columns = all of TMEM
 constexpr int kMaxStages = 4;
+constexpr int kLoadPieces = 4;    // bulk copies per reference tile (independent requests overlap their latency)
 
 struct MmaParams {
-  const unsigned char* q_img;  // n_q_tiles tiles of 128 x kp fp16
-  const unsigned char* r_img;  // n_r_tiles tiles
-  int n_q_tiles, n_r_tiles, splits, kp, stages;
+  const unsigned char* q_img;  // n_q_tiles tiles of 128 x kp_q fp16
+  const unsigned char* r_img;  // n_r_tiles tiles of 128 x kp_r fp16
+  int n_q_tiles, n_r_tiles, splits, kp_q, kp_r, dc, stages, k;
   float* cand_s;      // [n_q_pad][splits][kCandOut]
   int32_t* cand_i;    // same
   int32_t* cand_cnt;  // [n_q_pad][splits]
@@ -336,9 +392,44 @@ struct MmaParams {
   float* debug_out;   // optional raw accumulator dump [n_q_pad][n_r_tiles*128]
 };
 
+// One 32-column chunk of one query row: minimum by a depth-4 tree of 3-input mins; if anything in
+// the warp is below its row's threshold, every passing value is appended with predicated stores
+// (no branches: the code must be small and its cost independent of divergence).
+__device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], uint32_t c0, RowCand& rc, int trigger,
+                                              int keep_lo, int keep_hi) {
+  float t[11];
+#pragma unroll
+  for (int g = 0; g < 10; ++g)
+    t[g] = fminf(fminf(__uint_as_float(v[3 * g]), __uint_as_float(v[3 * g + 1])), __uint_as_float(v[3 * g + 2]));
+  t[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+  const float u0 = fminf(fminf(t[0], t[1]), t[2]), u1 = fminf(fminf(t[3], t[4]), t[5]);
+  const float u2 = fminf(fminf(t[6], t[7]), t[8]), u3 = fminf(t[9], t[10]);
+  const float m = fminf(fminf(fminf(u0, u1), u2), u3);
+  const float thr = rc.thr;
+  if (__any_sync(0xffffffffu, m < thr)) {
+    uint32_t w = rc.keys + (uint32_t)rc.cnt * kCandStride;
+    const uint32_t idx_off = rc.idx - rc.keys;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const bool pass = __uint_as_float(v[e]) < thr;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.u32 p, %4, 0;\n\t"
+          "@p st.shared.u32 [%0], %1;\n\t"
+          "@p st.shared.u32 [%2], %3;\n\t}"
+          ::"r"(w), "r"(v[e]), "r"(w + idx_off), "r"(c0 + e), "r"((uint32_t)pass)
+          : "memory");
+      w += pass ? kCandStride : 0u;
+    }
+    rc.cnt = (int)((w - rc.keys) / kCandStride);
+    if (__any_sync(0xffffffffu, rc.cnt > trigger)) compact_row(rc, keep_lo, keep_hi);
+  }
+}
+
+template <bool kDebug>
 __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[1 + 2 * kMaxStages + 4];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * kMaxStages + 2 * kAccBufs];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -348,17 +439,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   const int t_end = min(p.n_r_tiles, t_begin + tiles_per_split);
   const int n_tiles = max(0, t_end - t_begin);
 
-  const uint32_t tile_bytes = (uint32_t)kMmaTile * p.kp * 2;
+  const uint32_t a_bytes = (uint32_t)kMmaTile * p.kp_q * 2;
+  const uint32_t b_bytes = (uint32_t)kMmaTile * p.kp_r * 2;
   unsigned char* a_smem = smem;
-  unsigned char* b_smem = smem + tile_bytes;
-  uint32_t* cand_keys = reinterpret_cast<uint32_t*>(smem + tile_bytes * (1 + p.stages));
+  unsigned char* b_smem = smem + a_bytes;
+  uint32_t* cand_keys = reinterpret_cast<uint32_t*>(smem + a_bytes + b_bytes * p.stages);
   uint32_t* cand_idx = cand_keys + 4 * kCandCap * 32;
 
   const uint32_t bar_a_full = smem_u32(&bars[0]);
   auto bar_b_full = [&](int s) { return smem_u32(&bars[1 + s]); };
   auto bar_b_empty = [&](int s) { return smem_u32(&bars[1 + kMaxStages + s]); };
   auto bar_acc_full = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + b]); };
-  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + 2 + b]); };
+  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + kAccBufs + b]); };
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
@@ -366,7 +458,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       mbar_init(bar_b_full(s), 1);
       mbar_init(bar_b_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAccBufs; ++b) {
       mbar_init(bar_acc_full(b), 1);
       mbar_init(bar_acc_empty(b), 4);  // one arrive per epilogue warp
     }
@@ -384,39 +476,46 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   if (warp == 0) {
     // ===== producer: bulk-async copies of whole operand tiles =====
     if (lane == 0 && n_tiles > 0) {
-      mbar_expect_tx(bar_a_full, tile_bytes);
-      bulk_g2s(smem_u32(a_smem), p.q_img + (size_t)q_tile * tile_bytes, tile_bytes, bar_a_full);
+      mbar_expect_tx(bar_a_full, a_bytes);
+      bulk_g2s(smem_u32(a_smem), p.q_img + (size_t)q_tile * a_bytes, a_bytes, bar_a_full);
+      const uint32_t piece = b_bytes / kLoadPieces;  // b_bytes = 4096 * dc: divisible by 4 * 16
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(bar_b_empty(s), ph ^ 1u);
-        mbar_expect_tx(bar_b_full(s), tile_bytes);
-        bulk_g2s(smem_u32(b_smem + (size_t)s * tile_bytes), p.r_img + (size_t)(t_begin + it) * tile_bytes, tile_bytes,
-                 bar_b_full(s));
+        mbar_expect_tx(bar_b_full(s), b_bytes);
+        const unsigned char* src = p.r_img + (size_t)(t_begin + it) * b_bytes;
+        const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
+#pragma unroll
+        for (int c = 0; c < kLoadPieces; ++c) bulk_g2s(dst + c * piece, src + (size_t)c * piece, piece, bar_b_full(s));
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread drives the tensor core for the whole CTA =====
     if (lane == 0 && n_tiles > 0) {
       constexpr uint32_t idesc = make_idesc_f16(kMmaTile, kMmaTile);
-      const uint32_t sbo = (uint32_t)p.kp * 16u;  // bytes between 8-row groups
-      const uint32_t lbo = 128u;                  // bytes between the two 8-column halves of one K=16 step
-      const int ksteps = p.kp >> 4;
+      const uint32_t lbo = 128u;                     // bytes between the two 8-column halves of one K=16 step
+      const uint32_t sbo_a = (uint32_t)p.kp_q * 16u;  // bytes between 8-row groups of the query image
+      const uint32_t sbo_b = (uint32_t)p.kp_r * 16u;  // ... of the reference image
+      const int ksteps = p.kp_q >> 4;
+      const int seg2_chunks = 2 * p.dc;              // query chunks >= this re-read reference segment 0
       mbar_wait(bar_a_full, 0);
-      const uint64_t a_desc0 = make_smem_desc(smem_u32(a_smem), lbo, sbo);
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(a_smem), lbo, sbo_a);
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        const int buf = it & 1;
-        const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+        const int buf = it % kAccBufs;
+        const uint32_t aph = (uint32_t)(it / kAccBufs) & 1u;
         mbar_wait(bar_acc_empty(buf), aph ^ 1u);
         mbar_wait(bar_b_full(s), ph);
         tc_fence_after();
-        const uint64_t b_desc0 = make_smem_desc(smem_u32(b_smem + (size_t)s * tile_bytes), lbo, sbo);
+        const uint64_t b_desc0 = make_smem_desc(smem_u32(b_smem + (size_t)s * b_bytes), lbo, sbo_b);
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * kMmaTile;
         for (int kk = 0; kk < ksteps; ++kk) {
-          // one K=16 step = two 128-byte core-matrix columns = 256 bytes = 16 descriptor units
-          umma_f16_ss(d_tmem, a_desc0 + (uint64_t)(16 * kk), b_desc0 + (uint64_t)(16 * kk), idesc, kk > 0 ? 1u : 0u);
+          // K=16 step kk reads query chunks (2kk, 2kk+1) and the matching reference chunks; one chunk
+          // = 128 bytes = 8 descriptor address units
+          const int bchunk = 2 * kk < seg2_chunks ? 2 * kk : 2 * kk - seg2_chunks;
+          umma_f16_ss(d_tmem, a_desc0 + (uint64_t)(16 * kk), b_desc0 + (uint64_t)(8 * bchunk), idesc, kk > 0 ? 1u : 0u);
         }
         tc_commit(bar_b_empty(s));     // smem slot free once these MMAs have read it
         tc_commit(bar_acc_full(buf));  // accumulator complete
@@ -427,57 +526,66 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
     RowCand rc;
-    rc.keys = cand_keys + quad * kCandCap * 32 + lane;
-    rc.idx = cand_idx + quad * kCandCap * 32 + lane;
+    rc.keys = smem_u32(cand_keys + quad * kCandCap * 32 + lane);
+    rc.idx = smem_u32(cand_idx + quad * kCandCap * 32 + lane);
     rc.cnt = 0;
     rc.thr_key = 0xFFFFFFFFu;
     rc.thr = CUDART_INF_F;
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
+    const float inv_tiles = 1.f / (float)max(n_tiles, 1);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
 
-    for (int it = 0; it < n_tiles; ++it) {
-      const int buf = it & 1;
-      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(bar_acc_full(buf), aph);
+    uint32_t va[32], vb[32];  // two register sets: the next chunk's tcgen05.ld overlaps this chunk's math
+    if (n_tiles > 0) {
+      mbar_wait(bar_acc_full(0), 0);
       tc_fence_after();
+      tmem_ld_32x32b_x32(t_lane, va);
+    }
+    for (int it = 0; it < n_tiles; ++it) {
+      const int buf = it % kAccBufs;
+      int keep_lo, keep_hi;
+      keep_window(p.k, (float)(it + 1) * inv_tiles, keep_lo, keep_hi);
+      const int trigger = min(kCandCap - 32, 2 * keep_hi);
       const uint32_t col_base = (uint32_t)(t_begin + it) * kMmaTile;
+      const uint32_t t_buf = t_lane + (uint32_t)buf * kMmaTile;
+      float* dbg = kDebug ? p.debug_out + q_row * ((int64_t)p.n_r_tiles * kMmaTile) + col_base : nullptr;
+
 #pragma unroll 1
-      for (int chunk = 0; chunk < kMmaTile / 32; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * kMmaTile + chunk * 32, v);
-        tmem_ld_wait();
-        if (chunk == kMmaTile / 32 - 1) {
-          // all of this warp's reads of the buffer are complete: hand it back to the MMA warp
+      for (int half = 0; half < 2; ++half) {  // chunks (0,1) then (2,3): two copies of the chunk code, not four
+        const uint32_t cb = col_base + half * 64;
+        tmem_ld_wait();                                   // even chunk in va
+        tmem_ld_32x32b_x32(t_buf + half * 64 + 32, vb);   // odd chunk in flight
+        if (kDebug) for (int j = 0; j < 32; ++j) dbg[half * 64 + j] = __uint_as_float(va[j]);
+        process_chunk(va, cb, rc, trigger, keep_lo, keep_hi);
+
+        tmem_ld_wait();                                   // odd chunk in vb
+        if (half == 0) {
+          tmem_ld_32x32b_x32(t_buf + 64, va);             // chunk 2 in flight
+        } else {
+          // this warp has read the whole buffer: hand it back, then start on the next tile
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty(buf));
-        }
-        if (p.debug_out) {
-          float* dst = p.debug_out + q_row * ((int64_t)p.n_r_tiles * kMmaTile) + col_base + chunk * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(v[j]);
-        }
-        float m = __uint_as_float(v[0]);
-#pragma unroll
-        for (int j = 1; j < 32; ++j) m = fminf(m, __uint_as_float(v[j]));
-        if (m < rc.thr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float f = __uint_as_float(v[j]);
-            if (f < rc.thr) {
-              rc.keys[rc.cnt * 32] = float_to_ordered(f);
-              rc.idx[rc.cnt * 32] = col_base + chunk * 32 + j;
-              ++rc.cnt;
-            }
+          if (it + 1 < n_tiles) {
+            const int nbuf = (it + 1) % kAccBufs;
+            mbar_wait(bar_acc_full(nbuf), (uint32_t)((it + 1) / kAccBufs) & 1u);
+            tc_fence_after();
+            tmem_ld_32x32b_x32(t_lane + (uint32_t)nbuf * kMmaTile, va);
           }
         }
-        if (__any_sync(0xffffffffu, rc.cnt > kCandCap - 32)) compact_row(rc);
+        if (kDebug) for (int j = 0; j < 32; ++j) dbg[half * 64 + 32 + j] = __uint_as_float(vb[j]);
+        process_chunk(vb, cb + 32, rc, trigger, keep_lo, keep_hi);
       }
     }
-    compact_row(rc);  // leave at most kCandOut entries
+    {
+      int keep_lo, keep_hi;
+      keep_window(p.k, 1.f, keep_lo, keep_hi);
+      compact_row(rc, keep_lo, keep_hi);  // leave at most kCandOut entries
+    }
     const int64_t o = (q_row * p.splits + split);
     for (int e = 0; e < rc.cnt; ++e) {
-      p.cand_s[o * kCandOut + e] = ordered_to_float(rc.keys[e * 32]);
-      p.cand_i[o * kCandOut + e] = (int32_t)rc.idx[e * 32];
+      p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
+      p.cand_i[o * kCandOut + e] = (int32_t)lds_u32(rc.idx + e * kCandStride);
     }
     p.cand_cnt[o] = rc.cnt;
     p.cand_thr[o] = rc.thr;
@@ -503,7 +611,8 @@ __global__ void __launch_bounds__(kRerankWarps * 32)
 rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int64_t ldr, int64_t n_q, int64_t n_r, int d,
               int k, int splits, const double* __restrict__ q_norms, const float* __restrict__ cand_s,
               const int32_t* __restrict__ cand_i, const int32_t* __restrict__ cand_cnt,
-              const float* __restrict__ cand_thr, ScaleInfo* info, int64_t r_index_offset, int dist_mode,
+              const float* __restrict__ cand_thr, ScaleInfo* info, uint64_t perm_mul, int64_t n_r_pad,
+              int64_t r_index_offset, int dist_mode,
               double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -531,7 +640,8 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
       const int c_s = cand_cnt[q * splits + s];
       const int64_t o = (q * splits + s) * kCandOut;
       for (int e = lane; e < c_s; e += 32) {
-        const int id = cand_i[o + e];
+        const int pos = cand_i[o + e];
+        const int id = (int)((perm_mul * (uint64_t)pos) % (uint64_t)n_r_pad);  // scan position -> source row
         double d2 = CUDART_INF;
         if (id >= 0 && id < n_r) {
           const T* rp = R + (int64_t)id * ldr;
@@ -602,24 +712,54 @@ __global__ void publish_stats_kernel(const ScaleInfo* info, int64_t* stats_out) 
 }
 
 struct MmaPlan {
-  int kp, stages, splits;
+  uint64_t perm_mul;  // image position p holds reference row (perm_mul * p) mod n_r_pad
+  int kp_q, kp_r, dc, stages, splits;
   int64_t n_q_tiles, n_r_tiles, n_q_pad, n_r_pad;
   size_t smem_bytes;
 };
 
+int64_t gcd64(int64_t a, int64_t b) {
+  while (b) { int64_t t = a % b; a = b; b = t; }
+  return a;
+}
+// modular inverse by the extended Euclidean algorithm (a, m coprime)
+int64_t modinv64(int64_t a, int64_t m) {
+  int64_t g = m, x = 0, y = 1, aa = a % m;
+  while (aa) {
+    int64_t q = g / aa, t = g % aa;
+    g = aa; aa = t;
+    t = x - q * y; x = y; y = t;
+  }
+  return x < 0 ? x + m : x;
+}
+// Scrambled visiting order of the reference: source row o sits at position (h * o) mod N with h/N
+// close to the golden ratio conjugate, so ANY run of consecutive (e.g. same-cluster, same-batch)
+// rows is spread evenly over the scan (three-distance theorem).  Returns g = h^-1 mod N, the
+// multiplier that maps a position back to its source row.
+uint64_t scramble_multiplier(int64_t n_pad) {
+  if (n_pad <= 1) return 1;
+  int64_t h = (int64_t)((double)n_pad * 0.6180339887498949) | 1;
+  while (gcd64(h, n_pad) != 1) h += 2;
+  h %= n_pad;
+  return (uint64_t)modinv64(h, n_pad);
+}
+
 MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
   MmaPlan pl;
-  pl.kp = mma_kp(d);
+  pl.dc = mma_seg_chunks(d);
+  pl.kp_q = mma_kp_q(d);
+  pl.kp_r = mma_kp_r(d);
   pl.n_q_tiles = ceil_div(n_q, kMmaTile);
   pl.n_r_tiles = ceil_div(n_r, kMmaTile);
   pl.n_q_pad = pl.n_q_tiles * kMmaTile;
   pl.n_r_pad = pl.n_r_tiles * kMmaTile;
-  const size_t tile_bytes = (size_t)kMmaTile * pl.kp * 2;
+  pl.perm_mul = scramble_multiplier(pl.n_r_pad);
+  const size_t a_bytes = (size_t)kMmaTile * pl.kp_q * 2, b_bytes = (size_t)kMmaTile * pl.kp_r * 2;
   const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2;
-  const size_t budget = 227 * 1024 - 1024;
-  int stages = (int)((budget - cand_bytes - tile_bytes) / tile_bytes);
+  const size_t budget = 227 * 1024 - 1024;  // 1 KB of static shared memory (barriers, TMEM slot)
+  int stages = (int)((budget - cand_bytes - a_bytes) / b_bytes);
   pl.stages = stages > kMaxStages ? kMaxStages : stages;
-  pl.smem_bytes = tile_bytes * (1 + pl.stages) + cand_bytes;
+  pl.smem_bytes = a_bytes + b_bytes * pl.stages + cand_bytes;
   // enough CTAs for ~2 waves when the query side is small; every split keeps >= 4 reference tiles
   int64_t want = ceil_div(2 * kNumSMs, pl.n_q_tiles);
   int64_t cap = pl.n_r_tiles / 4 > 0 ? pl.n_r_tiles / 4 : 1;
@@ -648,8 +788,8 @@ MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
   b.info = ws.take<ScaleInfo>(1);
   b.q_norms = ws.take<double>(n_q);
   b.r_norms = ws.take<double>(n_r);
-  b.q_img = ws.take<unsigned char>((size_t)pl.n_q_pad * pl.kp * 2);
-  b.r_img = ws.take<unsigned char>((size_t)pl.n_r_pad * pl.kp * 2);
+  b.q_img = ws.take<unsigned char>((size_t)pl.n_q_pad * pl.kp_q * 2);
+  b.r_img = ws.take<unsigned char>((size_t)pl.n_r_pad * pl.kp_r * 2);
   b.cand_s = ws.take<float>((size_t)pl.n_q_pad * pl.splits * kCandOut);
   b.cand_i = ws.take<int32_t>((size_t)pl.n_q_pad * pl.splits * kCandOut);
   b.cand_cnt = ws.take<int32_t>((size_t)pl.n_q_pad * pl.splits);
@@ -669,36 +809,43 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
   CM_LAUNCH_CHECK("rowstats_kernel(Q)");
   rowstats_kernel<T><<<gr, wpb * 32, 0, st>>>(R, ldr, n_r, d, b.r_norms, b.info, 1);
   CM_LAUNCH_CHECK("rowstats_kernel(R)");
-  const int chunks = pl.kp / 8;
-  int64_t tq = pl.n_q_pad * chunks, tr = pl.n_r_pad * chunks;
+  int64_t tq = pl.n_q_pad * (pl.kp_q / 8), tr = pl.n_r_pad * (pl.kp_r / 8);
   int bq = (int)(ceil_div(tq, 256) < kNumSMs * 16 ? ceil_div(tq, 256) : kNumSMs * 16);
   int br = (int)(ceil_div(tr, 256) < kNumSMs * 16 ? ceil_div(tr, 256) : kNumSMs * 16);
-  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp, b.q_norms, b.info, 1,
+  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q, pl.dc, b.q_norms, b.info, 1, 0ULL,
                                      reinterpret_cast<uint4*>(b.q_img));
   CM_LAUNCH_CHECK("prep_kernel(Q)");
-  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp, b.r_norms, b.info, 0,
+  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r, pl.dc, b.r_norms, b.info, 0, pl.perm_mul,
                                      reinterpret_cast<uint4*>(b.r_img));
   CM_LAUNCH_CHECK("prep_kernel(R)");
   return CM_OK;
 }
 
-int run_mma(const MmaPlan& pl, const MmaBuffers& b, float* debug_out, cudaStream_t st) {
+int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cudaStream_t st) {
   MmaParams p;
   p.q_img = b.q_img;
   p.r_img = b.r_img;
   p.n_q_tiles = (int)pl.n_q_tiles;
   p.n_r_tiles = (int)pl.n_r_tiles;
   p.splits = pl.splits;
-  p.kp = pl.kp;
+  p.kp_q = pl.kp_q;
+  p.kp_r = pl.kp_r;
+  p.dc = pl.dc;
   p.stages = pl.stages;
+  p.k = k;
   p.cand_s = b.cand_s;
   p.cand_i = b.cand_i;
   p.cand_cnt = b.cand_cnt;
   p.cand_thr = b.cand_thr;
   p.debug_out = debug_out;
-  CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
   const int64_t grid = pl.n_q_tiles * pl.splits;
-  mma_topk_kernel<<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);
+  if (debug_out) {
+    CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    mma_topk_kernel<true><<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);
+  } else {
+    CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    mma_topk_kernel<false><<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);
+  }
   CM_LAUNCH_CHECK("mma_topk_kernel");
   return CM_OK;
 }
@@ -712,8 +859,9 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
   int64_t blocks = ceil_div(n_q, kRerankWarps);
   int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
   rerank_kernel<T><<<grid, kRerankWarps * 32, smem, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, pl.splits, b.q_norms,
-                                                         b.cand_s, b.cand_i, b.cand_cnt, b.cand_thr, b.info, r_off,
-                                                         dist_mode, out_dist, out_idx, b.fail_rows);
+                                                         b.cand_s, b.cand_i, b.cand_cnt, b.cand_thr, b.info,
+                                                         pl.perm_mul, pl.n_r_pad, r_off, dist_mode, out_dist, out_idx,
+                                                         b.fail_rows);
   CM_LAUNCH_CHECK("rerank_kernel");
   return CM_OK;
 }
@@ -746,7 +894,7 @@ int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64
   }
   if (rc) return rc;
   profile_mark(1, st);
-  if ((rc = run_mma(pl, b, nullptr, st))) return rc;
+  if ((rc = run_mma(pl, b, k, nullptr, st))) return rc;
   profile_mark(2, st);
   if (dtype == CM_F32) {
     rc = run_rerank<float>((const float*)Q, n_q, ldq, (const float*)R, n_r, ldr, d, k, pl, b, r_off, dist_mode,
@@ -783,6 +931,7 @@ int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st) {
   MmaPlan pl = make_plan(n_q, n_r, d);
   pl.splits = 1;
+  pl.perm_mul = 1;  // identity order: the dump is indexed by source row
   Workspace ws(workspace, ws_bytes);
   MmaBuffers b = carve(ws, pl, n_q, n_r);
   if (!ws.ok()) {
@@ -795,7 +944,7 @@ int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d
   else
     rc = run_prep<double>((const double*)Q, n_q, d, (const double*)R, n_r, d, d, pl, b, st);
   if (rc) return rc;
-  if ((rc = run_mma(pl, b, out, st))) return rc;
+  if ((rc = run_mma(pl, b, 1, out, st))) return rc;
   write_scale_kernel<<<1, 1, 0, st>>>(b.info, scale_out);
   CM_LAUNCH_CHECK("write_scale_kernel");
   return CM_OK;
