@@ -48,6 +48,8 @@ SIGNATURES = {
     "cm_launch_count": (c_int64, []),
     "cm_profile_enable": (c_int, [c_int]),
     "cm_profile_last_knn_ms": (c_int, [_P]),
+    "cm_debug_probe_flags": (c_int, [c_int]),
+    "cm_debug_probe_prof": (c_int, [_P]),
     "cm_debug_mma_tile": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
 }
 

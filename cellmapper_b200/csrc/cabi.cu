@@ -37,6 +37,8 @@ int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64
                    int k, int64_t r_off, int dist_mode, double* out_dist, int64_t* out_idx, void* workspace,
                    size_t ws_bytes, int64_t* stats_out, cudaStream_t st);
 size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d);
+void set_probe_flags(int f);
+void set_probe_prof(long long* p);
 int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st);
 
@@ -116,4 +118,14 @@ extern "C" int cm_debug_mma_tile(const void* Q, int64_t n_q, const void* R, int6
   CM_REQUIRE(Q && R && out && scale_out && workspace, "null pointer argument");
   CM_REQUIRE(mma_supported(d, 1), "d = %d not supported by the tensor-core path", d);
   return debug_mma_tile(Q, n_q, R, n_r, d, dtype, out, scale_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cm_debug_probe_flags(int flags) {
+  set_probe_flags(flags);
+  return CM_OK;
+}
+
+extern "C" int cm_debug_probe_prof(long long* device_buf) {
+  set_probe_prof(device_buf);
+  return CM_OK;
 }

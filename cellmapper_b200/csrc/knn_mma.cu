@@ -5,17 +5,19 @@
 //
 //   rowstats   : ||x||^2 (float64) per row, global max |x| and max ||r||^2
 //   prep       : scale by a power of two so max|x| in [32,64), split every value into fp16 hi + lo and
-//                write "operand images" -- the exact byte layout tcgen05.mma reads from shared
-//                memory (K-major, no swizzle, 8x16-byte core matrices) -- so a tile is ONE contiguous
-//                cp.async.bulk.  Columns: Q' = [-2hi,c c c | -2hi | -2lo], R' = [hi,n1 n2 n3 | lo]; the
+//                write the operands: the reference as an "operand image" -- the exact byte layout
+//                tcgen05.mma reads from shared memory (K-major, no swizzle, 8x16-byte core matrices), so
+//                a tile is ONE contiguous cp.async.bulk -- and the queries row-major (each CTA keeps its
+//                128-query tile in TENSOR memory: the MMAs run in TS mode, A from TMEM, B from smem).  Columns: Q' = [-2hi,c c c | -2hi | -2lo], R' = [hi,n1 n2 n3 | lo]; the
 //                K-steps of the third query segment re-read the reference's hi segment, so
 //                Q'.R'^T = c(n1+n2+n3) - 2(hi.hi + hi.lo + lo.hi) = ||r'||^2 - 2 q'.r'  (rank-equivalent
 //                to the squared distance) with ~2^-22 relative accuracy from three fp16 products,
 //                while the streamed reference tile carries only 2 of the 3 segments.
 //   mma_topk   : one CTA per (128-query tile, reference split).  Warp 0 streams reference tiles with
 //                bulk-async copies into a shared-memory ring, warp 1 issues tcgen05.mma (128x128xK')
-//                into four TMEM accumulator buffers, warps 2-5 drain TMEM (tcgen05.ld, one query
-//                row per thread) and keep a per-row threshold + candidate buffer in shared memory.
+//                into three TMEM accumulator buffers, warps 2-5 first store the query tile into TMEM,
+//                then drain the accumulators (tcgen05.ld, one query row per thread) and keep a per-row
+//                threshold + candidate buffer in shared memory.
 //                The n_q x n_r distance matrix never exists.
 //   rerank     : per query, exact float64 direct-difference distances of the <= 60*splits candidates,
 //                sort by (d2, index), emit k, and CERTIFY: d2_k + 2E <= smallest rejected value.
@@ -42,20 +44,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef CM_WAIT_HINT_NS
+#define CM_WAIT_HINT_NS 100
+#endif
+constexpr uint32_t kWaitHintNs = CM_WAIT_HINT_NS;
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the
+// hint (ns) expires, so a waiting warp does not burn issue slots of the epilogue warp that shares its
+// scheduler (ncu r1a: 38% of all executed instructions were barrier polls).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kWaitHintNs)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 20000000000LL) {  // ~10 s
@@ -64,6 +72,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (int i = 0; i < 4096; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -97,6 +111,33 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (the CTA's query tile) lives in tensor memory, lane =
+// row, two consecutive K elements per 32-bit column.  Only B is fetched from shared memory, which
+// halves the operand traffic of the 128x128x16 shape (SS mode needs 8 KB per 64-cycle MMA = the
+// whole 128 B/clk shared-memory port and measured 146 cycles per MMA, probe r1b).
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint4& a, const uint4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x),
+               "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+// one lane of a converged warp; the surrounding code stays warp-uniform so that descriptors and tensor
+// memory addresses live in uniform registers (a divergent `if (lane == 0)` loop costs an R2UR chain
+// per MMA: 146 instead of 64 cycles per 128x128x16 MMA, tools/mma_bench.cu)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -106,6 +147,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
       : "r"(taddr)
       : "memory");
 }
@@ -241,7 +290,10 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
     v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
     v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
     v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
-    img[group * (int64_t)(chunks * 8) + chunk * 8 + r8] = v;
+    if (is_query)
+      img[pos * chunks + chunk] = v;  // row-major: the epilogue threads copy their own row into TMEM
+    else
+      img[group * (int64_t)(chunks * 8) + chunk * 8 + r8] = v;
   }
 }
 
@@ -286,6 +338,20 @@ __device__ __forceinline__ int count_below(uint32_t keys, int cnt, uint32_t piv)
   return c;
 }
 
+// Adaptive keep window.  The reference rows are visited in a scrambled (golden-ratio stride) order,
+// so after a fraction f of a split has been seen the number of true top-k members among the seen
+// elements is Binomial(k, f).  Keeping k*f + 4.5 sigma + 8 candidates therefore loses a true
+// neighbour with probability ~1e-5 per row (caught by the certificate), while the threshold is as
+// tight as it can be from the very first tiles -- far fewer candidates pass than with a fixed window.
+__device__ __forceinline__ void keep_window(int k, float f, int& keep_lo, int& keep_hi) {
+  const float kf = (float)k * f;
+  int lo = (int)ceilf(kf + 4.5f * sqrtf(fmaxf(kf * (1.f - f), 0.f)) + 8.f);
+  int hi = min(lo + 14, kCandOut);
+  lo = min(lo, hi - 4);
+  keep_lo = lo;
+  keep_hi = hi;
+}
+
 // Shrink the buffer to between keep_lo and keep_hi entries and tighten the threshold.  Selection,
 // not sorting: bisection on the ordered-uint key until the count below the pivot lands in the
 // window.  Ties that straddle the window are cut arbitrarily and the threshold is set to the tied
@@ -293,7 +359,9 @@ __device__ __forceinline__ int count_below(uint32_t keys, int cnt, uint32_t piv)
 // Cold code, deliberately NOT inlined: the hot epilogue loop has to stay inside the instruction cache.
 // Returns (new count) | (new threshold key << 32).
 __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint32_t idx, int cnt, uint32_t thr_key,
-                                                            int keep_lo, int keep_hi) {
+                                                            int k, float f) {
+  int keep_lo, keep_hi;
+  keep_window(k, f, keep_lo, keep_hi);
   if (cnt <= keep_hi) return (unsigned long long)(uint32_t)cnt | ((unsigned long long)thr_key << 32);
   uint32_t lo = 0xFFFFFFFFu, mx = 0u;
   for (int e = 0; e < cnt; ++e) {
@@ -351,35 +419,30 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
   return (unsigned long long)(uint32_t)w | ((unsigned long long)tl << 32);
 }
 
-__device__ __forceinline__ void compact_row(RowCand& rc, int keep_lo, int keep_hi) {
-  const unsigned long long r = compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, keep_lo, keep_hi);
+// `it` = index of the reference tile being drained, inv_tiles = 1 / tiles of this split
+__device__ __forceinline__ void compact_row(RowCand& rc, int it, float inv_tiles, int k) {
+  const unsigned long long r =
+      compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, k, fminf((float)(it + 1) * inv_tiles, 1.f));
   rc.cnt = (int)(uint32_t)r;
   rc.thr_key = (uint32_t)(r >> 32);
   rc.thr = rc.thr_key == 0xFFFFFFFFu ? CUDART_INF_F : ordered_to_float(rc.thr_key);
 }
 
-// Adaptive keep window.  The reference rows are visited in a scrambled (golden-ratio stride) order,
-// so after a fraction f of a split has been seen the number of true top-k members among the seen
-// elements is Binomial(k, f).  Keeping k*f + 4.5 sigma + 8 candidates therefore loses a true
-// neighbour with probability ~1e-5 per row (caught by the certificate), while the threshold is as
-// tight as it can be from the very first tiles -- far fewer candidates pass than with a fixed window.
-__device__ __forceinline__ void keep_window(int k, float f, int& keep_lo, int& keep_hi) {
-  const float kf = (float)k * f;
-  int lo = (int)ceilf(kf + 4.5f * sqrtf(fmaxf(kf * (1.f - f), 0.f)) + 8.f);
-  int hi = min(lo + 14, kCandOut);
-  lo = min(lo, hi - 4);
-  keep_lo = lo;
-  keep_hi = hi;
-}
+constexpr int kCandTrigger = kCandCap - 27;  // a compaction check follows every <= 27 appended columns
 
 // ------------------------------------------------------------------------------------------------
 // the tensor-core kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kMmaThreads = 192;  // warp 0 producer, warp 1 MMA + TMEM owner, warps 2..5 epilogue
-constexpr int kAccBufs = 4;       // TMEM accumulator buffers: the MMA warp runs up to 3 tiles ahead
-constexpr int kTmemCols = kAccBufs * kMmaTile;  // 512 fp32 columns = all of TMEM
+constexpr int kMmaThreads = 224;  // warp 0 producer, warps 1 and 6 MMA issue (even / odd tiles), warps 2..5 epilogue
+constexpr int kAccBufs = 3;       // TMEM accumulator buffers: the MMA warp runs up to 2 tiles ahead
+constexpr int kTmemACols = kMmaTile;            // columns [0,128): the query operand (kp_q/2 <= 88 used)
+constexpr int kTmemCols = kTmemACols + kAccBufs * kMmaTile;  // 512 columns = all of TMEM
 constexpr int kMaxStages = 4;
+static_assert(kTmemCols == 512, "TMEM allocations are powers of two");
 constexpr int kLoadPieces = 4;    // bulk copies per reference tile (independent requests overlap their latency)
+
+int g_probe_flags = 0;  // set through cm_debug_probe_flags (development only)
+long long* g_probe_prof = nullptr;
 
 struct MmaParams {
   const unsigned char* q_img;  // n_q_tiles tiles of 128 x kp_q fp16
@@ -390,39 +453,142 @@ struct MmaParams {
   int32_t* cand_cnt;  // [n_q_pad][splits]
   float* cand_thr;    // [n_q_pad][splits]
   float* debug_out;   // optional raw accumulator dump [n_q_pad][n_r_tiles*128]
+  int flags;          // development probes: 1 = skip the epilogue math, 2 = skip the reference tile copies
+  long long* prof_out;  // optional [grid][8] cycle counters of the MMA warp (development)
 };
 
-// One 32-column chunk of one query row: minimum by a depth-4 tree of 3-input mins; if anything in
-// the warp is below its row's threshold, every passing value is appended with predicated stores
-// (no branches: the code must be small and its cost independent of divergence).
-__device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], uint32_t c0, RowCand& rc, int trigger,
-                                              int keep_lo, int keep_hi) {
-  float t[11];
+// Append the elements of one leaf (<= 3 consecutive columns) that are below the row's threshold:
+// predicated stores, no branches.
+template <int N>
+__device__ __forceinline__ void append_leaf(const uint32_t* v, uint32_t c0, RowCand& rc, float thr) {
+  uint32_t w = rc.keys + (uint32_t)rc.cnt * kCandStride;
+  const uint32_t idx_off = rc.idx - rc.keys;
+  int added = 0;
 #pragma unroll
-  for (int g = 0; g < 10; ++g)
+  for (int e = 0; e < N; ++e) {
+    const bool pass = __uint_as_float(v[e]) < thr;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "@p st.shared.u32 [%0], %1;\n\t"
+        "@p st.shared.u32 [%2], %3;\n\t}"
+        ::"r"(w), "r"(v[e]), "r"(w + idx_off), "r"(c0 + e), "r"((uint32_t)pass)
+        : "memory");
+    w += pass ? kCandStride : 0u;
+    added += pass ? 1 : 0;
+  }
+  rc.cnt += added;
+}
+
+// One 64-column half tile of one query row (thread = row).  Fast path: a depth-4 tree of 3-input
+// minima and ONE warp vote.  Slow path: descend the tree with warp-uniform votes (27 -> 9 -> 3
+// columns) and append only inside the leaves that hold a passing element, so its cost follows the
+// number of passing elements instead of the chunk width.
+__device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c0, RowCand& rc, int it, float inv_tiles,
+                                             int k) {
+  float t[22];
+#pragma unroll
+  for (int g = 0; g < 21; ++g)
     t[g] = fminf(fminf(__uint_as_float(v[3 * g]), __uint_as_float(v[3 * g + 1])), __uint_as_float(v[3 * g + 2]));
-  t[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-  const float u0 = fminf(fminf(t[0], t[1]), t[2]), u1 = fminf(fminf(t[3], t[4]), t[5]);
-  const float u2 = fminf(fminf(t[6], t[7]), t[8]), u3 = fminf(t[9], t[10]);
-  const float m = fminf(fminf(fminf(u0, u1), u2), u3);
-  const float thr = rc.thr;
-  if (__any_sync(0xffffffffu, m < thr)) {
-    uint32_t w = rc.keys + (uint32_t)rc.cnt * kCandStride;
-    const uint32_t idx_off = rc.idx - rc.keys;
+  t[21] = __uint_as_float(v[63]);
+  float u[8];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const bool pass = __uint_as_float(v[e]) < thr;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "setp.ne.u32 p, %4, 0;\n\t"
-          "@p st.shared.u32 [%0], %1;\n\t"
-          "@p st.shared.u32 [%2], %3;\n\t}"
-          ::"r"(w), "r"(v[e]), "r"(w + idx_off), "r"(c0 + e), "r"((uint32_t)pass)
-          : "memory");
-      w += pass ? kCandStride : 0u;
+  for (int g = 0; g < 7; ++g) u[g] = fminf(fminf(t[3 * g], t[3 * g + 1]), t[3 * g + 2]);
+  u[7] = t[21];
+  float w[3];
+  w[0] = fminf(fminf(u[0], u[1]), u[2]);
+  w[1] = fminf(fminf(u[3], u[4]), u[5]);
+  w[2] = fminf(u[6], u[7]);
+  const float m = fminf(fminf(w[0], w[1]), w[2]);
+  if (__any_sync(0xffffffffu, m < rc.thr)) {
+#pragma unroll
+    for (int W = 0; W < 3; ++W) {
+      if (__any_sync(0xffffffffu, w[W] < rc.thr)) {
+        const float thr = rc.thr;
+#pragma unroll
+        for (int U = 3 * W; U < 3 * W + 3 && U < 8; ++U) {
+          if (__any_sync(0xffffffffu, u[U] < thr)) {
+            if (U == 7) {
+              append_leaf<1>(&v[63], c0 + 63, rc, thr);
+            } else {
+#pragma unroll
+              for (int T = 3 * U; T < 3 * U + 3; ++T)
+                if (__any_sync(0xffffffffu, t[T] < thr)) append_leaf<3>(&v[3 * T], c0 + 3 * T, rc, thr);
+            }
+          }
+        }
+        // at most 27 appends since the last check: cnt <= kCandTrigger + 27 <= kCandCap
+        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) compact_row(rc, it, inv_tiles, k);
+      }
     }
-    rc.cnt = (int)((w - rc.keys) / kCandStride);
-    if (__any_sync(0xffffffffu, rc.cnt > trigger)) compact_row(rc, keep_lo, keep_hi);
+  }
+}
+
+struct MmaIssueArgs {
+  int n_tiles, stages, flags, first;  // this warp issues tiles first, first + 2, ...
+  uint32_t b_bytes, b_smem, tmem_base;
+  uint32_t bar_a_full, bar_b_full0, bar_b_empty0, bar_acc_full0, bar_acc_empty0;  // consecutive barriers are 8 bytes apart
+  long long* prof;
+};
+
+// K' = 16 * KSTEPS columns per tile, all descriptor offsets compile-time constants.  DC = 8-column
+// chunks per operand segment: the query has 3 segments (+ one zero chunk when 3*DC is odd), the
+// reference image 2; query chunks >= 2*DC (the -2*lo segment) re-read reference segment 0.
+template <int DC>
+__device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
+  constexpr int kSteps = (3 * DC + 1) / 2;
+  constexpr uint32_t idesc = make_idesc_f16(kMmaTile, kMmaTile);
+  constexpr uint32_t lbo = 128u;              // bytes between the two 8-column halves of one K=16 step
+  constexpr uint32_t sbo_b = 2u * DC * 128u;  // bytes between 8-row groups of the reference image (kp_r * 16)
+  const uint32_t leader = elect_one();
+  mbar_wait(a.bar_a_full, 0);  // the epilogue warps have stored the query tile into TMEM
+  tc_fence_after();
+  const uint64_t b_desc_base = make_smem_desc(a.b_smem, lbo, sbo_b);
+  // two warps issue alternate tiles: while one is held back by the tensor pipe's ~5-deep issue queue, the
+  // other does its barrier waits and descriptor set-up, so the pipe never drains between tiles
+  // (tools/mma_queue.cu: an issuing thread runs at most ~350 cycles ahead of the pipe)
+  int s = a.first % a.stages, buf = a.first % kAccBufs;
+  uint32_t ph = 0, aph = 0;
+  long long c_acc = 0, c_b = 0, c_issue = 0, t_start = clock64();
+#pragma unroll 1
+  for (int it = a.first; it < a.n_tiles; it += 2) {
+    const long long t0 = a.prof ? clock64() : 0;
+    if (!(a.flags & 8)) mbar_wait(a.bar_acc_empty0 + 8 * buf, aph ^ 1u);  // probe 8: free-running MMA issue
+    const long long t1 = a.prof ? clock64() : 0;
+    mbar_wait(a.bar_b_full0 + 8 * s, ph);
+    const long long t2 = a.prof ? clock64() : 0;
+    tc_fence_after();
+    const uint64_t b_desc = b_desc_base + (uint64_t)(((uint32_t)s * a.b_bytes) >> 4);
+    const uint32_t d_tmem = a.tmem_base + kTmemACols + (uint32_t)buf * kMmaTile;
+    if (leader) {
+#pragma unroll
+      for (int kk = 0; kk < kSteps; ++kk) {
+        // K=16 step kk reads query columns [16kk, 16kk+16) = TMEM columns [8kk, 8kk+8) and reference chunks
+        // (bchunk, bchunk+1); one chunk = 128 bytes = 8 descriptor address units
+        const int bchunk = 2 * kk < 2 * DC ? 2 * kk : 2 * kk - 2 * DC;
+        umma_f16_ts(d_tmem, a.tmem_base + (uint32_t)(8 * kk), b_desc + (uint64_t)(8 * bchunk), idesc, kk > 0 ? 1u : 0u);
+      }
+      tc_commit(a.bar_b_empty0 + 8 * s);     // smem slot free once these MMAs have read it
+      tc_commit(a.bar_acc_full0 + 8 * buf);  // accumulator complete
+    }
+    __syncwarp();
+    if (a.prof) {
+      const long long t3 = clock64();
+      c_acc += t1 - t0;
+      c_b += t2 - t1;
+      c_issue += t3 - t2;
+    }
+    s += 2;
+    if (s >= a.stages) { s -= a.stages; ph ^= 1u; }
+    buf += 2;
+    if (buf >= kAccBufs) { buf -= kAccBufs; aph ^= 1u; }
+  }
+  if (a.prof && leader && a.first == 0) {
+    a.prof[0] = c_acc;
+    a.prof[1] = c_b;
+    a.prof[2] = c_issue;
+    a.prof[3] = clock64() - t_start;
+    a.prof[4] = a.n_tiles;
   }
 }
 
@@ -439,11 +605,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   const int t_end = min(p.n_r_tiles, t_begin + tiles_per_split);
   const int n_tiles = max(0, t_end - t_begin);
 
-  const uint32_t a_bytes = (uint32_t)kMmaTile * p.kp_q * 2;
   const uint32_t b_bytes = (uint32_t)kMmaTile * p.kp_r * 2;
-  unsigned char* a_smem = smem;
-  unsigned char* b_smem = smem + a_bytes;
-  uint32_t* cand_keys = reinterpret_cast<uint32_t*>(smem + a_bytes + b_bytes * p.stages);
+  unsigned char* b_smem = smem;
+  uint32_t* cand_keys = reinterpret_cast<uint32_t*>(smem + b_bytes * p.stages);
   uint32_t* cand_idx = cand_keys + 4 * kCandCap * 32;
 
   const uint32_t bar_a_full = smem_u32(&bars[0]);
@@ -453,7 +617,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   auto bar_acc_empty = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + kAccBufs + b]); };
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_full, 4);  // one arrive per epilogue warp once its 32 query rows are in TMEM
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(bar_b_full(s), 1);
       mbar_init(bar_b_empty(s), 1);
@@ -476,49 +640,48 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   if (warp == 0) {
     // ===== producer: bulk-async copies of whole operand tiles =====
     if (lane == 0 && n_tiles > 0) {
-      mbar_expect_tx(bar_a_full, a_bytes);
-      bulk_g2s(smem_u32(a_smem), p.q_img + (size_t)q_tile * a_bytes, a_bytes, bar_a_full);
       const uint32_t piece = b_bytes / kLoadPieces;  // b_bytes = 4096 * dc: divisible by 4 * 16
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         mbar_wait(bar_b_empty(s), ph ^ 1u);
-        mbar_expect_tx(bar_b_full(s), b_bytes);
-        const unsigned char* src = p.r_img + (size_t)(t_begin + it) * b_bytes;
-        const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
+        if (p.flags & 2) {
+          mbar_arrive(bar_b_full(s));
+        } else {
+          mbar_expect_tx(bar_b_full(s), b_bytes);
+          const unsigned char* src = p.r_img + (size_t)(t_begin + it) * b_bytes;
+          const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
 #pragma unroll
-        for (int c = 0; c < kLoadPieces; ++c) bulk_g2s(dst + c * piece, src + (size_t)c * piece, piece, bar_b_full(s));
+          for (int c = 0; c < kLoadPieces; ++c) bulk_g2s(dst + c * piece, src + (size_t)c * piece, piece, bar_b_full(s));
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: one thread drives the tensor core for the whole CTA =====
-    if (lane == 0 && n_tiles > 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kMmaTile, kMmaTile);
-      const uint32_t lbo = 128u;                     // bytes between the two 8-column halves of one K=16 step
-      const uint32_t sbo_a = (uint32_t)p.kp_q * 16u;  // bytes between 8-row groups of the query image
-      const uint32_t sbo_b = (uint32_t)p.kp_r * 16u;  // ... of the reference image
-      const int ksteps = p.kp_q >> 4;
-      const int seg2_chunks = 2 * p.dc;              // query chunks >= this re-read reference segment 0
-      mbar_wait(bar_a_full, 0);
-      const uint64_t a_desc0 = make_smem_desc(smem_u32(a_smem), lbo, sbo_a);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        const int buf = it % kAccBufs;
-        const uint32_t aph = (uint32_t)(it / kAccBufs) & 1u;
-        mbar_wait(bar_acc_empty(buf), aph ^ 1u);
-        mbar_wait(bar_b_full(s), ph);
-        tc_fence_after();
-        const uint64_t b_desc0 = make_smem_desc(smem_u32(b_smem + (size_t)s * b_bytes), lbo, sbo_b);
-        const uint32_t d_tmem = tmem_base + (uint32_t)buf * kMmaTile;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          // K=16 step kk reads query chunks (2kk, 2kk+1) and the matching reference chunks; one chunk
-          // = 128 bytes = 8 descriptor address units
-          const int bchunk = 2 * kk < seg2_chunks ? 2 * kk : 2 * kk - seg2_chunks;
-          umma_f16_ss(d_tmem, a_desc0 + (uint64_t)(16 * kk), b_desc0 + (uint64_t)(8 * bchunk), idesc, kk > 0 ? 1u : 0u);
-        }
-        tc_commit(bar_b_empty(s));     // smem slot free once these MMAs have read it
-        tc_commit(bar_acc_full(buf));  // accumulator complete
+  } else if (warp == 1 || warp == 6) {
+    // ===== MMA issuers: the whole warp runs the loop, one elected lane drives the tensor core =====
+    if (n_tiles > 0) {
+      MmaIssueArgs a;
+      a.first = warp == 1 ? 0 : 1;
+      a.n_tiles = n_tiles;
+      a.stages = p.stages;
+      a.b_bytes = b_bytes;
+      a.b_smem = smem_u32(b_smem);
+      a.tmem_base = tmem_base;
+      a.bar_a_full = bar_a_full;
+      a.bar_b_full0 = bar_b_full(0);
+      a.bar_b_empty0 = bar_b_empty(0);
+      a.bar_acc_full0 = bar_acc_full(0);
+      a.bar_acc_empty0 = bar_acc_empty(0);
+      a.flags = p.flags;
+      a.prof = p.prof_out ? p.prof_out + (size_t)blockIdx.x * 8 : nullptr;
+      switch (p.dc) {
+        case 1: mma_issue_loop<1>(a); break;
+        case 2: mma_issue_loop<2>(a); break;
+        case 3: mma_issue_loop<3>(a); break;
+        case 4: mma_issue_loop<4>(a); break;
+        case 5: mma_issue_loop<5>(a); break;
+        case 6: mma_issue_loop<6>(a); break;
+        default: mma_issue_loop<7>(a); break;
       }
     }
   } else {
@@ -533,55 +696,57 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     rc.thr = CUDART_INF_F;
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
     const float inv_tiles = 1.f / (float)max(n_tiles, 1);
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_lane = t_lane_a + kTmemACols;
+    {
+      // query operand: this thread's row of Q' (kp_q fp16, row-major) -> TMEM columns [0, kp_q/2)
+      const uint4* src = reinterpret_cast<const uint4*>(p.q_img + (size_t)q_row * p.kp_q * 2);
+      for (int c = 0; c < (p.kp_q >> 4); ++c) tmem_st_32x32b_x8(t_lane_a + 8 * c, src[2 * c], src[2 * c + 1]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full);
+    }
 
-    uint32_t va[32], vb[32];  // two register sets: the next chunk's tcgen05.ld overlaps this chunk's math
+    uint32_t va[64], vb[64];  // two register sets: the next half tile's tcgen05.ld overlaps this half's math
     if (n_tiles > 0) {
       mbar_wait(bar_acc_full(0), 0);
       tc_fence_after();
-      tmem_ld_32x32b_x32(t_lane, va);
+      tmem_ld_32x32b_x64(t_lane, va);
     }
+#pragma unroll 1
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it % kAccBufs;
-      int keep_lo, keep_hi;
-      keep_window(p.k, (float)(it + 1) * inv_tiles, keep_lo, keep_hi);
-      const int trigger = min(kCandCap - 32, 2 * keep_hi);
       const uint32_t col_base = (uint32_t)(t_begin + it) * kMmaTile;
       const uint32_t t_buf = t_lane + (uint32_t)buf * kMmaTile;
       float* dbg = kDebug ? p.debug_out + q_row * ((int64_t)p.n_r_tiles * kMmaTile) + col_base : nullptr;
 
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {  // chunks (0,1) then (2,3): two copies of the chunk code, not four
-        const uint32_t cb = col_base + half * 64;
-        tmem_ld_wait();                                   // even chunk in va
-        tmem_ld_32x32b_x32(t_buf + half * 64 + 32, vb);   // odd chunk in flight
-        if (kDebug) for (int j = 0; j < 32; ++j) dbg[half * 64 + j] = __uint_as_float(va[j]);
-        process_chunk(va, cb, rc, trigger, keep_lo, keep_hi);
-
-        tmem_ld_wait();                                   // odd chunk in vb
-        if (half == 0) {
-          tmem_ld_32x32b_x32(t_buf + 64, va);             // chunk 2 in flight
-        } else {
-          // this warp has read the whole buffer: hand it back, then start on the next tile
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty(buf));
-          if (it + 1 < n_tiles) {
-            const int nbuf = (it + 1) % kAccBufs;
-            mbar_wait(bar_acc_full(nbuf), (uint32_t)((it + 1) / kAccBufs) & 1u);
-            tc_fence_after();
-            tmem_ld_32x32b_x32(t_lane + (uint32_t)nbuf * kMmaTile, va);
-          }
-        }
-        if (kDebug) for (int j = 0; j < 32; ++j) dbg[half * 64 + 32 + j] = __uint_as_float(vb[j]);
-        process_chunk(vb, cb + 32, rc, trigger, keep_lo, keep_hi);
+      if (p.flags & 4) {  // probe: MMA pipeline alone, accumulators are never read
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+        if (it + 1 < n_tiles) mbar_wait(bar_acc_full((it + 1) % kAccBufs), (uint32_t)((it + 1) / kAccBufs) & 1u);
+        continue;
       }
+      tmem_ld_wait();                          // columns 0..63 in va
+      tmem_ld_32x32b_x64(t_buf + 64, vb);      // columns 64..127 in flight
+      if (kDebug) for (int j = 0; j < 64; ++j) dbg[j] = __uint_as_float(va[j]);
+      if (!(p.flags & 1)) process_half(va, col_base, rc, it, inv_tiles, p.k);
+
+      tmem_ld_wait();                          // columns 64..127 in vb
+      // this warp has read the whole buffer: hand it back, then start on the next tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+      if (it + 1 < n_tiles) {
+        const int nbuf = (it + 1) % kAccBufs;
+        mbar_wait(bar_acc_full(nbuf), (uint32_t)((it + 1) / kAccBufs) & 1u);
+        tc_fence_after();
+        tmem_ld_32x32b_x64(t_lane + (uint32_t)nbuf * kMmaTile, va);
+      }
+      if (kDebug) for (int j = 0; j < 64; ++j) dbg[64 + j] = __uint_as_float(vb[j]);
+      if (!(p.flags & 1)) process_half(vb, col_base + 64, rc, it, inv_tiles, p.k);
     }
-    {
-      int keep_lo, keep_hi;
-      keep_window(p.k, 1.f, keep_lo, keep_hi);
-      compact_row(rc, keep_lo, keep_hi);  // leave at most kCandOut entries
-    }
+    compact_row(rc, n_tiles, inv_tiles, p.k);  // f = 1: leave at most kCandOut entries
     const int64_t o = (q_row * p.splits + split);
     for (int e = 0; e < rc.cnt; ++e) {
       p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
@@ -754,12 +919,12 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
   pl.n_q_pad = pl.n_q_tiles * kMmaTile;
   pl.n_r_pad = pl.n_r_tiles * kMmaTile;
   pl.perm_mul = scramble_multiplier(pl.n_r_pad);
-  const size_t a_bytes = (size_t)kMmaTile * pl.kp_q * 2, b_bytes = (size_t)kMmaTile * pl.kp_r * 2;
+  const size_t b_bytes = (size_t)kMmaTile * pl.kp_r * 2;
   const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2;
   const size_t budget = 227 * 1024 - 1024;  // 1 KB of static shared memory (barriers, TMEM slot)
-  int stages = (int)((budget - cand_bytes - a_bytes) / b_bytes);
+  int stages = (int)((budget - cand_bytes) / b_bytes);
   pl.stages = stages > kMaxStages ? kMaxStages : stages;
-  pl.smem_bytes = a_bytes + b_bytes * pl.stages + cand_bytes;
+  pl.smem_bytes = b_bytes * pl.stages + cand_bytes;
   // enough CTAs for ~2 waves when the query side is small; every split keeps >= 4 reference tiles
   int64_t want = ceil_div(2 * kNumSMs, pl.n_q_tiles);
   int64_t cap = pl.n_r_tiles / 4 > 0 ? pl.n_r_tiles / 4 : 1;
@@ -838,6 +1003,8 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.cand_cnt = b.cand_cnt;
   p.cand_thr = b.cand_thr;
   p.debug_out = debug_out;
+  p.flags = g_probe_flags;
+  p.prof_out = g_probe_prof;
   const int64_t grid = pl.n_q_tiles * pl.splits;
   if (debug_out) {
     CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
@@ -919,6 +1086,8 @@ int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64
 }
 
 size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d) { return mma_workspace_bytes(n_q, n_r, d); }
+void set_probe_flags(int f) { g_probe_flags = f; }
+void set_probe_prof(long long* p) { g_probe_prof = p; }
 
 int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st);

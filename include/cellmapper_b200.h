@@ -160,6 +160,13 @@ int cm_profile_last_knn_ms(float* out4_host);
 int cm_debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                       float* scale_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* development probes of the tensor-core kernel (results become INVALID): bit 0 skips the epilogue
+ * math, bit 1 skips the reference-tile copies.  0 restores normal operation. */
+int cm_debug_probe_flags(int flags);
+/* device buffer of 8 int64 per CTA of the tensor-core kernel receiving the MMA warp's cycle counters
+ * [wait accumulator, wait reference tile, issue, total, tiles]; NULL switches it off. */
+int cm_debug_probe_prof(long long* device_buf);
+
 #ifdef __cplusplus
 }
 #endif
