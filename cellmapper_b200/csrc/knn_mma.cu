@@ -45,7 +45,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 #ifndef CM_WAIT_HINT_NS
-#define CM_WAIT_HINT_NS 100
+#define CM_WAIT_HINT_NS 20000
 #endif
 constexpr uint32_t kWaitHintNs = CM_WAIT_HINT_NS;
 // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the
@@ -239,7 +239,7 @@ constexpr float kNormColumn = 256.f;  // the constant c in the three norm column
 template <typename T>
 __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int64_t n_pad, int d, int kp, int dc,
                             const double* __restrict__ norms, const ScaleInfo* __restrict__ info, int is_query,
-                            uint64_t perm_mul, uint4* __restrict__ img) {
+                            const int32_t* __restrict__ perm, uint4* __restrict__ img) {
   const int chunks = kp >> 3;
   const float scale = scale_from_absmax(info->absmax_bits);
   const int64_t total = n_pad * chunks;
@@ -249,8 +249,9 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
     const int rem = (int)(t - group * 8 * chunks);
     const int chunk = rem >> 3, r8 = rem & 7;
     const int64_t pos = group * 8 + r8;
-    // image position -> source row: identity for queries, golden-ratio scramble for the reference
-    const int64_t row = perm_mul ? (int64_t)((perm_mul * (uint64_t)pos) % (uint64_t)n_pad) : pos;
+    // image position -> source row (scan order, see the "coarse cells" section); -1 = padding
+    const int64_t prow = perm[pos];
+    const int64_t row = prow < 0 ? n : prow;
     const int seg = chunk / dc;
     const int n_seg = is_query ? 3 : 2;
     __half h[8];
@@ -298,6 +299,176 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
 }
 
 // ------------------------------------------------------------------------------------------------
+// coarse cells: the order in which a query tile scans the reference
+//
+// The scan is exhaustive, so ANY order gives the exact answer; the order decides how fast the per-row
+// thresholds converge and with them how often the epilogue leaves its branch-free fast path.  With a
+// random order a row appends ~keep*ln(n/keep) candidates spread over the whole scan (at 100k
+// references every half tile of every warp holds several).  Instead both sides are bucketed by their
+// nearest of <= 256 pivots (reference rows at a fixed stride), the reference image is laid out cell by
+// cell, the queries are sorted by cell, and the scan of a query tile starts at the first tile of its
+// own cell and wraps around: the thresholds are tight after the home cell and the rest of the scan
+// runs on the fast path.  (A heuristic for speed only -- the certificate of the re-rank does not
+// depend on it.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxCells = 256;
+constexpr int kAssignThreads = 256;
+constexpr int kAssignMaxD = 56;  // >= the largest d of the tensor-core path (53)
+constexpr int kMinRefsForCells = 16384;  // below this the scan is short anyway: scrambled order, no cells
+
+// pivot j = reference row j * stride; stored transposed [d][n_cells] so 4 pivots are one 16-byte read
+template <typename T>
+__global__ void gather_pivots_kernel(const T* __restrict__ R, int64_t ldr, int64_t stride, int d, int n_cells,
+                                     float* __restrict__ piv_t, float* __restrict__ piv_norm) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cells) return;
+  const T* row = R + (int64_t)j * stride * ldr;
+  float nn = 0.f;
+  for (int c = 0; c < d; ++c) {
+    const float v = (float)row[c];
+    piv_t[(size_t)c * n_cells + j] = v;
+    nn = fmaf(v, v, nn);
+  }
+  piv_norm[j] = nn;
+}
+
+// nearest pivot of every row: argmin_j ||p_j||^2 - 2 x.p_j  (float32; only the scan order depends on it).
+// DP = d rounded up (zero padding) so that the inner loop is branch-free: the thread's row sits in
+// registers and every 4 FMAs cost one broadcast 16-byte read of the pivot table in shared memory.
+template <typename T, int DP>
+__global__ void __launch_bounds__(kAssignThreads)
+assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const float* __restrict__ piv_t,
+                    const float* __restrict__ piv_norm, int n_cells, uint8_t* __restrict__ cell,
+                    int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) float asm_smem[];
+  float* sp = asm_smem;                          // [DP][n_cells]
+  float* sn = sp + (size_t)DP * n_cells;         // [n_cells]
+  float* sx = sn + n_cells;                      // [DP][kAssignThreads]
+  __shared__ int hist[kMaxCells];
+  for (int i = threadIdx.x; i < DP * n_cells; i += blockDim.x) sp[i] = i < d * n_cells ? piv_t[i] : 0.f;
+  for (int i = threadIdx.x; i < n_cells; i += blockDim.x) sn[i] = piv_norm[i];
+  for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x) hist[i] = 0;
+  for (int i = threadIdx.x; i < DP * kAssignThreads; i += blockDim.x) sx[i] = 0.f;
+  __syncthreads();
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+    // coalesced stage of this block's rows, transposed: sx[c][thread]
+    const int rows_here = (int)min((int64_t)blockDim.x, n - base);
+    for (int i = threadIdx.x; i < rows_here * d; i += blockDim.x) {
+      const int r = i / d, c = i - r * d;
+      sx[c * kAssignThreads + r] = (float)X[(base + r) * ld + c];
+    }
+    __syncthreads();
+    if (threadIdx.x < rows_here) {
+      float x[DP];
+#pragma unroll
+      for (int c = 0; c < DP; ++c) x[c] = sx[c * kAssignThreads + threadIdx.x];
+      float best = CUDART_INF_F;
+      int best_j = 0;
+      for (int j0 = 0; j0 < n_cells; j0 += 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < DP; ++c) {
+          const float4 pv = *reinterpret_cast<const float4*>(sp + (size_t)c * n_cells + j0);
+          a0 = fmaf(x[c], pv.x, a0);
+          a1 = fmaf(x[c], pv.y, a1);
+          a2 = fmaf(x[c], pv.z, a2);
+          a3 = fmaf(x[c], pv.w, a3);
+        }
+        const float s0 = sn[j0] - 2.f * a0, s1 = sn[j0 + 1] - 2.f * a1, s2 = sn[j0 + 2] - 2.f * a2, s3 = sn[j0 + 3] - 2.f * a3;
+        if (s0 < best) { best = s0; best_j = j0; }
+        if (s1 < best) { best = s1; best_j = j0 + 1; }
+        if (s2 < best) { best = s2; best_j = j0 + 2; }
+        if (s3 < best) { best = s3; best_j = j0 + 3; }
+      }
+      cell[base + threadIdx.x] = (uint8_t)best_j;
+      atomicAdd(&hist[best_j], 1);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n_cells; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[i], hist[i]);
+}
+
+template <typename T, int DP>
+int launch_assign(const T* X, int64_t ld, int64_t n, int d, const float* piv_t, const float* piv_norm, int nc, uint8_t* cell,
+                  int32_t* counts, cudaStream_t st) {
+  const size_t smem = ((size_t)DP * nc + nc + (size_t)DP * kAssignThreads) * sizeof(float);
+  CM_CUDA_CHECK(cudaFuncSetAttribute(assign_cells_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(ceil_div(n, kAssignThreads) < kNumSMs * 2 ? ceil_div(n, kAssignThreads) : kNumSMs * 2);
+  assign_cells_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts);
+  CM_LAUNCH_CHECK("assign_cells_kernel");
+  return CM_OK;
+}
+template <typename T>
+int launch_assign_any(const T* X, int64_t ld, int64_t n, int d, const float* piv_t, const float* piv_norm, int nc,
+                      uint8_t* cell, int32_t* counts, cudaStream_t st) {
+  if (d <= 16) return launch_assign<T, 16>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
+  if (d <= 32) return launch_assign<T, 32>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
+  if (d <= 48) return launch_assign<T, 48>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
+  return launch_assign<T, kAssignMaxD>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
+}
+
+// exclusive scan of the two count arrays -> cell starts (+ a copy used as scatter cursor)
+__global__ void cell_scan_kernel(const int32_t* __restrict__ counts /*[2][kMaxCells]*/, int n_cells,
+                                 int32_t* __restrict__ starts /*[2][kMaxCells+1]*/, int32_t* __restrict__ cursor /*[2][kMaxCells]*/) {
+  if (threadIdx.x < 2) {
+    const int32_t* c = counts + threadIdx.x * kMaxCells;
+    int32_t* st = starts + threadIdx.x * (kMaxCells + 1);
+    int32_t* cu = cursor + threadIdx.x * kMaxCells;
+    int32_t run = 0;
+    for (int j = 0; j < n_cells; ++j) {
+      st[j] = run;
+      cu[j] = run;
+      run += c[j];
+    }
+    for (int j = n_cells; j <= kMaxCells; ++j) st[j] = run;
+  }
+}
+
+// counting-sort scatter: perm[position] = row.  One global atomic per (block, cell); the order inside
+// a cell is arbitrary (it only permutes candidates of equal rank in the scan).
+__global__ void __launch_bounds__(kAssignThreads)
+cell_scatter_kernel(const uint8_t* __restrict__ cell, int64_t n, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+  __shared__ int hist[kMaxCells];
+  __shared__ int base[kMaxCells];
+  for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += (int64_t)gridDim.x * blockDim.x) {
+    for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t row = b0 + threadIdx.x;
+    int c = -1, rank = 0;
+    if (row < n) {
+      c = cell[row];
+      rank = atomicAdd(&hist[c], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x)
+      if (hist[i]) base[i] = atomicAdd(&cursor[i], hist[i]);
+    __syncthreads();
+    if (row < n) perm[base[c] + rank] = (int32_t)row;
+    __syncthreads();
+  }
+}
+
+// home reference tile of every query tile: the tile holding the first reference of the cell of the
+// tile's first query
+__global__ void home_tile_kernel(const int32_t* __restrict__ perm_q, const uint8_t* __restrict__ q_cell,
+                                 const int32_t* __restrict__ r_starts, int n_q_tiles, int32_t* __restrict__ home) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_q_tiles) return;
+  const int32_t q0 = perm_q[(int64_t)t * kMmaTile];
+  home[t] = q0 >= 0 ? r_starts[q_cell[q0]] / kMmaTile : 0;
+}
+
+// without cells: queries in their own order, reference rows scrambled by a golden-ratio stride so that
+// any run of similar consecutive rows is spread evenly over the scan
+__global__ void fill_perm_kernel(int32_t* __restrict__ perm, int64_t n, int64_t n_pad, uint64_t mul) {
+  for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < n_pad; pos += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = mul ? (int64_t)((mul * (uint64_t)pos) % (uint64_t)n_pad) : pos;
+    perm[pos] = row < n ? (int32_t)row : -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-row candidate buffer in shared memory (one query row per epilogue thread)
 // layout inside a warp's region: keys[e][lane], idx[e][lane] (4-byte cells) -> conflict-free.
 // All accesses go through explicit ld/st.shared on 32-bit shared addresses.
@@ -320,93 +491,96 @@ struct RowCand {
   float thr;         // the same threshold as a float; +inf at start
 };
 
-// keys are stored as raw fp32 bit patterns (cheapest for the append path) and mapped to their
-// order-preserving uint image when the cold compaction code reads them
-__device__ __forceinline__ uint32_t lds_key(uint32_t addr) { return float_to_ordered(__uint_as_float(lds_u32(addr))); }
+// keys are stored as raw fp32 bit patterns and compared as floats; only pivots move between the float
+// and the order-preserving uint domain (bisection needs integer midpoints)
+__device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds_u32(addr)); }
 
-__device__ __forceinline__ int count_below(uint32_t keys, int cnt, uint32_t piv) {
+__device__ __forceinline__ int count_below(uint32_t keys, int cnt, float piv) {
   int c = 0;
   int e = 0;
   for (; e + 8 <= cnt; e += 8) {  // 8 independent loads in flight: one warp per scheduler, so ILP matters
-    uint32_t k0 = lds_key(keys + (e + 0) * kCandStride), k1 = lds_key(keys + (e + 1) * kCandStride);
-    uint32_t k2 = lds_key(keys + (e + 2) * kCandStride), k3 = lds_key(keys + (e + 3) * kCandStride);
-    uint32_t k4 = lds_key(keys + (e + 4) * kCandStride), k5 = lds_key(keys + (e + 5) * kCandStride);
-    uint32_t k6 = lds_key(keys + (e + 6) * kCandStride), k7 = lds_key(keys + (e + 7) * kCandStride);
+    const float k0 = lds_f32(keys + (e + 0) * kCandStride), k1 = lds_f32(keys + (e + 1) * kCandStride);
+    const float k2 = lds_f32(keys + (e + 2) * kCandStride), k3 = lds_f32(keys + (e + 3) * kCandStride);
+    const float k4 = lds_f32(keys + (e + 4) * kCandStride), k5 = lds_f32(keys + (e + 5) * kCandStride);
+    const float k6 = lds_f32(keys + (e + 6) * kCandStride), k7 = lds_f32(keys + (e + 7) * kCandStride);
     c += (k0 < piv) + (k1 < piv) + (k2 < piv) + (k3 < piv) + (k4 < piv) + (k5 < piv) + (k6 < piv) + (k7 < piv);
   }
-  for (; e < cnt; ++e) c += lds_key(keys + e * kCandStride) < piv;
+  for (; e < cnt; ++e) c += lds_f32(keys + e * kCandStride) < piv;
   return c;
 }
 
-// Adaptive keep window.  The reference rows are visited in a scrambled (golden-ratio stride) order,
-// so after a fraction f of a split has been seen the number of true top-k members among the seen
-// elements is Binomial(k, f).  Keeping k*f + 4.5 sigma + 8 candidates therefore loses a true
-// neighbour with probability ~1e-5 per row (caught by the certificate), while the threshold is as
-// tight as it can be from the very first tiles -- far fewer candidates pass than with a fixed window.
-__device__ __forceinline__ void keep_window(int k, float f, int& keep_lo, int& keep_hi) {
-  const float kf = (float)k * f;
-  int lo = (int)ceilf(kf + 4.5f * sqrtf(fmaxf(kf * (1.f - f), 0.f)) + 8.f);
-  int hi = min(lo + 14, kCandOut);
-  lo = min(lo, hi - 4);
-  keep_lo = lo;
-  keep_hi = hi;
+// Keep window: after a compaction a row holds between k + 6 and k + 20 candidates, never fewer than k,
+// so "everything below the threshold is in the buffer" holds for ANY scan order -- the order (home
+// cell first, see "coarse cells") only decides how quickly the threshold converges.
+__device__ __forceinline__ void keep_window(int k, int& keep_lo, int& keep_hi) {
+  keep_hi = min(k + 20, kCandOut);
+  keep_lo = min(k + 6, keep_hi - 4);
 }
 
 // Shrink the buffer to between keep_lo and keep_hi entries and tighten the threshold.  Selection,
-// not sorting: bisection on the ordered-uint key until the count below the pivot lands in the
-// window.  Ties that straddle the window are cut arbitrarily and the threshold is set to the tied
-// value (the row then keeps fewer strictly-below entries and, if it matters, fails its certificate).
+// not sorting: a bracketed search for a pivot whose rank lands in the window -- the first probes
+// interpolate (neighbour distances grow smoothly with rank, so they usually hit at once), then plain
+// bisection on the ordered-uint image of the key.  Ties that straddle the window are cut arbitrarily
+// and the threshold is set to the tied value (the row then keeps fewer strictly-below entries and, if
+// it matters, fails its certificate).
 // Cold code, deliberately NOT inlined: the hot epilogue loop has to stay inside the instruction cache.
 // Returns (new count) | (new threshold key << 32).
 __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint32_t idx, int cnt, uint32_t thr_key,
-                                                            int k, float f) {
+                                                            int k) {
   int keep_lo, keep_hi;
-  keep_window(k, f, keep_lo, keep_hi);
+  keep_window(k, keep_lo, keep_hi);
   if (cnt <= keep_hi) return (unsigned long long)(uint32_t)cnt | ((unsigned long long)thr_key << 32);
-  uint32_t lo = 0xFFFFFFFFu, mx = 0u;
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
   for (int e = 0; e < cnt; ++e) {
-    const uint32_t kx = lds_key(keys + e * kCandStride);
-    lo = min(lo, kx);
-    mx = max(mx, kx);
+    const float kx = lds_f32(keys + e * kCandStride);
+    mn = fminf(mn, kx);
+    mx = fmaxf(mx, kx);
   }
-  // invariants of the bisection: count(key < lo) < keep_lo ; count(key < hi) > keep_hi
-  uint32_t tl = mx;
-  bool tie = false;
-  int c = count_below(keys, cnt, mx);
-  int c_tl = c;
-  if (c <= keep_hi) {
-    tie = c < keep_lo;  // more than cnt - keep_lo entries share the maximum
-  } else {
-    uint32_t hi = mx;
-    bool found = false;
-    while (hi - lo > 1u) {
-      const uint32_t piv = lo + ((hi - lo) >> 1);
-      c = count_below(keys, cnt, piv);
-      if (c < keep_lo) {
-        lo = piv;
-      } else if (c > keep_hi) {
-        hi = piv;
-      } else {
-        tl = piv;
-        c_tl = c;
-        found = true;
-        break;
-      }
+  // bracket in the ordered domain: count(key < lo) = c_lo < keep_lo ; count(key < hi) = c_hi > keep_hi
+  uint32_t lo = float_to_ordered(mn), hi = float_to_ordered(mx) + 1u;  // keys are finite: no wrap
+  int c_lo = 0, c_hi = cnt;
+  uint32_t tl = hi;
+  int c_tl = cnt;
+  bool tie = false, found = false;
+  const float target = 0.5f * (float)(keep_lo + keep_hi);
+  for (int iter = 0; hi - lo > 1u; ++iter) {
+    uint32_t piv;
+    if (iter < 3) {
+      const float f_lo = ordered_to_float(lo), f_hi = ordered_to_float(hi - 1u);
+      const float frac = (target - (float)c_lo) / (float)(c_hi - c_lo);
+      piv = float_to_ordered(f_lo + (f_hi - f_lo) * frac);
+      piv = min(max(piv, lo + 1u), hi - 1u);
+    } else {
+      piv = lo + ((hi - lo) >> 1);
     }
-    if (!found) {  // keys equal to `lo` straddle the window
-      tl = lo;
-      c_tl = count_below(keys, cnt, lo);
-      tie = true;
+    const int c = count_below(keys, cnt, ordered_to_float(piv));
+    if (c < keep_lo) {
+      lo = piv;
+      c_lo = c;
+    } else if (c > keep_hi) {
+      hi = piv;
+      c_hi = c;
+    } else {
+      tl = piv;
+      c_tl = c;
+      found = true;
+      break;
     }
   }
+  if (!found) {  // keys equal to `lo` straddle the window
+    tl = lo;
+    c_tl = c_lo;
+    tie = true;
+  }
+  const float tl_f = ordered_to_float(tl);
   int extra = tie ? keep_hi - c_tl : 0;
   int w = 0;
   for (int e = 0; e < cnt; ++e) {
     const uint32_t raw = lds_u32(keys + e * kCandStride);
-    const uint32_t kx = float_to_ordered(__uint_as_float(raw));
+    const float kx = __uint_as_float(raw);
     const uint32_t ix = lds_u32(idx + e * kCandStride);
-    bool keep = kx < tl;
-    if (!keep && tie && kx == tl && extra > 0) {
+    bool keep = kx < tl_f;
+    if (!keep && tie && kx == tl_f && extra > 0) {
       keep = true;
       --extra;
     }
@@ -419,10 +593,8 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
   return (unsigned long long)(uint32_t)w | ((unsigned long long)tl << 32);
 }
 
-// `it` = index of the reference tile being drained, inv_tiles = 1 / tiles of this split
-__device__ __forceinline__ void compact_row(RowCand& rc, int it, float inv_tiles, int k) {
-  const unsigned long long r =
-      compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, k, fminf((float)(it + 1) * inv_tiles, 1.f));
+__device__ __forceinline__ void compact_row(RowCand& rc, int k) {
+  const unsigned long long r = compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, k);
   rc.cnt = (int)(uint32_t)r;
   rc.thr_key = (uint32_t)(r >> 32);
   rc.thr = rc.thr_key == 0xFFFFFFFFu ? CUDART_INF_F : ordered_to_float(rc.thr_key);
@@ -447,14 +619,16 @@ long long* g_probe_prof = nullptr;
 struct MmaParams {
   const unsigned char* q_img;  // n_q_tiles tiles of 128 x kp_q fp16
   const unsigned char* r_img;  // n_r_tiles tiles of 128 x kp_r fp16
-  int n_q_tiles, n_r_tiles, splits, kp_q, kp_r, dc, stages, k;
-  float* cand_s;      // [n_q_pad][splits][kCandOut]
+  int n_q_tiles, n_r_tiles, kp_q, kp_r, dc, stages, k;
+  int n_full, splits;  // work items: query tiles [0, n_full) scan the whole reference, the rest are cut in `splits`
+  float* cand_s;      // [n_items * 128][kCandOut], item = blockIdx.x
   int32_t* cand_i;    // same
-  int32_t* cand_cnt;  // [n_q_pad][splits]
-  float* cand_thr;    // [n_q_pad][splits]
+  int32_t* cand_cnt;  // [n_items * 128]
+  float* cand_thr;    // [n_items * 128]
   float* debug_out;   // optional raw accumulator dump [n_q_pad][n_r_tiles*128]
   int flags;          // development probes: 1 = skip the epilogue math, 2 = skip the reference tile copies
   long long* prof_out;  // optional [grid][8] cycle counters of the MMA warp (development)
+  const int32_t* home_tile;  // [n_q_tiles] reference tile at which the scan of a query tile starts (may be null)
 };
 
 // Append the elements of one leaf (<= 3 consecutive columns) that are below the row's threshold:
@@ -481,11 +655,12 @@ __device__ __forceinline__ void append_leaf(const uint32_t* v, uint32_t c0, RowC
 }
 
 // One 64-column half tile of one query row (thread = row).  Fast path: a depth-4 tree of 3-input
-// minima and ONE warp vote.  Slow path: descend the tree with warp-uniform votes (27 -> 9 -> 3
-// columns) and append only inside the leaves that hold a passing element, so its cost follows the
-// number of passing elements instead of the chunk width.
-__device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c0, RowCand& rc, int it, float inv_tiles,
-                                             int k) {
+// minima and ONE warp vote.  Slow path: every lane marks which of its 22 leaves (3 columns each) hold a
+// passing element, one REDUX.OR turns that into a warp-uniform leaf mask, and the append code of a leaf
+// runs only if its bit is set.  All tests of the descent read that one ready register -- the epilogue
+// has a single warp per scheduler, so a chain of compare -> vote -> branch per tree node would run at
+// branch latency, not at issue rate.
+__device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c0, RowCand& rc, int k, int flags) {
   float t[22];
 #pragma unroll
   for (int g = 0; g < 21; ++g)
@@ -495,30 +670,53 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
 #pragma unroll
   for (int g = 0; g < 7; ++g) u[g] = fminf(fminf(t[3 * g], t[3 * g + 1]), t[3 * g + 2]);
   u[7] = t[21];
-  float w[3];
-  w[0] = fminf(fminf(u[0], u[1]), u[2]);
-  w[1] = fminf(fminf(u[3], u[4]), u[5]);
-  w[2] = fminf(u[6], u[7]);
-  const float m = fminf(fminf(w[0], w[1]), w[2]);
-  if (__any_sync(0xffffffffu, m < rc.thr)) {
+  const float w0 = fminf(fminf(u[0], u[1]), u[2]);
+  const float w1 = fminf(fminf(u[3], u[4]), u[5]);
+  const float w2 = fminf(u[6], u[7]);
+  const float m = fminf(fminf(w0, w1), w2);
+  if (__any_sync(0xffffffffu, m < rc.thr) && !(flags & 16)) {  // probe 16: fast path only
+    const float thr0 = rc.thr;
+    // three partial masks so the bit-insert chains are 8 deep instead of 22
+    uint32_t ma = 0, mb = 0, mc = 0;
 #pragma unroll
-    for (int W = 0; W < 3; ++W) {
-      if (__any_sync(0xffffffffu, w[W] < rc.thr)) {
-        const float thr = rc.thr;
+    for (int T = 0; T < 8; ++T) ma |= (t[T] < thr0) ? (1u << T) : 0u;
 #pragma unroll
-        for (int U = 3 * W; U < 3 * W + 3 && U < 8; ++U) {
-          if (__any_sync(0xffffffffu, u[U] < thr)) {
-            if (U == 7) {
-              append_leaf<1>(&v[63], c0 + 63, rc, thr);
-            } else {
+    for (int T = 8; T < 16; ++T) mb |= (t[T] < thr0) ? (1u << T) : 0u;
 #pragma unroll
-              for (int T = 3 * U; T < 3 * U + 3; ++T)
-                if (__any_sync(0xffffffffu, t[T] < thr)) append_leaf<3>(&v[3 * T], c0 + 3 * T, rc, thr);
-            }
-          }
-        }
-        // at most 27 appends since the last check: cnt <= kCandTrigger + 27 <= kCandCap
-        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) compact_row(rc, it, inv_tiles, k);
+    for (int T = 16; T < 22; ++T) mc |= (t[T] < thr0) ? (1u << T) : 0u;
+    uint32_t leaves = __reduce_or_sync(0xffffffffu, ma | mb | mc);
+    // Loop over the flagged leaves only.  The switch just moves the leaf's three values into fixed
+    // registers (22 tiny cases behind one indexed branch); the append code exists once.  An unrolled
+    // `if (leaves & bit)` ladder costs a taken branch per skipped leaf and ran at instruction-fetch
+    // latency (ncu r1c: 62% "no instruction" stalls on those branches).
+    int since_check = 0;
+    while (leaves) {
+      const int T = __ffs((int)leaves) - 1;
+      leaves &= leaves - 1;
+      uint32_t x0, x1, x2;
+      switch (T) {
+#define CM_LEAF(i) case i: x0 = v[3 * i]; x1 = v[3 * i + 1]; x2 = v[3 * i + 2]; break;
+        CM_LEAF(0) CM_LEAF(1) CM_LEAF(2) CM_LEAF(3) CM_LEAF(4) CM_LEAF(5) CM_LEAF(6) CM_LEAF(7) CM_LEAF(8) CM_LEAF(9)
+        CM_LEAF(10) CM_LEAF(11) CM_LEAF(12) CM_LEAF(13) CM_LEAF(14) CM_LEAF(15) CM_LEAF(16) CM_LEAF(17) CM_LEAF(18)
+        CM_LEAF(19) CM_LEAF(20)
+#undef CM_LEAF
+        default: x0 = v[63]; x1 = x2 = 0x7F800000u; break;  // leaf 21 is the single column 63 (+inf never passes)
+      }
+      const float thr = rc.thr;  // may have been tightened by a compaction since the mask was built
+      const bool p0 = __uint_as_float(x0) < thr, p1 = __uint_as_float(x1) < thr, p2 = __uint_as_float(x2) < thr;
+      const uint32_t w0 = rc.keys + (uint32_t)rc.cnt * kCandStride;
+      const uint32_t w1 = w0 + (p0 ? kCandStride : 0u);
+      const uint32_t w2 = w1 + (p1 ? kCandStride : 0u);
+      const uint32_t idx_off = rc.idx - rc.keys;
+      const uint32_t col = c0 + 3u * (uint32_t)T;
+      if (p0) { sts_u32(w0, x0); sts_u32(w0 + idx_off, col); }
+      if (p1) { sts_u32(w1, x1); sts_u32(w1 + idx_off, col + 1); }
+      if (p2) { sts_u32(w2, x2); sts_u32(w2 + idx_off, col + 2); }
+      rc.cnt += (int)p0 + (int)p1 + (int)p2;
+      // at most 27 appends between checks: cnt <= kCandTrigger + 27 <= kCandCap
+      if (++since_check == 9 || leaves == 0) {
+        since_check = 0;
+        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) compact_row(rc, k);
       }
     }
   }
@@ -599,11 +797,24 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x / p.splits, split = blockIdx.x - q_tile * p.splits;
-  const int tiles_per_split = (p.n_r_tiles + p.splits - 1) / p.splits;
-  const int t_begin = split * tiles_per_split;
-  const int t_end = min(p.n_r_tiles, t_begin + tiles_per_split);
+  // Work items.  Whole waves of query tiles scan the full reference; the query tiles of the last,
+  // partial wave are cut into `splits` reference ranges so that they fill the machine too.
+  int q_tile = blockIdx.x, t_begin = 0, t_end = p.n_r_tiles;
+  if ((int)blockIdx.x >= p.n_full) {
+    const int j = blockIdx.x - p.n_full;
+    q_tile = p.n_full + j / p.splits;
+    const int split = j - (j / p.splits) * p.splits;
+    const int tiles_per_split = (p.n_r_tiles + p.splits - 1) / p.splits;
+    t_begin = split * tiles_per_split;
+    t_end = min(p.n_r_tiles, t_begin + tiles_per_split);
+  }
   const int n_tiles = max(0, t_end - t_begin);
+  // scan order: start at the query tile's home reference tile (its coarse cell), wrap around inside the split
+  int t_first = t_begin;
+  if (p.home_tile) {
+    const int h = p.home_tile[q_tile];
+    if (h >= t_begin && h < t_end) t_first = h;
+  }
 
   const uint32_t b_bytes = (uint32_t)kMmaTile * p.kp_r * 2;
   unsigned char* b_smem = smem;
@@ -641,7 +852,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     // ===== producer: bulk-async copies of whole operand tiles =====
     if (lane == 0 && n_tiles > 0) {
       const uint32_t piece = b_bytes / kLoadPieces;  // b_bytes = 4096 * dc: divisible by 4 * 16
-      int s = 0;
+      int s = 0, tcur = t_first;
       uint32_t ph = 0;
       for (int it = 0; it < n_tiles; ++it) {
         mbar_wait(bar_b_empty(s), ph ^ 1u);
@@ -649,12 +860,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
           mbar_arrive(bar_b_full(s));
         } else {
           mbar_expect_tx(bar_b_full(s), b_bytes);
-          const unsigned char* src = p.r_img + (size_t)(t_begin + it) * b_bytes;
+          const unsigned char* src = p.r_img + (size_t)tcur * b_bytes;
           const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
 #pragma unroll
           for (int c = 0; c < kLoadPieces; ++c) bulk_g2s(dst + c * piece, src + (size_t)c * piece, piece, bar_b_full(s));
         }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++tcur == t_end) tcur = t_begin;
       }
     }
   } else if (warp == 1 || warp == 6) {
@@ -695,7 +907,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     rc.thr_key = 0xFFFFFFFFu;
     rc.thr = CUDART_INF_F;
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
-    const float inv_tiles = 1.f / (float)max(n_tiles, 1);
     const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t t_lane = t_lane_a + kTmemACols;
     {
@@ -714,10 +925,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       tc_fence_after();
       tmem_ld_32x32b_x64(t_lane, va);
     }
+    int tcur = t_first;
 #pragma unroll 1
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it % kAccBufs;
-      const uint32_t col_base = (uint32_t)(t_begin + it) * kMmaTile;
+      const uint32_t col_base = (uint32_t)tcur * kMmaTile;
+      if (++tcur == t_end) tcur = t_begin;
       const uint32_t t_buf = t_lane + (uint32_t)buf * kMmaTile;
       float* dbg = kDebug ? p.debug_out + q_row * ((int64_t)p.n_r_tiles * kMmaTile) + col_base : nullptr;
 
@@ -730,7 +943,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       tmem_ld_wait();                          // columns 0..63 in va
       tmem_ld_32x32b_x64(t_buf + 64, vb);      // columns 64..127 in flight
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[j] = __uint_as_float(va[j]);
-      if (!(p.flags & 1)) process_half(va, col_base, rc, it, inv_tiles, p.k);
+      if (!(p.flags & 1)) process_half(va, col_base, rc, p.k, p.flags);
 
       tmem_ld_wait();                          // columns 64..127 in vb
       // this warp has read the whole buffer: hand it back, then start on the next tile
@@ -744,10 +957,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
         tmem_ld_32x32b_x64(t_lane + (uint32_t)nbuf * kMmaTile, va);
       }
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[64 + j] = __uint_as_float(vb[j]);
-      if (!(p.flags & 1)) process_half(vb, col_base + 64, rc, it, inv_tiles, p.k);
+      if (!(p.flags & 1)) process_half(vb, col_base + 64, rc, p.k, p.flags);
     }
-    compact_row(rc, n_tiles, inv_tiles, p.k);  // f = 1: leave at most kCandOut entries
-    const int64_t o = (q_row * p.splits + split);
+    compact_row(rc, p.k);  // leave at most kCandOut entries
+    const int64_t o = (int64_t)blockIdx.x * kMmaTile + row_in_tile;
     for (int e = 0; e < rc.cnt; ++e) {
       p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
       p.cand_i[o * kCandOut + e] = (int32_t)lds_u32(rc.idx + e * kCandStride);
@@ -767,60 +980,97 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
 // ------------------------------------------------------------------------------------------------
 // exact re-rank + certificate: one warp per query
 // ------------------------------------------------------------------------------------------------
-constexpr int kRerankWarps = 4;
-constexpr int kRerankNp = 512;  // >= kMaxSplits * kCandOut = 480 candidates per query
+constexpr int kRerankWarps = 8;
+constexpr int kRerankNp = 512;  // >= kMaxSplits * kCandOut = 480 candidates per query (the launch uses less when it can)
+constexpr int kStageRows = 16;  // candidate rows staged per batch (d <= 64: two elements per lane and row)
 static_assert(kMaxSplits * kCandOut <= kRerankNp, "re-rank buffer too small");
 
 template <typename T>
 __global__ void __launch_bounds__(kRerankWarps * 32)
 rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int64_t ldr, int64_t n_q, int64_t n_r, int d,
-              int k, int splits, const double* __restrict__ q_norms, const float* __restrict__ cand_s,
+              int k, int n_full, int splits, int np_max, const double* __restrict__ q_norms, const float* __restrict__ cand_s,
               const int32_t* __restrict__ cand_i, const int32_t* __restrict__ cand_cnt,
-              const float* __restrict__ cand_thr, ScaleInfo* info, uint64_t perm_mul, int64_t n_r_pad,
-              int64_t r_index_offset, int dist_mode,
+              const float* __restrict__ cand_thr, ScaleInfo* info, const int32_t* __restrict__ perm_q,
+              const int32_t* __restrict__ perm_r, int64_t r_index_offset, int dist_mode,
               double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* keys = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kRerankNp;
-  int* vals = reinterpret_cast<int*>(smem_raw + (size_t)kRerankWarps * kRerankNp * sizeof(double)) + (size_t)warp * kRerankNp;
-  double* qrow = reinterpret_cast<double*>(smem_raw + (size_t)kRerankWarps * kRerankNp * (sizeof(double) + sizeof(int))) +
+  double* keys = reinterpret_cast<double*>(smem_raw) + (size_t)warp * np_max;
+  int* vals = reinterpret_cast<int*>(smem_raw + (size_t)kRerankWarps * np_max * sizeof(double)) + (size_t)warp * np_max;
+  double* qrow = reinterpret_cast<double*>(smem_raw + (size_t)kRerankWarps * np_max * (sizeof(double) + sizeof(int))) +
                  (size_t)warp * d;
+  const int ds = d | 1;  // odd row stride of the staging slab: conflict-free column walks
+  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)kRerankWarps * (np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double))) +
+             (size_t)warp * kStageRows * ds;
   const double scale = (double)scale_from_absmax(info->absmax_bits);
   const double max_rnorm = __longlong_as_double((long long)info->max_rnorm_bits);
 
-  for (int64_t q = (int64_t)blockIdx.x * kRerankWarps + warp; q < n_q; q += (int64_t)gridDim.x * kRerankWarps) {
+  // qs = position of the query in the (cell-sorted) scan order, q = its row in the caller's arrays
+  for (int64_t qs = (int64_t)blockIdx.x * kRerankWarps + warp; qs < n_q; qs += (int64_t)gridDim.x * kRerankWarps) {
+    const int64_t q = perm_q[qs];
     for (int c = lane; c < d; c += 32) qrow[c] = (double)Q[q * ldq + c];
     __syncwarp();
     int total = 0;
     float thr_min = CUDART_INF_F;
-    for (int s = 0; s < splits; ++s) {
-      total += cand_cnt[q * splits + s];
-      thr_min = fminf(thr_min, cand_thr[q * splits + s]);
+    // the work items (CTAs of the tensor-core kernel) that hold this query's candidates
+    const int qt = (int)(qs / kMmaTile), qr = (int)(qs - (int64_t)qt * kMmaTile);
+    const int n_it = qt < n_full ? 1 : splits;
+    const int64_t item0 = qt < n_full ? qt : (int64_t)n_full + (int64_t)(qt - n_full) * splits;
+    for (int s = 0; s < n_it; ++s) {
+      total += cand_cnt[(item0 + s) * kMmaTile + qr];
+      thr_min = fminf(thr_min, cand_thr[(item0 + s) * kMmaTile + qr]);
     }
     int np = 64;  // >= kMmaMaxK so that keys[k-1] is always inside the sorted range
     while (np < total) np <<= 1;
-    // gather + exact float64 direct-difference distance, one candidate per lane
+    // candidate ids (scan position -> source row, -1 = padding)
     int filled = 0;
-    for (int s = 0; s < splits; ++s) {
-      const int c_s = cand_cnt[q * splits + s];
-      const int64_t o = (q * splits + s) * kCandOut;
-      for (int e = lane; e < c_s; e += 32) {
-        const int pos = cand_i[o + e];
-        const int id = (int)((perm_mul * (uint64_t)pos) % (uint64_t)n_r_pad);  // scan position -> source row
-        double d2 = CUDART_INF;
-        if (id >= 0 && id < n_r) {
-          const T* rp = R + (int64_t)id * ldr;
-          double acc = 0.0;
-          for (int c = 0; c < d; ++c) {
-            const double df = (double)rp[c] - qrow[c];
-            acc = fma(df, df, acc);
-          }
-          d2 = acc;
-        }
-        keys[filled + e] = d2;
-        vals[filled + e] = id;
-      }
+    for (int s = 0; s < n_it; ++s) {
+      const int c_s = cand_cnt[(item0 + s) * kMmaTile + qr];
+      const int64_t o = ((item0 + s) * kMmaTile + qr) * kCandOut;
+      for (int e = lane; e < c_s; e += 32) vals[filled + e] = perm_r[cand_i[o + e]];
       filled += c_s;
+    }
+    __syncwarp();
+    // exact float64 direct-difference distances, kStageRows candidates at a time: the warp copies the
+    // candidate rows with coalesced loads (all loads of a batch in flight before the first store) into
+    // its staging slab, then lane l reduces candidate l
+    for (int base = 0; base < filled; base += kStageRows) {
+      const int my_id = (lane < kStageRows && base + lane < filled) ? vals[base + lane] : -1;
+      const bool my_ok = my_id >= 0 && my_id < n_r;
+      T r0[kStageRows], r1[kStageRows];
+#pragma unroll
+      for (int j = 0; j < kStageRows; ++j) {
+        const int idj = __shfl_sync(0xffffffffu, my_id, j);
+        const T* rp = R + (int64_t)((idj >= 0 && idj < n_r) ? idj : 0) * ldr;
+        r0[j] = lane < d ? rp[lane] : (T)0;
+        r1[j] = lane + 32 < d ? rp[lane + 32] : (T)0;
+      }
+#pragma unroll
+      for (int j = 0; j < kStageRows; ++j) {
+        if (lane < d) stage[j * ds + lane] = r0[j];
+        if (lane + 32 < d) stage[j * ds + lane + 32] = r1[j];
+      }
+      __syncwarp();
+      if (lane < kStageRows && base + lane < filled) {
+        double d2 = CUDART_INF;
+        if (my_ok) {
+          const T* sp = stage + lane * ds;
+          double acc0 = 0.0, acc1 = 0.0;
+          int c = 0;
+          for (; c + 2 <= d; c += 2) {
+            const double df0 = (double)sp[c] - qrow[c], df1 = (double)sp[c + 1] - qrow[c + 1];
+            acc0 = fma(df0, df0, acc0);
+            acc1 = fma(df1, df1, acc1);
+          }
+          if (c < d) {
+            const double df = (double)sp[c] - qrow[c];
+            acc0 = fma(df, df, acc0);
+          }
+          d2 = acc0 + acc1;
+        }
+        keys[base + lane] = d2;
+      }
+      __syncwarp();
     }
     for (int t = filled + lane; t < np; t += 32) {
       keys[t] = CUDART_INF;
@@ -877,8 +1127,10 @@ __global__ void publish_stats_kernel(const ScaleInfo* info, int64_t* stats_out) 
 }
 
 struct MmaPlan {
-  uint64_t perm_mul;  // image position p holds reference row (perm_mul * p) mod n_r_pad
+  uint64_t perm_mul;  // no cells: image position p holds reference row (perm_mul * p) mod n_r_pad
+  int n_cells;        // 0 = no coarse cells
   int kp_q, kp_r, dc, stages, splits;
+  int64_t n_full, n_items;  // query tiles scanned by one CTA each; total CTAs
   int64_t n_q_tiles, n_r_tiles, n_q_pad, n_r_pad;
   size_t smem_bytes;
 };
@@ -919,18 +1171,26 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
   pl.n_q_pad = pl.n_q_tiles * kMmaTile;
   pl.n_r_pad = pl.n_r_tiles * kMmaTile;
   pl.perm_mul = scramble_multiplier(pl.n_r_pad);
+  pl.n_cells = n_r >= kMinRefsForCells ? kMaxCells : 0;
   const size_t b_bytes = (size_t)kMmaTile * pl.kp_r * 2;
   const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2;
   const size_t budget = 227 * 1024 - 1024;  // 1 KB of static shared memory (barriers, TMEM slot)
   int stages = (int)((budget - cand_bytes) / b_bytes);
   pl.stages = stages > kMaxStages ? kMaxStages : stages;
   pl.smem_bytes = b_bytes * pl.stages + cand_bytes;
-  // enough CTAs for ~2 waves when the query side is small; every split keeps >= 4 reference tiles
-  int64_t want = ceil_div(2 * kNumSMs, pl.n_q_tiles);
-  int64_t cap = pl.n_r_tiles / 4 > 0 ? pl.n_r_tiles / 4 : 1;
-  int64_t s = want < cap ? want : cap;
-  if (s > kMaxSplits) s = kMaxSplits;
-  if (s < 1) s = 1;
+  // whole waves of query tiles take one CTA each; the tail (or a small query side) is cut into reference
+  // ranges of >= 8 tiles so that its CTAs fill the machine once more
+  pl.n_full = (pl.n_q_tiles / kNumSMs) * kNumSMs;
+  const int64_t tail = pl.n_q_tiles - pl.n_full;
+  int64_t s = 1;
+  if (tail > 0) {
+    s = pl.n_full > 0 ? kNumSMs / tail : ceil_div(2 * kNumSMs, tail);
+    const int64_t cap = pl.n_r_tiles / 8 > 0 ? pl.n_r_tiles / 8 : 1;
+    if (s > cap) s = cap;
+    if (s > kMaxSplits) s = kMaxSplits;
+    if (s < 1) s = 1;
+  }
+  pl.n_items = pl.n_full + tail * s;
   pl.splits = (int)s;
   return pl;
 }
@@ -946,6 +1206,16 @@ struct MmaBuffers {
   int32_t* cand_cnt;
   float* cand_thr;
   int32_t* fail_rows;
+  int32_t* perm_q;      // [n_q_pad] scan position -> query row, -1 = padding
+  int32_t* perm_r;      // [n_r_pad] scan position -> reference row, -1 = padding
+  int32_t* home_tile;   // [n_q_tiles]
+  uint8_t* q_cell;      // [n_q]
+  uint8_t* r_cell;      // [n_r]
+  float* piv_t;         // [d][kMaxCells]
+  float* piv_norm;      // [kMaxCells]
+  int32_t* cell_counts; // [2][kMaxCells]  (0 = reference, 1 = query)
+  int32_t* cell_starts; // [2][kMaxCells + 1]
+  int32_t* cell_cursor; // [2][kMaxCells]
 };
 
 MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
@@ -955,11 +1225,21 @@ MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
   b.r_norms = ws.take<double>(n_r);
   b.q_img = ws.take<unsigned char>((size_t)pl.n_q_pad * pl.kp_q * 2);
   b.r_img = ws.take<unsigned char>((size_t)pl.n_r_pad * pl.kp_r * 2);
-  b.cand_s = ws.take<float>((size_t)pl.n_q_pad * pl.splits * kCandOut);
-  b.cand_i = ws.take<int32_t>((size_t)pl.n_q_pad * pl.splits * kCandOut);
-  b.cand_cnt = ws.take<int32_t>((size_t)pl.n_q_pad * pl.splits);
-  b.cand_thr = ws.take<float>((size_t)pl.n_q_pad * pl.splits);
+  b.cand_s = ws.take<float>((size_t)pl.n_items * kMmaTile * kCandOut);
+  b.cand_i = ws.take<int32_t>((size_t)pl.n_items * kMmaTile * kCandOut);
+  b.cand_cnt = ws.take<int32_t>((size_t)pl.n_items * kMmaTile);
+  b.cand_thr = ws.take<float>((size_t)pl.n_items * kMmaTile);
   b.fail_rows = ws.take<int32_t>(n_q);
+  b.perm_q = ws.take<int32_t>(pl.n_q_pad);
+  b.perm_r = ws.take<int32_t>(pl.n_r_pad);
+  b.home_tile = ws.take<int32_t>(pl.n_q_tiles);
+  b.q_cell = ws.take<uint8_t>(n_q);
+  b.r_cell = ws.take<uint8_t>(n_r);
+  b.piv_t = ws.take<float>((size_t)kMaxCells * 64);
+  b.piv_norm = ws.take<float>(kMaxCells);
+  b.cell_counts = ws.take<int32_t>(2 * kMaxCells);
+  b.cell_starts = ws.take<int32_t>(2 * (kMaxCells + 1));
+  b.cell_cursor = ws.take<int32_t>(2 * kMaxCells);
   return b;
 }
 
@@ -974,13 +1254,44 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
   CM_LAUNCH_CHECK("rowstats_kernel(Q)");
   rowstats_kernel<T><<<gr, wpb * 32, 0, st>>>(R, ldr, n_r, d, b.r_norms, b.info, 1);
   CM_LAUNCH_CHECK("rowstats_kernel(R)");
+  // scan order
+  if (pl.n_cells > 0) {
+    const int nc = pl.n_cells;
+    CM_CUDA_CHECK(cudaMemsetAsync(b.cell_counts, 0, 2 * kMaxCells * sizeof(int32_t), st));
+    CM_CUDA_CHECK(cudaMemsetAsync(b.perm_q, 0xFF, (size_t)pl.n_q_pad * sizeof(int32_t), st));
+    CM_CUDA_CHECK(cudaMemsetAsync(b.perm_r, 0xFF, (size_t)pl.n_r_pad * sizeof(int32_t), st));
+    gather_pivots_kernel<T><<<ceil_div(nc, 128), 128, 0, st>>>(R, ldr, n_r / nc, d, nc, b.piv_t, b.piv_norm);
+    CM_LAUNCH_CHECK("gather_pivots_kernel");
+    int rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, st);
+    if (rc_a) return rc_a;
+    rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, st);
+    if (rc_a) return rc_a;
+    cell_scan_kernel<<<1, 32, 0, st>>>(b.cell_counts, nc, b.cell_starts, b.cell_cursor);
+    CM_LAUNCH_CHECK("cell_scan_kernel");
+    const int gs_r = (int)(ceil_div(n_r, kAssignThreads) < kNumSMs * 8 ? ceil_div(n_r, kAssignThreads) : kNumSMs * 8);
+    const int gs_q = (int)(ceil_div(n_q, kAssignThreads) < kNumSMs * 8 ? ceil_div(n_q, kAssignThreads) : kNumSMs * 8);
+    cell_scatter_kernel<<<gs_r, kAssignThreads, 0, st>>>(b.r_cell, n_r, b.cell_cursor, b.perm_r);
+    CM_LAUNCH_CHECK("cell_scatter_kernel(R)");
+    cell_scatter_kernel<<<gs_q, kAssignThreads, 0, st>>>(b.q_cell, n_q, b.cell_cursor + kMaxCells, b.perm_q);
+    CM_LAUNCH_CHECK("cell_scatter_kernel(Q)");
+    home_tile_kernel<<<(unsigned)ceil_div(pl.n_q_tiles, 128), 128, 0, st>>>(b.perm_q, b.q_cell, b.cell_starts,
+                                                                           (int)pl.n_q_tiles, b.home_tile);
+    CM_LAUNCH_CHECK("home_tile_kernel");
+  } else {
+    fill_perm_kernel<<<(unsigned)(ceil_div(pl.n_q_pad, 256) < kNumSMs * 8 ? ceil_div(pl.n_q_pad, 256) : kNumSMs * 8), 256, 0, st>>>(
+        b.perm_q, n_q, pl.n_q_pad, 0ULL);
+    CM_LAUNCH_CHECK("fill_perm_kernel(Q)");
+    fill_perm_kernel<<<(unsigned)(ceil_div(pl.n_r_pad, 256) < kNumSMs * 8 ? ceil_div(pl.n_r_pad, 256) : kNumSMs * 8), 256, 0, st>>>(
+        b.perm_r, n_r, pl.n_r_pad, pl.perm_mul);
+    CM_LAUNCH_CHECK("fill_perm_kernel(R)");
+  }
   int64_t tq = pl.n_q_pad * (pl.kp_q / 8), tr = pl.n_r_pad * (pl.kp_r / 8);
   int bq = (int)(ceil_div(tq, 256) < kNumSMs * 16 ? ceil_div(tq, 256) : kNumSMs * 16);
   int br = (int)(ceil_div(tr, 256) < kNumSMs * 16 ? ceil_div(tr, 256) : kNumSMs * 16);
-  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q, pl.dc, b.q_norms, b.info, 1, 0ULL,
+  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q, pl.dc, b.q_norms, b.info, 1, b.perm_q,
                                      reinterpret_cast<uint4*>(b.q_img));
   CM_LAUNCH_CHECK("prep_kernel(Q)");
-  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r, pl.dc, b.r_norms, b.info, 0, pl.perm_mul,
+  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r, pl.dc, b.r_norms, b.info, 0, b.perm_r,
                                      reinterpret_cast<uint4*>(b.r_img));
   CM_LAUNCH_CHECK("prep_kernel(R)");
   return CM_OK;
@@ -993,6 +1304,7 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.n_q_tiles = (int)pl.n_q_tiles;
   p.n_r_tiles = (int)pl.n_r_tiles;
   p.splits = pl.splits;
+  p.n_full = (int)pl.n_full;
   p.kp_q = pl.kp_q;
   p.kp_r = pl.kp_r;
   p.dc = pl.dc;
@@ -1005,7 +1317,8 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.debug_out = debug_out;
   p.flags = g_probe_flags;
   p.prof_out = g_probe_prof;
-  const int64_t grid = pl.n_q_tiles * pl.splits;
+  p.home_tile = pl.n_cells > 0 ? b.home_tile : nullptr;
+  const int64_t grid = pl.n_items;
   if (debug_out) {
     CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
     mma_topk_kernel<true><<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);
@@ -1021,13 +1334,16 @@ template <typename T>
 int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int64_t ldr, int d, int k,
                const MmaPlan& pl, const MmaBuffers& b, int64_t r_off, int dist_mode, double* out_dist,
                int64_t* out_idx, cudaStream_t st) {
-  size_t smem = (size_t)kRerankWarps * (kRerankNp * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double));
+  int np_max = 64;  // power of two >= the candidates one query can have and >= kMmaMaxK
+  while (np_max < (pl.n_items > pl.n_full ? pl.splits : 1) * kCandOut) np_max <<= 1;
+  size_t smem = (size_t)kRerankWarps * (np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double) +
+                                       (size_t)kStageRows * (d | 1) * sizeof(T));
   CM_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = ceil_div(n_q, kRerankWarps);
   int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
-  rerank_kernel<T><<<grid, kRerankWarps * 32, smem, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, pl.splits, b.q_norms,
+  rerank_kernel<T><<<grid, kRerankWarps * 32, smem, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, (int)pl.n_full, pl.splits, np_max, b.q_norms,
                                                          b.cand_s, b.cand_i, b.cand_cnt, b.cand_thr, b.info,
-                                                         pl.perm_mul, pl.n_r_pad, r_off, dist_mode, out_dist, out_idx,
+                                                         b.perm_q, b.perm_r, r_off, dist_mode, out_dist, out_idx,
                                                          b.fail_rows);
   CM_LAUNCH_CHECK("rerank_kernel");
   return CM_OK;
@@ -1100,7 +1416,10 @@ int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st) {
   MmaPlan pl = make_plan(n_q, n_r, d);
   pl.splits = 1;
+  pl.n_full = 0;
+  pl.n_items = pl.n_q_tiles;
   pl.perm_mul = 1;  // identity order: the dump is indexed by source row
+  pl.n_cells = 0;
   Workspace ws(workspace, ws_bytes);
   MmaBuffers b = carve(ws, pl, n_q, n_r);
   if (!ws.ok()) {
