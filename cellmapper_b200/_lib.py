@@ -42,7 +42,8 @@ SIGNATURES = {
     "cm_spmm_csr_dense": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, c_int, _P, c_int64, _P]),
     "cm_spgemm_count": (c_int, [_P, _P, c_int64, _P, _P, c_int32, _P, _P]),
     "cm_spgemm_fill": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P, _P, _P]),
-    "cm_reverse_lists": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P]),
+    "cm_reverse_lists_workspace_bytes": (c_size_t, [c_int64]),
+    "cm_reverse_lists": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P, c_size_t, _P]),
     "cm_jaccard_count": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
     "cm_jaccard_fill": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, c_int, _P, _P, _P, _P]),
     "cm_launch_count": (c_int64, []),
@@ -98,8 +99,15 @@ def check(rc: int, what: str) -> None:
     raise RuntimeError(f"{what} failed (status {rc}): {msg}")
 
 
+_checked_devices: set[int] = set()
+
+
 def require_device(device_index: int) -> None:
-    """Fail loudly unless CUDA + an sm_100 device + the native library are all present."""
+    """Fail loudly unless CUDA + an sm_100 device + the native library are all present.
+    The answer for a device cannot change within a process, so a passed check is remembered
+    (cudaGetDeviceProperties costs ~2.5 ms per call)."""
+    if int(device_index) in _checked_devices:
+        return
     import torch
 
     if not torch.cuda.is_available():
@@ -107,3 +115,4 @@ def require_device(device_index: int) -> None:
             "method='b200' needs a CUDA device (NVIDIA B200, sm_100a); none is visible and there is no CPU fallback."
         )
     check(load().cm_device_check(int(device_index)), "cm_device_check")
+    _checked_devices.add(int(device_index))

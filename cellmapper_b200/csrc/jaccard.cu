@@ -1,0 +1,294 @@
+// P2': jaccard / hnoca mapping matrix.  Replaces (cellmapper.py:287-301)
+//     J = yx @ xx.T + yy @ xy.T ;  J.data /= 4k - J.data   |   J.data /= 2k - J.data; J.data **= 2
+// on the 0/1 adjacencies of the four k-NN graphs (knn.py:228-266, 467-483):
+//     J[i, j] = |N_ref(q_i) & N_ref(r_j)| + |N_qry(q_i) & N_qry(r_j)|      (shared-neighbour counts)
+// Integer work.  Row i of J is the multiset union of the REVERSE neighbour lists
+//     RevXX(a) = { j : a in xx[j] }  for a in yx[i]      and      RevXY(b) = { j : b in xy[j] }  for b in yy[i],
+// each reverse list sorted, so one warp produces a row -- columns ascending, counts exact -- by a 2k-way merge
+// (`redux.sync.min` over the list heads).  No hash table, no capacity limit, deterministic.
+#include "common.cuh"
+
+namespace cm {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// reverse neighbour lists: (n, k) int64 indices -> CSR-like (indptr, rows) by target, rows ascending
+// ------------------------------------------------------------------------------------------------
+__global__ void rev_count_kernel(const int64_t* __restrict__ idx, int64_t n_edges, int64_t n_targets,
+                                 int32_t* __restrict__ counts /* indptr + 1 */) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx[e];
+    if (t >= 0 && t < n_targets) atomicAdd(&counts[t], 1);  // -1 = padding of ragged graphs (knn.py:68-77)
+  }
+}
+
+constexpr int kScanBlock = 1024;
+__global__ void scan_local_kernel(int32_t* a, int64_t n, int32_t* block_sums) {
+  __shared__ int32_t sh[kScanBlock];
+  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  sh[threadIdx.x] = i < n ? a[i] : 0;
+  __syncthreads();
+  for (int o = 1; o < kScanBlock; o <<= 1) {
+    int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  if (i < n) a[i] = sh[threadIdx.x];
+  if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void scan_sums_kernel(int32_t* block_sums, int64_t nb) {
+  __shared__ int32_t sh[kScanBlock];
+  int32_t carry = 0;
+  for (int64_t base = 0; base < nb; base += kScanBlock) {
+    const int64_t i = base + threadIdx.x;
+    sh[threadIdx.x] = i < nb ? block_sums[i] : 0;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+      int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (i < nb) block_sums[i] = sh[threadIdx.x] + carry;
+    carry += sh[kScanBlock - 1];
+    __syncthreads();
+  }
+}
+__global__ void scan_add_kernel(int32_t* a, int64_t n, const int32_t* block_sums) {
+  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  if (blockIdx.x > 0 && i < n) a[i] += block_sums[blockIdx.x - 1];
+}
+
+// cursor[t] = indptr[t]: the fill reserves slots with atomics, the per-list sort below restores order
+__global__ void rev_fill_kernel(const int64_t* __restrict__ idx, int64_t n, int k, int64_t n_targets,
+                                int32_t* __restrict__ cursor, int32_t* __restrict__ rows) {
+  const int64_t n_edges = n * k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx[e];
+    if (t >= 0 && t < n_targets) rows[atomicAdd(&cursor[t], 1)] = (int32_t)(e / k);
+  }
+}
+
+// ascending sort of every reverse list: short lists (<= kSortSmem) by one warp in shared memory, long ones (hubs)
+// by a whole block in place in global memory.  Both use the ascending-only bitonic network that is valid for any
+// length when slots beyond the end count as +inf.
+constexpr int kSortWarps = 8;
+constexpr int kSortSmem = 256;  // elements per warp slab
+
+__device__ __forceinline__ void bitonic_step(int32_t* a, int n, int np, int tid, int nthreads, bool block_sync) {
+  for (int size = 2; size <= np; size <<= 1) {
+    const int half = size >> 1;
+    for (int t = tid; t < (np >> 1); t += nthreads) {
+      const int blk = t / half, off = t - blk * half;
+      const int i = blk * size + off, j = blk * size + size - 1 - off;
+      if (j < n) {
+        const int32_t x = a[i], y = a[j];
+        if (y < x) { a[i] = y; a[j] = x; }
+      }
+    }
+    if (block_sync) __syncthreads(); else __syncwarp();
+    for (int stride = size >> 2; stride >= 1; stride >>= 1) {
+      for (int t = tid; t < (np >> 1); t += nthreads) {
+        const int i = 2 * stride * (t / stride) + (t % stride), j = i + stride;
+        if (j < n) {
+          const int32_t x = a[i], y = a[j];
+          if (y < x) { a[i] = y; a[j] = x; }
+        }
+      }
+      if (block_sync) __syncthreads(); else __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSortWarps * 32)
+rev_sort_short_kernel(const int32_t* __restrict__ indptr, int64_t n_targets, int32_t* __restrict__ rows) {
+  __shared__ int32_t slab[kSortWarps][kSortSmem];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t t = (int64_t)blockIdx.x * kSortWarps + warp; t < n_targets; t += (int64_t)gridDim.x * kSortWarps) {
+    const int32_t lo = indptr[t], n = indptr[t + 1] - lo;
+    if (n < 2 || n > kSortSmem) continue;
+    for (int i = lane; i < n; i += 32) slab[warp][i] = rows[lo + i];
+    __syncwarp();
+    int np = 2;
+    while (np < n) np <<= 1;
+    bitonic_step(slab[warp], n, np, lane, 32, false);
+    for (int i = lane; i < n; i += 32) rows[lo + i] = slab[warp][i];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rev_sort_long_kernel(const int32_t* __restrict__ indptr, int64_t n_targets, int32_t* __restrict__ rows) {
+  for (int64_t t = blockIdx.x; t < n_targets; t += gridDim.x) {
+    const int32_t lo = indptr[t], n = indptr[t + 1] - lo;
+    if (n <= kSortSmem) continue;  // block-uniform
+    int np = 2;
+    while (np < n) np <<= 1;
+    bitonic_step(rows + lo, n, np, threadIdx.x, blockDim.x, true);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the merge: one warp per query row, list l of the row = reverse list of its l-th neighbour
+// ------------------------------------------------------------------------------------------------
+constexpr int kJacWarps = 4;
+
+template <int L, bool kFill>  // L = lists per lane: 2k <= 32 * L
+__global__ void __launch_bounds__(kJacWarps * 32)
+jaccard_kernel(const int64_t* __restrict__ yx, const int64_t* __restrict__ yy, int64_t n_q, int k, int64_t n_r,
+               const int32_t* __restrict__ rxx_indptr, const int32_t* __restrict__ rxx_rows,
+               const int32_t* __restrict__ rxy_indptr, const int32_t* __restrict__ rxy_rows, int hnoca,
+               int32_t* __restrict__ out_row_nnz, const int32_t* __restrict__ out_indptr, int32_t* __restrict__ out_cols,
+               double* __restrict__ out_vals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const double denom_k = hnoca ? 2.0 * k : 4.0 * k;  // cellmapper.py:297,299
+  for (int64_t row = warp0; row < n_q; row += nwarps) {
+    const int32_t* ptr[L];
+    const int32_t* end[L];
+    uint32_t head[L];
+#pragma unroll
+    for (int s = 0; s < L; ++s) {
+      const int l = lane + 32 * s;
+      ptr[s] = end[s] = nullptr;
+      if (l < 2 * k) {
+        const bool first = l < k;
+        const int64_t a = first ? yx[row * k + l] : yy[row * k + (l - k)];
+        const int64_t n_targets = first ? n_r : n_q;
+        if (a >= 0 && a < n_targets) {
+          const int32_t* ip = first ? rxx_indptr : rxy_indptr;
+          const int32_t* rw = first ? rxx_rows : rxy_rows;
+          ptr[s] = rw + ip[a];
+          end[s] = rw + ip[a + 1];
+        }
+      }
+      head[s] = ptr[s] < end[s] ? (uint32_t)*ptr[s] : 0xFFFFFFFFu;
+    }
+    int64_t o = kFill ? out_indptr[row] : 0;
+    int n_out = 0;
+    while (true) {
+      uint32_t m = head[0];
+#pragma unroll
+      for (int s = 1; s < L; ++s) m = min(m, head[s]);
+      m = __reduce_min_sync(0xffffffffu, m);
+      if (m == 0xFFFFFFFFu) break;
+      int c = 0;
+#pragma unroll
+      for (int s = 0; s < L; ++s) {
+        while (head[s] == m) {  // duplicates inside one list = adjacency entries > 1 (summed duplicates of the COO build)
+          ++c;
+          ++ptr[s];
+          head[s] = ptr[s] < end[s] ? (uint32_t)*ptr[s] : 0xFFFFFFFFu;
+        }
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (kFill && lane == 0) {
+        const double j = (double)c;
+        double v = j / (denom_k - j);
+        if (hnoca) v = v * v;
+        out_cols[o + n_out] = (int32_t)m;
+        out_vals[o + n_out] = v;
+      }
+      ++n_out;
+    }
+    if (!kFill && lane == 0) out_row_nnz[row] = n_out;
+  }
+}
+
+template <bool kFill>
+int launch_jaccard(const int64_t* yx, const int64_t* yy, int64_t n_q, int k, int64_t n_r, const int32_t* rxx_indptr,
+                   const int32_t* rxx_rows, const int32_t* rxy_indptr, const int32_t* rxy_rows, int hnoca,
+                   int32_t* out_row_nnz, const int32_t* out_indptr, int32_t* out_cols, double* out_vals, cudaStream_t st) {
+  CM_REQUIRE(yx && yy && rxx_indptr && rxx_rows && rxy_indptr && rxy_rows, "null pointer argument");
+  CM_REQUIRE(n_q >= 0 && k >= 1 && 2 * k <= 256, "jaccard supports 1 <= k <= 128 (got %d)", k);
+  if (n_q == 0) return CM_OK;
+  const int64_t blocks = ceil_div(n_q, kJacWarps);
+  const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  const int lists = 2 * k;
+#define CM_JAC(L)                                                                                                     \
+  jaccard_kernel<L, kFill><<<grid, kJacWarps * 32, 0, st>>>(yx, yy, n_q, k, n_r, rxx_indptr, rxx_rows, rxy_indptr,    \
+                                                            rxy_rows, hnoca, out_row_nnz, out_indptr, out_cols, out_vals)
+  if (lists <= 32) CM_JAC(1);
+  else if (lists <= 64) CM_JAC(2);
+  else if (lists <= 128) CM_JAC(4);
+  else CM_JAC(8);
+#undef CM_JAC
+  CM_LAUNCH_CHECK("jaccard_kernel");
+  return CM_OK;
+}
+
+}  // namespace
+}  // namespace cm
+
+using namespace cm;
+
+extern "C" size_t cm_reverse_lists_workspace_bytes(int64_t n_targets) {
+  return align_up((size_t)(n_targets + 1) * sizeof(int32_t), 256) + align_up((size_t)(ceil_div(n_targets, kScanBlock) + 1) * sizeof(int32_t), 256);
+}
+
+extern "C" int cm_reverse_lists(const int64_t* idx, int64_t n, int k, int64_t n_targets, int32_t* out_indptr,
+                                int32_t* out_rows, void* workspace, size_t workspace_bytes, void* stream) {
+  CM_REQUIRE(idx && out_indptr && out_rows && workspace, "null pointer argument");
+  CM_REQUIRE(n >= 0 && k >= 1 && n_targets >= 1, "bad reverse-list shape");
+  CM_REQUIRE(n * (int64_t)k < (int64_t)INT32_MAX && n_targets < (int64_t)INT32_MAX, "edge count must fit int32");
+  CM_REQUIRE(workspace_bytes >= cm_reverse_lists_workspace_bytes(n_targets), "reverse-list workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  int32_t* cursor = ws.take<int32_t>(n_targets + 1);
+  int32_t* block_sums = ws.take<int32_t>(ceil_div(n_targets, kScanBlock) + 1);
+  CM_CUDA_CHECK(cudaMemsetAsync(out_indptr, 0, (size_t)(n_targets + 1) * sizeof(int32_t), st));
+  const int64_t n_edges = n * k;
+  if (n_edges > 0) {
+    const int64_t blocks = ceil_div(n_edges, 256);
+    const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+    rev_count_kernel<<<grid, 256, 0, st>>>(idx, n_edges, n_targets, out_indptr + 1);
+    CM_LAUNCH_CHECK("rev_count_kernel");
+  }
+  const int64_t nb = ceil_div(n_targets, kScanBlock);
+  scan_local_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(out_indptr + 1, n_targets, block_sums);
+  CM_LAUNCH_CHECK("scan_local_kernel");
+  if (nb > 1) {
+    scan_sums_kernel<<<1, kScanBlock, 0, st>>>(block_sums, nb);
+    CM_LAUNCH_CHECK("scan_sums_kernel");
+    scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(out_indptr + 1, n_targets, block_sums);
+    CM_LAUNCH_CHECK("scan_add_kernel");
+  }
+  if (n_edges == 0) return CM_OK;
+  CM_CUDA_CHECK(cudaMemcpyAsync(cursor, out_indptr, (size_t)n_targets * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  {
+    const int64_t blocks = ceil_div(n_edges, 256);
+    const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+    rev_fill_kernel<<<grid, 256, 0, st>>>(idx, n, k, n_targets, cursor, out_rows);
+    CM_LAUNCH_CHECK("rev_fill_kernel");
+  }
+  {
+    const int64_t blocks = ceil_div(n_targets, kSortWarps);
+    const int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
+    rev_sort_short_kernel<<<grid, kSortWarps * 32, 0, st>>>(out_indptr, n_targets, out_rows);
+    CM_LAUNCH_CHECK("rev_sort_short_kernel");
+    const int grid_long = (int)(n_targets < (int64_t)kNumSMs * 8 ? n_targets : (int64_t)kNumSMs * 8);
+    rev_sort_long_kernel<<<grid_long, 256, 0, st>>>(out_indptr, n_targets, out_rows);
+    CM_LAUNCH_CHECK("rev_sort_long_kernel");
+  }
+  return CM_OK;
+}
+
+extern "C" int cm_jaccard_count(const int64_t* yx, const int64_t* yy, int64_t n_q, int k, int64_t n_r,
+                                const int32_t* rxx_indptr, const int32_t* rxx_rows, const int32_t* rxy_indptr,
+                                const int32_t* rxy_rows, int32_t* out_row_nnz, void* stream) {
+  CM_REQUIRE(out_row_nnz, "null pointer argument");
+  return launch_jaccard<false>(yx, yy, n_q, k, n_r, rxx_indptr, rxx_rows, rxy_indptr, rxy_rows, 0, out_row_nnz, nullptr,
+                               nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cm_jaccard_fill(const int64_t* yx, const int64_t* yy, int64_t n_q, int k, int64_t n_r,
+                               const int32_t* rxx_indptr, const int32_t* rxx_rows, const int32_t* rxy_indptr,
+                               const int32_t* rxy_rows, int hnoca, const int32_t* out_indptr, int32_t* out_cols,
+                               double* out_vals, void* stream) {
+  CM_REQUIRE(out_indptr && out_cols && out_vals, "null pointer argument");
+  return launch_jaccard<true>(yx, yy, n_q, k, n_r, rxx_indptr, rxx_rows, rxy_indptr, rxy_rows, hnoca, nullptr, out_indptr,
+                              out_cols, out_vals, (cudaStream_t)stream);
+}

@@ -24,6 +24,8 @@ __all__ = [
     "vote_argmax",
     "spmm",
     "spgemm",
+    "reverse_lists",
+    "jaccard",
     "debug_mma_tile",
     "counters",
 ]
@@ -33,7 +35,10 @@ counters = {"calls": 0, "launches": 0}
 
 # kernels launched per C-ABI call (upper bound used for the bench's `gpu_launches` claim)
 _LAUNCHES = {
-    "cm_knn_search": 8,
+    "cm_knn_search": 17,
+    "cm_reverse_lists": 8,
+    "cm_jaccard_count": 1,
+    "cm_jaccard_fill": 1,
     "cm_knn_merge_topk": 1,
     "cm_edge_stats": 1,
     "cm_edge_kernel_to_csr": 5,
@@ -281,6 +286,59 @@ def spgemm(indptr, cols, vals, x_indptr: torch.Tensor, x_cols: torch.Tensor, x_v
             int(n_genes), _ptr(out_indptr), _ptr(out_cols), _ptr(out_vals), _stream(),
         )  # fmt: skip
     return out_indptr, out_cols[:nnz], out_vals[:nnz]
+
+
+# ------------------------------------------------------------------------------------------------
+# P2' jaccard / hnoca
+# ------------------------------------------------------------------------------------------------
+def reverse_lists(idx: torch.Tensor, n_targets: int):
+    """Reverse neighbour lists of an (n, k) int64 index tensor: (indptr int32 (n_targets+1,), rows int32),
+    i.e. the transposed boolean adjacency (knn.py:228-266) in CSR form; -1 entries are skipped."""
+    dev = _check_cuda(idx)
+    idx = idx.to(torch.int64).contiguous()
+    n, k = idx.shape
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        indptr = torch.empty(n_targets + 1, dtype=torch.int32, device=dev)
+        rows = torch.empty(max(n * k, 1), dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.cm_reverse_lists_workspace_bytes(n_targets))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _call("cm_reverse_lists", _ptr(idx), n, k, int(n_targets), _ptr(indptr), _ptr(rows), _ptr(ws), ws_bytes, _stream())
+    return indptr, rows
+
+
+def jaccard(yx: torch.Tensor, yy: torch.Tensor, xx: torch.Tensor, xy: torch.Tensor, hnoca: bool = False):
+    """J = yx @ xx.T + yy @ xy.T with J/(4k-J) (jaccard) or (J/(2k-J))^2 (hnoca) -- cellmapper.py:287-301.
+    Inputs are the four (n, k) int64 neighbour index tensors.  Returns the device CSR
+    (indptr int32 (n_q+1,), cols int32, vals float64), columns ascending; one host sync for the output size."""
+    dev = _check_cuda(yx, yy, xx, xy)
+    yx = yx.to(torch.int64).contiguous()
+    yy = yy.to(torch.int64).contiguous()
+    n_q, k = yx.shape
+    n_r = xx.shape[0]
+    if tuple(yy.shape) != (n_q, k) or xx.shape[1] != k or tuple(xy.shape) != (n_r, k):
+        raise ValueError("the four neighbour arrays must share n_neighbors and be shaped (n_q,k), (n_q,k), (n_r,k), (n_r,k)")
+    rxx_ip, rxx_rows = reverse_lists(xx, n_r)  # a -> reference cells j with a in N_ref(r_j)
+    rxy_ip, rxy_rows = reverse_lists(xy, n_q)  # b -> reference cells j with b in N_qry(r_j)
+    with torch.cuda.device(dev):
+        row_nnz = torch.empty(n_q, dtype=torch.int32, device=dev)
+        _call(
+            "cm_jaccard_count", _ptr(yx), _ptr(yy), n_q, k, n_r, _ptr(rxx_ip), _ptr(rxx_rows), _ptr(rxy_ip), _ptr(rxy_rows),
+            _ptr(row_nnz), _stream(),
+        )  # fmt: skip
+        indptr64 = torch.zeros(n_q + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(row_nnz, 0, out=indptr64[1:])
+        nnz = int(indptr64[-1].item())
+        if nnz >= 2**31:
+            raise ValueError(f"jaccard mapping matrix has {nnz} entries; scipy CSR int32 indices cannot hold it")
+        indptr = indptr64.to(torch.int32)
+        cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)
+        _call(
+            "cm_jaccard_fill", _ptr(yx), _ptr(yy), n_q, k, n_r, _ptr(rxx_ip), _ptr(rxx_rows), _ptr(rxy_ip), _ptr(rxy_rows),
+            int(bool(hnoca)), _ptr(indptr), _ptr(cols), _ptr(vals), _stream(),
+        )  # fmt: skip
+    return indptr, cols[:nnz], vals[:nnz]
 
 
 def debug_mma_tile(q: torch.Tensor, r: torch.Tensor):

@@ -109,6 +109,27 @@ int cm_edge_kernel_to_csr(const double* dist, const int64_t* idx, int64_t n_q, i
 int cm_csr_row_normalize(const int32_t* indptr, const double* vals_in, int64_t n_rows, float* vals_out,
                          int64_t* zero_rows_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * P2'  jaccard / hnoca mapping matrix:  J = yx @ xx.T + yy @ xy.T on the 0/1 adjacencies of the four
+ * k-NN graphs, J/(4k-J) or (J/(2k-J))^2  (cellmapper.py:287-301, knn.py:228-266,467-483).
+ * ------------------------------------------------------------------------------------------- */
+/* Reverse neighbour lists of an (n, k) index array (entries -1 are skipped): out_indptr (n_targets+1)
+ * int32, out_rows (n*k) int32 = for every target the ascending list of rows that name it.
+ * This is the transpose `xx.T` / `xy.T` of the reference's product in CSR form. */
+size_t cm_reverse_lists_workspace_bytes(int64_t n_targets);
+int cm_reverse_lists(const int64_t* idx, int64_t n, int k, int64_t n_targets, int32_t* out_indptr, int32_t* out_rows,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* Row i of J merges the reverse lists RevXX(a), a in yx[i], and RevXY(b), b in yy[i] (yx, yy: (n_q, k)
+ * int64).  count: out_row_nnz (n_q) int32.  fill: out_indptr (n_q+1) int32 = exclusive scan of the
+ * counts (caller); writes ascending columns and float64 values J/(4k-J) (hnoca = 0) or (J/(2k-J))^2
+ * (hnoca = 1); row-normalise with cm_csr_row_normalize.  2k <= 256. */
+int cm_jaccard_count(const int64_t* yx, const int64_t* yy, int64_t n_q, int k, int64_t n_r, const int32_t* rxx_indptr,
+                     const int32_t* rxx_rows, const int32_t* rxy_indptr, const int32_t* rxy_rows, int32_t* out_row_nnz,
+                     void* stream);
+int cm_jaccard_fill(const int64_t* yx, const int64_t* yy, int64_t n_q, int k, int64_t n_r, const int32_t* rxx_indptr,
+                    const int32_t* rxx_rows, const int32_t* rxy_indptr, const int32_t* rxy_rows, int hnoca,
+                    const int32_t* out_indptr, int32_t* out_cols, double* out_vals, void* stream);
+
 /* column sums of a float64 CSR: presence score, evaluate.py:457 (`conn.sum(axis=0)`). out (n_cols)
  * float64 must be zeroed by the caller (it is accumulated into, so shards can share it). */
 int cm_csr_col_sums(const int32_t* indptr, const int32_t* cols, const double* vals, int64_t n_rows, double* out,

@@ -421,3 +421,97 @@ def test_precomputed_ragged_selfmapping(torch_cuda, tag, include_self):
     cm.map_obs("celltype")
     np.testing.assert_array_equal(ad.obs["celltype_pred"].to_numpy().astype(str), g[f"pred_{tag}"])
     np.testing.assert_allclose(ad.obs["celltype_conf"].to_numpy(), g[f"conf_{tag}"], rtol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------
+# P2' jaccard / hnoca (four-direction search)
+# --------------------------------------------------------------------------------------------
+def test_reverse_lists(torch_cuda):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    rng = np.random.default_rng(7)
+    n, k, n_t = 3000, 12, 500
+    idx = rng.integers(0, n_t, (n, k))
+    idx[:, 0] = 3  # a hub: reverse list of 3000 entries (the block-wide sort path)
+    idx[::5, -2:] = -1
+    ip, rows = device.reverse_lists(dev(torch, idx), n_t)
+    ip, rows = ip.cpu().numpy(), rows.cpu().numpy()
+    for t in [0, 3, 17, n_t - 1]:
+        want = np.sort(np.repeat(np.arange(n), k)[(idx == t).ravel()])
+        np.testing.assert_array_equal(rows[ip[t] : ip[t + 1]], want)
+    assert ip[-1] == (idx >= 0).sum()
+
+
+@pytest.mark.parametrize("method", ["jaccard", "hnoca"])
+def test_jaccard_from_reference_graphs(torch_cuda, method):
+    """Given the reference's four neighbour graphs, the jaccard / hnoca mapping matrix has the
+    reference's structure and values within 1 float32 ulp, and the transferred labels are identical."""
+    torch = torch_cuda
+    from cellmapper_b200 import device
+    from oracle import cellmapper_oracle as orc
+
+    g = load_golden("four_graphs")
+    ip, cols, vals64 = device.jaccard(
+        dev(torch, g["yx_indices"]), dev(torch, g["yy_indices"]), dev(torch, g["xx_indices"]), dev(torch, g["xy_indices"]),
+        hnoca=(method == "hnoca"),
+    )  # fmt: skip
+    vals, _ = device.csr_row_normalize(ip, vals64)
+    n_q, n_r = g["yx_indices"].shape[0], g["xx_indices"].shape[0]
+    m = scipy_from_device(ip, cols, vals, (n_q, n_r))
+    ref = golden_csr(g, f"mm_{method}")
+    ref.sort_indices()
+    np.testing.assert_array_equal(m.indptr, ref.indptr)
+    np.testing.assert_array_equal(m.indices, ref.indices)
+    assert ulp_diff_f32(m.data, ref.data).max() <= 1
+    cats, codes = orc.onehot_sorted(g["labels"])
+    code, conf = device.vote_argmax(ip, cols, vals, dev(torch, codes), len(cats))
+    np.testing.assert_array_equal(cats[code.cpu().numpy()].astype(str), g[f"pred_{method}"])
+    np.testing.assert_allclose(conf.cpu().numpy(), g[f"conf_{method}"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("method", ["jaccard", "hnoca"])
+def test_cellmapper_four_graph_mapping(torch_cuda, method):
+    import pandas as pd
+    from scipy.sparse import csr_matrix
+
+    from cellmapper_b200 import CellMapper
+    from cellmapper_b200._anndata import AnnData
+
+    g = load_golden("four_graphs")
+    n_r, n_q = g["xr"].shape[0], g["xq"].shape[0]
+    ref = AnnData(
+        X=csr_matrix((n_r, 2), dtype=np.float32),
+        obs=pd.DataFrame({"celltype": pd.Categorical(g["labels"])}, index=[f"r{i}" for i in range(n_r)]),
+        obsm={"X_joint": g["xr"]},
+    )
+    qry = AnnData(X=csr_matrix((n_q, 2), dtype=np.float32), obs=pd.DataFrame(index=[f"q{i}" for i in range(n_q)]), obsm={"X_joint": g["xq"]})
+    cm = CellMapper(qry, ref).map(use_rep="X_joint", obs_keys="celltype", n_neighbors=int(g["k"]), only_yx=False, mapping_method=method)
+    for name in ("xx", "yy", "xy", "yx"):
+        res = getattr(cm.knn, name)
+        assert neighbours_match(res.indices, res.distances, g[f"{name}_indices"], g[f"{name}_distances"]) == 0
+    same = all(np.array_equal(getattr(cm.knn, n).indices, g[f"{n}_indices"]) for n in ("xx", "yy", "xy", "yx"))
+    if same:
+        assert_csr_equal(cm.mapping_matrix, golden_csr(g, f"mm_{method}"), rtol=1e-6, structure=False)
+        np.testing.assert_array_equal(qry.obs["celltype_pred"].to_numpy().astype(str), g[f"pred_{method}"])
+    np.testing.assert_allclose(np.asarray(cm.mapping_matrix.sum(1)).ravel(), 1.0, atol=1e-6)
+
+
+def test_self_mapping_identity(torch_cuda):
+    """k = 1 jaccard self-mapping reproduces the labels exactly (reference tests/model/test_self_mapping.py:18-37)."""
+    import pandas as pd
+    from scipy.sparse import csr_matrix
+
+    from cellmapper_b200 import CellMapper
+    from cellmapper_b200._anndata import AnnData
+
+    g = load_golden("four_graphs")
+    n = g["xr"].shape[0]
+    ad = AnnData(
+        X=csr_matrix((n, 2), dtype=np.float32),
+        obs=pd.DataFrame({"celltype": pd.Categorical(g["labels"])}, index=[f"c{i}" for i in range(n)]),
+        obsm={"X_joint": g["xr"]},
+    )
+    CellMapper(ad).map(use_rep="X_joint", obs_keys="celltype", n_neighbors=1, only_yx=False, mapping_method="jaccard")
+    np.testing.assert_array_equal(ad.obs["celltype_pred"].to_numpy().astype(str), g["labels"])
+    np.testing.assert_array_equal(ad.obs["celltype_pred"].to_numpy().astype(str), g["self_pred"])
