@@ -489,7 +489,11 @@ struct RowCand {
   int cnt;
   uint32_t thr_key;  // every element seen so far with key < thr_key is in the buffer
   float thr;         // the same threshold as a float; +inf at start
+  int n_trig, n_leaf, n_compact;  // development counters (warp-uniform)
+  long long c_slow, c_compact;    // cycles inside the slow path / inside compactions (only with a probe buffer)
 };
+
+__device__ long long* g_compact_dbg = nullptr;  // development: per-lane compaction statistics
 
 // keys are stored as raw fp32 bit patterns and compared as floats; only pivots move between the float
 // and the order-preserving uint domain (bisection needs integer midpoints)
@@ -498,23 +502,39 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float
 __device__ __forceinline__ int count_below(uint32_t keys, int cnt, float piv) {
   int c = 0;
   int e = 0;
-  for (; e + 8 <= cnt; e += 8) {  // 8 independent loads in flight: one warp per scheduler, so ILP matters
+  // 16 independent loads in flight: one warp per scheduler, so every pass runs at shared-memory latency / ILP
+  for (; e + 16 <= cnt; e += 16) {
+    float kk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) kk[j] = lds_f32(keys + (e + j) * kCandStride);
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      c0 += kk[j] < piv;
+      c1 += kk[j + 1] < piv;
+      c2 += kk[j + 2] < piv;
+      c3 += kk[j + 3] < piv;
+    }
+    c += (c0 + c1) + (c2 + c3);
+  }
+  for (; e + 4 <= cnt; e += 4) {
     const float k0 = lds_f32(keys + (e + 0) * kCandStride), k1 = lds_f32(keys + (e + 1) * kCandStride);
     const float k2 = lds_f32(keys + (e + 2) * kCandStride), k3 = lds_f32(keys + (e + 3) * kCandStride);
-    const float k4 = lds_f32(keys + (e + 4) * kCandStride), k5 = lds_f32(keys + (e + 5) * kCandStride);
-    const float k6 = lds_f32(keys + (e + 6) * kCandStride), k7 = lds_f32(keys + (e + 7) * kCandStride);
-    c += (k0 < piv) + (k1 < piv) + (k2 < piv) + (k3 < piv) + (k4 < piv) + (k5 < piv) + (k6 < piv) + (k7 < piv);
+    c += (k0 < piv) + (k1 < piv) + (k2 < piv) + (k3 < piv);
   }
   for (; e < cnt; ++e) c += lds_f32(keys + e * kCandStride) < piv;
   return c;
 }
 
-// Keep window: after a compaction a row holds between k + 6 and k + 20 candidates, never fewer than k,
+// Keep window: after a compaction a row holds between k + 2 and k + 18 candidates, never fewer than k,
 // so "everything below the threshold is in the buffer" holds for ANY scan order -- the order (home
-// cell first, see "coarse cells") only decides how quickly the threshold converges.
+// cell first, see "coarse cells") only decides how quickly the threshold converges.  The window is
+// wide on purpose: the 32 rows of a warp compact in lockstep, so the number of counting passes is the
+// worst row's; a 17-wide target lets the first interpolated pivot land inside most of the time, and
+// keeping few entries frees the most slots per compaction.
 __device__ __forceinline__ void keep_window(int k, int& keep_lo, int& keep_hi) {
-  keep_hi = min(k + 20, kCandOut);
-  keep_lo = min(k + 6, keep_hi - 4);
+  keep_hi = min(k + 18, kCandOut - 2);
+  keep_lo = min(k + 2, keep_hi - 4);
 }
 
 // Shrink the buffer to between keep_lo and keep_hi entries and tighten the threshold.  Selection,
@@ -526,16 +546,35 @@ __device__ __forceinline__ void keep_window(int k, int& keep_lo, int& keep_hi) {
 // Cold code, deliberately NOT inlined: the hot epilogue loop has to stay inside the instruction cache.
 // Returns (new count) | (new threshold key << 32).
 __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint32_t idx, int cnt, uint32_t thr_key,
-                                                            int k) {
+                                                            int k, long long* dbg) {
+  const long long tc0 = clock64();
   int keep_lo, keep_hi;
   keep_window(k, keep_lo, keep_hi);
   if (cnt <= keep_hi) return (unsigned long long)(uint32_t)cnt | ((unsigned long long)thr_key << 32);
+  int n_iter = 0;
   float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-  for (int e = 0; e < cnt; ++e) {
-    const float kx = lds_f32(keys + e * kCandStride);
-    mn = fminf(mn, kx);
-    mx = fmaxf(mx, kx);
+  {
+    int e = 0;
+    for (; e + 16 <= cnt; e += 16) {  // 16 independent loads in flight, tree reduction
+      float kk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) kk[j] = lds_f32(keys + (e + j) * kCandStride);
+      float a0 = fminf(fminf(kk[0], kk[1]), kk[2]), a1 = fminf(fminf(kk[3], kk[4]), kk[5]);
+      float a2 = fminf(fminf(kk[6], kk[7]), kk[8]), a3 = fminf(fminf(kk[9], kk[10]), kk[11]);
+      float a4 = fminf(fminf(kk[12], kk[13]), fminf(kk[14], kk[15]));
+      mn = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(a4, mn));
+      float b0 = fmaxf(fmaxf(kk[0], kk[1]), kk[2]), b1 = fmaxf(fmaxf(kk[3], kk[4]), kk[5]);
+      float b2 = fmaxf(fmaxf(kk[6], kk[7]), kk[8]), b3 = fmaxf(fmaxf(kk[9], kk[10]), kk[11]);
+      float b4 = fmaxf(fmaxf(kk[12], kk[13]), fmaxf(kk[14], kk[15]));
+      mx = fmaxf(fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)), fmaxf(b4, mx));
+    }
+    for (; e < cnt; ++e) {
+      const float kx = lds_f32(keys + e * kCandStride);
+      mn = fminf(mn, kx);
+      mx = fmaxf(mx, kx);
+    }
   }
+  const long long tc1 = clock64();
   // bracket in the ordered domain: count(key < lo) = c_lo < keep_lo ; count(key < hi) = c_hi > keep_hi
   uint32_t lo = float_to_ordered(mn), hi = float_to_ordered(mx) + 1u;  // keys are finite: no wrap
   int c_lo = 0, c_hi = cnt;
@@ -545,15 +584,19 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
   const float target = 0.5f * (float)(keep_lo + keep_hi);
   for (int iter = 0; hi - lo > 1u; ++iter) {
     uint32_t piv;
-    if (iter < 3) {
+    if (iter < 4) {
+      // neighbour counts grow like a power of the distance, so the count is interpolated in log space
+      // (linear interpolation needs ~8 probes at 50 dimensions, this ~2)
       const float f_lo = ordered_to_float(lo), f_hi = ordered_to_float(hi - 1u);
-      const float frac = (target - (float)c_lo) / (float)(c_hi - c_lo);
+      const float l_lo = __log2f(fmaxf((float)c_lo, 0.5f));
+      const float frac = (__log2f(target) - l_lo) / (__log2f((float)c_hi) - l_lo);
       piv = float_to_ordered(f_lo + (f_hi - f_lo) * frac);
       piv = min(max(piv, lo + 1u), hi - 1u);
     } else {
       piv = lo + ((hi - lo) >> 1);
     }
     const int c = count_below(keys, cnt, ordered_to_float(piv));
+    ++n_iter;
     if (c < keep_lo) {
       lo = piv;
       c_lo = c;
@@ -572,35 +615,63 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
     c_tl = c_lo;
     tie = true;
   }
+  const long long tc2 = clock64();
   const float tl_f = ordered_to_float(tl);
   int extra = tie ? keep_hi - c_tl : 0;
-  int w = 0;
-  for (int e = 0; e < cnt; ++e) {
-    const uint32_t raw = lds_u32(keys + e * kCandStride);
+  const uint32_t idx_off = idx - keys;
+  uint32_t wa = keys;  // shared address of the next kept slot
+  // branch-free: the 32 rows of the warp run this in lockstep, a divergent branch per entry costs more
+  // than the two predicated stores
+  auto put = [&](uint32_t raw, uint32_t ix) {
     const float kx = __uint_as_float(raw);
-    const uint32_t ix = lds_u32(idx + e * kCandStride);
-    bool keep = kx < tl_f;
-    if (!keep && tie && kx == tl_f && extra > 0) {
-      keep = true;
-      --extra;
+    const bool tie_keep = tie & (kx == tl_f) & (extra > 0);
+    const bool keep = (kx < tl_f) | tie_keep;
+    extra -= tie_keep ? 1 : 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "@p st.shared.u32 [%0], %1;\n\t"
+        "@p st.shared.u32 [%2], %3;\n\t}"
+        ::"r"(wa), "r"(raw), "r"(wa + idx_off), "r"(ix), "r"((uint32_t)keep)
+        : "memory");
+    wa += keep ? kCandStride : 0u;
+  };
+  int e = 0;
+  for (; e + 8 <= cnt; e += 8) {  // all loads of a group before its stores (kept slot <= e: a store never hits an unread slot)
+    uint32_t rr[8], ii[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      rr[j] = lds_u32(keys + (e + j) * kCandStride);
+      ii[j] = lds_u32(idx + (e + j) * kCandStride);
     }
-    if (keep) {
-      sts_u32(keys + w * kCandStride, raw);
-      sts_u32(idx + w * kCandStride, ix);
-      ++w;
-    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) put(rr[j], ii[j]);
+  }
+  for (; e < cnt; ++e) put(lds_u32(keys + e * kCandStride), lds_u32(idx + e * kCandStride));
+  const int w = (int)((wa - keys) / kCandStride);
+  if (dbg) {
+    const long long tc3 = clock64();
+    atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)n_iter);
+    atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(tc1 - tc0));
+    atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(tc2 - tc1));
+    atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)(tc3 - tc2));
+    atomicAdd((unsigned long long*)&dbg[4], 1ULL);
+    atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)cnt);
   }
   return (unsigned long long)(uint32_t)w | ((unsigned long long)tl << 32);
 }
 
 __device__ __forceinline__ void compact_row(RowCand& rc, int k) {
-  const unsigned long long r = compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, k);
+  const long long t0 = clock64();
+  const unsigned long long r = compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, k, g_compact_dbg);
+  rc.c_compact += clock64() - t0;
   rc.cnt = (int)(uint32_t)r;
   rc.thr_key = (uint32_t)(r >> 32);
   rc.thr = rc.thr_key == 0xFFFFFFFFu ? CUDART_INF_F : ordered_to_float(rc.thr_key);
 }
 
-constexpr int kCandTrigger = kCandCap - 27;  // a compaction check follows every <= 27 appended columns
+constexpr int kCandTrigger = kCandCap - 27;
+constexpr int kDenseLeaves = 8;  // flagged leaves (of 22) from which a half tile is appended without per-leaf branches  // a compaction check follows every <= 27 appended columns
 
 // ------------------------------------------------------------------------------------------------
 // the tensor-core kernel
@@ -676,6 +747,8 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
   const float m = fminf(fminf(w0, w1), w2);
   if (__any_sync(0xffffffffu, m < rc.thr) && !(flags & 16)) {  // probe 16: fast path only
     const float thr0 = rc.thr;
+    ++rc.n_trig;
+    const long long t_slow0 = clock64();
     // three partial masks so the bit-insert chains are 8 deep instead of 22
     uint32_t ma = 0, mb = 0, mc = 0;
 #pragma unroll
@@ -689,10 +762,35 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     // registers (22 tiny cases behind one indexed branch); the append code exists once.  An unrolled
     // `if (leaves & bit)` ladder costs a taken branch per skipped leaf and ran at instruction-fetch
     // latency (ncu r1c: 62% "no instruction" stalls on those branches).
+    if (__popc(leaves) >= kDenseLeaves) {
+      // Dense half (the scan is inside the query's own neighbourhood: most leaves hold a passing element):
+      // straight-line predicated appends of all 64 columns, no per-leaf control flow.
+#pragma unroll
+      for (int W = 0; W < 3; ++W) {
+        const float thr = rc.thr;
+        const uint32_t idx_off = rc.idx - rc.keys;
+        uint32_t w = rc.keys + (uint32_t)rc.cnt * kCandStride;
+#pragma unroll
+        for (int e = 27 * W; e < 27 * W + 27 && e < 64; ++e) {
+          const bool pass = __uint_as_float(v[e]) < thr;
+          if (pass) { sts_u32(w, v[e]); sts_u32(w + idx_off, c0 + e); }
+          w += pass ? kCandStride : 0u;
+        }
+        rc.cnt = (int)((w - rc.keys) / kCandStride);
+        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
+          ++rc.n_compact;
+          compact_row(rc, k);
+        }
+      }
+      rc.n_leaf += 22;
+      rc.c_slow += clock64() - t_slow0;
+      return;
+    }
     int since_check = 0;
     while (leaves) {
       const int T = __ffs((int)leaves) - 1;
       leaves &= leaves - 1;
+      ++rc.n_leaf;
       uint32_t x0, x1, x2;
       switch (T) {
 #define CM_LEAF(i) case i: x0 = v[3 * i]; x1 = v[3 * i + 1]; x2 = v[3 * i + 2]; break;
@@ -716,9 +814,13 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
       // at most 27 appends between checks: cnt <= kCandTrigger + 27 <= kCandCap
       if (++since_check == 9 || leaves == 0) {
         since_check = 0;
-        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) compact_row(rc, k);
+        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
+          ++rc.n_compact;
+          compact_row(rc, k);
+        }
       }
     }
+    rc.c_slow += clock64() - t_slow0;
   }
 }
 
@@ -782,8 +884,6 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
     if (buf >= kAccBufs) { buf -= kAccBufs; aph ^= 1u; }
   }
   if (a.prof && leader && a.first == 0) {
-    a.prof[0] = c_acc;
-    a.prof[1] = c_b;
     a.prof[2] = c_issue;
     a.prof[3] = clock64() - t_start;
     a.prof[4] = a.n_tiles;
@@ -906,6 +1006,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     rc.cnt = 0;
     rc.thr_key = 0xFFFFFFFFu;
     rc.thr = CUDART_INF_F;
+    rc.n_trig = rc.n_leaf = rc.n_compact = 0;
+    rc.c_slow = rc.c_compact = 0;
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
     const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t t_lane = t_lane_a + kTmemACols;
@@ -960,6 +1062,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       if (!(p.flags & 1)) process_half(vb, col_base + 64, rc, p.k, p.flags);
     }
     compact_row(rc, p.k);  // leave at most kCandOut entries
+    if (p.prof_out && lane == 0) {
+      atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 5], (unsigned long long)rc.n_trig);
+      atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 6], (unsigned long long)rc.n_leaf);
+      atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 7], (unsigned long long)rc.n_compact);
+      atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 0], (unsigned long long)rc.c_slow);
+      atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 1], (unsigned long long)rc.c_compact);
+    }
     const int64_t o = (int64_t)blockIdx.x * kMmaTile + row_in_tile;
     for (int e = 0; e < rc.cnt; ++e) {
       p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
@@ -1403,7 +1512,12 @@ int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64
 
 size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d) { return mma_workspace_bytes(n_q, n_r, d); }
 void set_probe_flags(int f) { g_probe_flags = f; }
-void set_probe_prof(long long* p) { g_probe_prof = p; }
+void set_probe_prof(long long* p) {
+  g_probe_prof = p;
+  long long* d = p ? p + 8 * 8192 : nullptr;  // the statistics block follows the per-CTA counters
+  cudaError_t e = cudaMemcpyToSymbol(g_compact_dbg, &d, sizeof(d));
+  if (e != cudaSuccess) fprintf(stderr, "set_probe_prof: %s\n", cudaGetErrorString(e));
+}
 
 int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st);
