@@ -130,8 +130,8 @@ def physical_gpu_index(local_rank: int) -> int:
 # ------------------------------------------------------------------------------------------------
 def cpu_sample_queries(name: str) -> int:
     n_q, n_r, d, _ = WORKLOADS[name]
-    # brute force is linear in n_q: keep one step at ~2-4 s on 8 cores (2.5e9 pair-dims/s/8 cores measured)
-    budget_pairs = 2.5e9
+    # brute force is linear in n_q: keep one step at ~3-10 s of host time (about 4e9 pairs/s at d=50 on 16 cores measured)
+    budget_pairs = 3.0e10
     return int(max(1000, min(n_q, budget_pairs / n_r)))
 
 
@@ -240,12 +240,26 @@ def b200_arm(args):
     xr_d, xq_d = xr_t.to(dev), xq_t.to(dev)
     umap_d, codes_d = umap_t.to(dev), codes_t.to(dev)
 
-    def device_step():
+    PHASES = ["search", "edge_stats", "kernel_to_csr", "vote", "spmm"]
+
+    def device_step(marks=None):
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+
+        mark()
         dd, ii = device.knn_search(xq_d, xr_d, K, dist_mode=mode)
-        st = device.edge_stats(dd, ii, allreduce=allreduce)
+        mark()
+        st = device.edge_stats(dd, ii, allreduce=allreduce, need_std=False)
+        mark()
         ip, cols, vals = device.edge_kernel_to_csr(dd, ii, "gaussian", st, normalize=True)
+        mark()
         code, conf = device.vote_argmax(ip, cols, vals, codes_d, len(cats))
+        mark()
         emb = device.spmm(ip, cols, vals, umap_d)
+        mark()
         return dd, ii, code, conf, emb
 
     for _ in range(args.warmup):
@@ -262,11 +276,14 @@ def b200_arm(args):
     import ctypes
 
     buf4 = (ctypes.c_float * 4)()
+    step_marks = []
     for s in range(args.steps):
         flush.zero_()
         ev[s][0].record()
-        res = device_step()
+        marks = []
+        res = device_step(marks)
         ev[s][1].record()
+        step_marks.append(marks)
         if lib.cm_profile_last_knn_ms(buf4) == 0:  # synchronises on the search's own events only
             phase_ms += np.array(list(buf4))
     torch.cuda.synchronize()
@@ -275,6 +292,8 @@ def b200_arm(args):
     clocks = sampler.stop()
     lib.cm_profile_enable(0)
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    path_ms = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in step_marks])) for i, n in enumerate(PHASES)}
     phase_ms /= args.steps
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
     if world > 1:
@@ -340,6 +359,12 @@ def b200_arm(args):
         "avg_launch_ms": phase_ms[1],
         "phases_ms": {"prep": phase_ms[0], "mma_topk": phase_ms[1], "rerank": phase_ms[2], "exact_fallback": phase_ms[3]},
     }
+    # HBM-side phases: algorithmic bytes per query (SURVEY.md 8d / DESIGN.md 4) over the CUDA-event time of the call
+    hbm_bytes = {"edge_stats": K * 16.0, "kernel_to_csr": 484.0, "vote": 368.0, "spmm": K * 8.0 + K * UMAP_DIMS * 4.0 + UMAP_DIMS * 4.0}
+    hbm_phases = {
+        n: {"ms": path_ms[n], "achieved_gbs": hbm_bytes[n] * n_q / (path_ms[n] * 1e-3) / 1e9, "frac_of_hbm_peak": hbm_bytes[n] * n_q / (path_ms[n] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        for n in hbm_bytes
+    }
 
     # ---------------- CPU baseline (oracle port) + recall against it ----------------
     cpu = None
@@ -377,6 +402,9 @@ def b200_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "path_phases_ms": path_ms,
+        "hbm_phases": hbm_phases,
+        "step_ms": step_ms,
         "cpu_baseline": cpu,
         "recall_at_30": recall,
     }

@@ -259,6 +259,87 @@ edge_to_csr_kernel(const double* __restrict__ dist, const int64_t* __restrict__ 
   }
 }
 
+// k <= 32: the row lives in registers, one edge per lane.  Column sort = bitonic network over
+// shuffles; the float64 row sum reproduces numpy's `add.reduceat` order (first element, then the
+// 8-accumulator pairwise routine) with the accumulators spread over lanes 0..7.
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+  return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+
+// sum of a[0..n) held one per lane (lane i = a[i]) in numpy_row_sum's order; result valid on all lanes
+__device__ __forceinline__ double numpy_row_sum_lanes(double a, int n) {
+  const int lane = threadIdx.x & 31;
+  if (n == 0) return 0.0;
+  const int m = n - 1;  // pairwise part covers a[1..n)
+  double res;
+  if (m < 8) {
+    res = 0.0;
+    for (int i = 0; i < m; ++i) res += shfl_f64(a, 1 + i);
+  } else {
+    // r[j] = a[1+j] + a[1+8+j] + a[1+16+j] ... on lane j < 8 (m <= 31: at most 3 rounds)
+    const int full = m - (m % 8);
+    double r = shfl_f64(a, 1 + (lane & 7));
+    for (int i = 8; i < full; i += 8) r += shfl_f64(a, 1 + i + (lane & 7));
+    const double r1 = shfl_f64(r, (lane & 7) ^ 1);
+    const double p2 = (lane & 1) ? r1 + r : r + r1;                // (r0+r1), (r2+r3), ... same operand order on both lanes
+    const double q2 = shfl_f64(p2, (lane & 7) ^ 2);
+    const double p4 = (lane & 2) ? q2 + p2 : p2 + q2;              // (r0+r1)+(r2+r3) , (r4+r5)+(r6+r7)
+    const double q4 = shfl_f64(p4, (lane & 7) ^ 4);
+    res = (lane & 4) ? q4 + p4 : p4 + q4;
+    res = shfl_f64(res, 0);
+    for (int i = full; i < m; ++i) res += shfl_f64(a, 1 + i);
+  }
+  return shfl_f64(a, 0) + res;
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+edge_to_csr_small_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n_q, int k, int kernel,
+                         const double* __restrict__ stats3, int normalize, const int32_t* __restrict__ indptr,
+                         int32_t* __restrict__ cols, float* __restrict__ vals_f32, double* __restrict__ vals_f64) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double p0 = kernel_param(kernel, stats3);
+  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < n_q; row += (int64_t)gridDim.x * kRowWarps) {
+    double w = 0.0;
+    int32_t c = INT32_MAX;
+    if (lane < k) {
+      const double dv = dist[row * k + lane];
+      const int64_t iv = idx[row * k + lane];
+      if (edge_valid(dv, iv)) {
+        w = kernel_value(kernel, dv, p0);
+        c = (int32_t)iv;
+      }
+    }
+    // ascending sort by column (invalid edges sink to the end); ties keep scipy's summed-duplicates semantics
+    // only for distinct columns, which is what a k-NN row has
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+        const int32_t oc = __shfl_xor_sync(0xffffffffu, c, stride);
+        const double ow = shfl_f64(w, lane ^ stride);
+        const bool up = ((lane & size) == 0);           // ascending block?
+        const bool lower = ((lane & stride) == 0);      // this lane holds the lower index of the pair
+        const bool take_min = (up == lower);
+        const bool swap = take_min ? (oc < c) : (oc > c);
+        if (swap) { c = oc; w = ow; }
+      }
+    }
+    const int32_t start = indptr[row];
+    const int n_valid = indptr[row + 1] - start;
+    double inv = 1.0;
+    if (normalize) {
+      double rs = numpy_row_sum_lanes(w, n_valid);
+      if (rs == 0.0) rs = 1.0;  // zero rows are left unchanged (cellmapper.py:127-129)
+      inv = 1.0 / rs;
+    }
+    if (lane < n_valid) {
+      cols[start + lane] = c;
+      if (vals_f32) vals_f32[start + lane] = (float)(w * inv);
+      if (vals_f64) vals_f64[start + lane] = w * inv;
+    }
+  }
+}
+
 __global__ void csr_row_normalize_kernel(const int32_t* __restrict__ indptr, const double* __restrict__ vals_in,
                                          int64_t n_rows, float* __restrict__ vals_out, unsigned long long* zero_rows) {
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
@@ -338,9 +419,15 @@ extern "C" int cm_edge_kernel_to_csr(const double* dist, const int64_t* idx, int
     CM_CUDA_CHECK(cudaFuncSetAttribute(edge_to_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = ceil_div(n_q, kRowWarps);
     int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
-    edge_to_csr_kernel<<<grid, kRowWarps * 32, smem, st>>>(dist, idx, n_q, k, np, kernel, stats3, normalize, indptr,
-                                                          cols, vals_f32, vals_f64);
-    CM_LAUNCH_CHECK("edge_to_csr_kernel");
+    if (k <= 32) {
+      edge_to_csr_small_kernel<<<grid, kRowWarps * 32, 0, st>>>(dist, idx, n_q, k, kernel, stats3, normalize, indptr, cols,
+                                                               vals_f32, vals_f64);
+      CM_LAUNCH_CHECK("edge_to_csr_small_kernel");
+    } else {
+      edge_to_csr_kernel<<<grid, kRowWarps * 32, smem, st>>>(dist, idx, n_q, k, np, kernel, stats3, normalize, indptr,
+                                                            cols, vals_f32, vals_f64);
+      CM_LAUNCH_CHECK("edge_to_csr_kernel");
+    }
   }
   return CM_OK;
 }

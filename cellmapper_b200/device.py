@@ -148,11 +148,14 @@ def knn_merge_topk(cand_dist: torch.Tensor, cand_idx: torch.Tensor, k: int):
 # ------------------------------------------------------------------------------------------------
 # P2 graph kernel
 # ------------------------------------------------------------------------------------------------
-def edge_stats(dist: torch.Tensor, idx: torch.Tensor, allreduce: Callable[[torch.Tensor], None] | None = None):
+def edge_stats(
+    dist: torch.Tensor, idx: torch.Tensor, allreduce: Callable[[torch.Tensor], None] | None = None, need_std: bool = True
+):
     """[sum d, sum (d-mean)^2, count] over valid edges, float64 (3,) on the device.
 
     Two passes like numpy's mean/std (knn.py:196,206).  ``allreduce(t)`` (in-place SUM over ranks)
-    couples the shards: the bandwidth is ONE global statistic over all query rows.
+    couples the shards: the bandwidth is ONE global statistic over all query rows.  ``need_std=False``
+    skips the second pass (only the scarches kernel uses the standard deviation); slot 1 is then NaN.
     """
     dev = _check_cuda(dist, idx)
     dist = dist.contiguous()
@@ -164,6 +167,9 @@ def edge_stats(dist: torch.Tensor, idx: torch.Tensor, allreduce: Callable[[torch
         _call("cm_edge_stats", _ptr(dist), _ptr(idx), n, None, _ptr(first), _ptr(ws), ws.numel(), _stream())
         if allreduce is not None:
             allreduce(first)
+        if not need_std:  # gaussian / equal / inverse_distance only use the mean (knn.py:196-219)
+            first[1] = float("nan")
+            return first
         mean = (first[0] / first[2]).reshape(1).contiguous()
         second = torch.empty(3, dtype=torch.float64, device=dev)
         _call("cm_edge_stats", _ptr(dist), _ptr(idx), n, _ptr(mean), _ptr(second), _ptr(ws), ws.numel(), _stream())

@@ -118,7 +118,7 @@ class NeighborsResults:
         """Device CSR (indptr, cols, vals) of the kernel graph; float64 raw weights, or the
         row-normalised float32 mapping matrix when ``normalize``."""
         d, i = self.distances_device, self.indices_device
-        stats = device.edge_stats(d, i, allreduce=allreduce)
+        stats = device.edge_stats(d, i, allreduce=allreduce, need_std=(kernel == "scarches"))
         if float(stats[2].item()) == 0.0:
             raise ValueError("No finite distances found in the neighborhood graph")  # knn.py:191-192
         if kernel == "random":  # knn.py:211-213 -- unseeded, for testing purposes only
