@@ -190,6 +190,7 @@ struct ScaleInfo {
   unsigned long long max_rnorm_bits;   // max ||r||^2 (double bits)
   unsigned long long fail_count;       // rows whose certificate failed
   unsigned long long cand_total;       // candidates examined by the re-rank
+  unsigned long long tiles_scanned;    // (query tile, reference tile) pairs the tensor-core kernel evaluated
 };
 
 template <typename T>
@@ -315,6 +316,9 @@ constexpr int kMaxCells = 256;
 constexpr int kAssignThreads = 256;
 constexpr int kAssignMaxD = 56;  // >= the largest d of the tensor-core path (53)
 constexpr int kMinRefsForCells = 16384;  // below this the scan is short anyway: scrambled order, no cells
+// float32 expansion ||x||^2 + ||p||^2 - 2 x.p with d <= 56: |error| <= ~4e-6 (||x||^2 + ||p||^2); the bounds
+// used for pruning give away 2^-16 = 1.5e-5 of that sum
+constexpr float kBoundSlack = 1.52587890625e-05f;
 
 // pivot j = reference row j * stride; stored transposed [d][n_cells] so 4 pivots are one 16-byte read
 template <typename T>
@@ -339,15 +343,16 @@ template <typename T, int DP>
 __global__ void __launch_bounds__(kAssignThreads)
 assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const float* __restrict__ piv_t,
                     const float* __restrict__ piv_norm, int n_cells, uint8_t* __restrict__ cell,
-                    int32_t* __restrict__ counts) {
+                    int32_t* __restrict__ counts, unsigned int* __restrict__ rad2_bits) {
   extern __shared__ __align__(16) float asm_smem[];
   float* sp = asm_smem;                          // [DP][n_cells]
   float* sn = sp + (size_t)DP * n_cells;         // [n_cells]
   float* sx = sn + n_cells;                      // [DP][kAssignThreads]
   __shared__ int hist[kMaxCells];
+  __shared__ unsigned int rad[kMaxCells];  // float bits of the largest squared distance to the cell's pivot
   for (int i = threadIdx.x; i < DP * n_cells; i += blockDim.x) sp[i] = i < d * n_cells ? piv_t[i] : 0.f;
   for (int i = threadIdx.x; i < n_cells; i += blockDim.x) sn[i] = piv_norm[i];
-  for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x) hist[i] = 0;
+  for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x) { hist[i] = 0; rad[i] = 0u; }
   for (int i = threadIdx.x; i < DP * kAssignThreads; i += blockDim.x) sx[i] = 0.f;
   __syncthreads();
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
@@ -382,30 +387,41 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
       }
       cell[base + threadIdx.x] = (uint8_t)best_j;
       atomicAdd(&hist[best_j], 1);
+      if (rad2_bits) {
+        // upper bound of ||x - p||^2 from the expansion: the float32 rounding of the three terms is covered
+        // by kBoundSlack * (||x||^2 + ||p||^2)   (see tile_bounds_kernel)
+        float xn = 0.f;
+#pragma unroll
+        for (int c = 0; c < DP; ++c) xn = fmaf(x[c], x[c], xn);
+        const float up = best + xn + kBoundSlack * (xn + sn[best_j]);
+        atomicMax(&rad[best_j], __float_as_uint(fmaxf(up, 0.f)));
+      }
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < n_cells; i += blockDim.x)
+  for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
     if (hist[i]) atomicAdd(&counts[i], hist[i]);
+    if (rad2_bits && rad[i]) atomicMax(&rad2_bits[i], rad[i]);
+  }
 }
 
 template <typename T, int DP>
 int launch_assign(const T* X, int64_t ld, int64_t n, int d, const float* piv_t, const float* piv_norm, int nc, uint8_t* cell,
-                  int32_t* counts, cudaStream_t st) {
+                  int32_t* counts, unsigned int* rad2_bits, cudaStream_t st) {
   const size_t smem = ((size_t)DP * nc + nc + (size_t)DP * kAssignThreads) * sizeof(float);
   CM_CUDA_CHECK(cudaFuncSetAttribute(assign_cells_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(ceil_div(n, kAssignThreads) < kNumSMs * 2 ? ceil_div(n, kAssignThreads) : kNumSMs * 2);
-  assign_cells_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts);
+  assign_cells_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits);
   CM_LAUNCH_CHECK("assign_cells_kernel");
   return CM_OK;
 }
 template <typename T>
 int launch_assign_any(const T* X, int64_t ld, int64_t n, int d, const float* piv_t, const float* piv_norm, int nc,
-                      uint8_t* cell, int32_t* counts, cudaStream_t st) {
-  if (d <= 16) return launch_assign<T, 16>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
-  if (d <= 32) return launch_assign<T, 32>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
-  if (d <= 48) return launch_assign<T, 48>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
-  return launch_assign<T, kAssignMaxD>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, st);
+                      uint8_t* cell, int32_t* counts, unsigned int* rad2_bits, cudaStream_t st) {
+  if (d <= 16) return launch_assign<T, 16>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 32) return launch_assign<T, 32>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 48) return launch_assign<T, 48>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  return launch_assign<T, kAssignMaxD>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
 }
 
 // exclusive scan of the two count arrays -> cell starts (+ a copy used as scatter cursor)
@@ -449,14 +465,118 @@ cell_scatter_kernel(const uint8_t* __restrict__ cell, int64_t n, int32_t* __rest
   }
 }
 
-// home reference tile of every query tile: the tile holding the first reference of the cell of the
-// tile's first query
-__global__ void home_tile_kernel(const int32_t* __restrict__ perm_q, const uint8_t* __restrict__ q_cell,
-                                 const int32_t* __restrict__ r_starts, int n_q_tiles, int32_t* __restrict__ home) {
+// home cell of every query tile = the cell of the tile's first query: its scan of the reference starts there
+__global__ void home_cell_kernel(const int32_t* __restrict__ perm_q, const uint8_t* __restrict__ q_cell, int n_q_tiles,
+                                 int32_t* __restrict__ home) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_q_tiles) return;
   const int32_t q0 = perm_q[(int64_t)t * kMmaTile];
-  home[t] = q0 >= 0 ? r_starts[q_cell[q0]] / kMmaTile : 0;
+  home[t] = q0 >= 0 ? (int)q_cell[q0] : 0;
+}
+
+// Pruning bounds.  For query tile T and reference cell c (pivot p_c, radius rho_c = max ||r - p_c|| over the
+// cell's rows), every pair (q in T, r in c) has  ||q - r|| >= ||q - p_c|| - rho_c  (triangle inequality), so
+//   lb2[T][c] = max(0, min_{q in T} ||q - p_c|| - rho_c)^2
+// is a lower bound of every squared distance between the tile and the cell.  The tensor-core kernel
+// skips a cell while lb2 exceeds the largest current threshold of the tile's rows: nothing in the cell
+// can enter any row's candidate list, so the scan stays EXACT -- only distances that cannot matter are
+// never computed.  All roundings are directed (kBoundSlack, the final 1e-4 shrink) so the bound can
+// only be too small.  One block = two query tiles, thread = query row (same inner loop as
+// assign_cells_kernel), redux.min over the rows of a warp, then over the tile's four warps.
+template <typename T, int DP>
+__global__ void __launch_bounds__(kAssignThreads)
+tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const int32_t* __restrict__ perm_q, int64_t n_q_tiles,
+                   const float* __restrict__ piv_t, const float* __restrict__ piv_norm, int n_cells,
+                   const unsigned int* __restrict__ rad2_bits, float* __restrict__ lb2) {
+  extern __shared__ __align__(16) float asm_smem[];
+  float* sp = asm_smem;                          // [DP][n_cells]
+  float* sn = sp + (size_t)DP * n_cells;         // [n_cells]
+  float* sx = sn + n_cells;                      // [DP][kAssignThreads]
+  __shared__ uint32_t wmin[kAssignThreads / 32][kMaxCells];
+  __shared__ int32_t srow[kAssignThreads];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < DP * n_cells; i += blockDim.x) sp[i] = i < d * n_cells ? piv_t[i] : 0.f;
+  for (int i = threadIdx.x; i < n_cells; i += blockDim.x) sn[i] = piv_norm[i];
+  for (int i = threadIdx.x; i < DP * kAssignThreads; i += blockDim.x) sx[i] = 0.f;
+  __syncthreads();
+  constexpr int kTilesPerBlock = kAssignThreads / kMmaTile;
+  for (int64_t t0 = (int64_t)blockIdx.x * kTilesPerBlock; t0 < n_q_tiles; t0 += (int64_t)gridDim.x * kTilesPerBlock) {
+    const int64_t pos = t0 * kMmaTile + threadIdx.x;
+    srow[threadIdx.x] = pos < n_q_tiles * kMmaTile ? perm_q[pos] : -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAssignThreads * d; i += blockDim.x) {
+      const int r = i / d, c = i - r * d;
+      const int32_t row = srow[r];
+      sx[c * kAssignThreads + r] = row >= 0 ? (float)X[(int64_t)row * ld + c] : 0.f;
+    }
+    __syncthreads();
+    {
+      const bool valid = srow[threadIdx.x] >= 0;
+      float x[DP];
+      float xn = 0.f;
+#pragma unroll
+      for (int c = 0; c < DP; ++c) {
+        x[c] = sx[c * kAssignThreads + threadIdx.x];
+        xn = fmaf(x[c], x[c], xn);
+      }
+      for (int j0 = 0; j0 < n_cells; j0 += 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < DP; ++c) {
+          const float4 pv = *reinterpret_cast<const float4*>(sp + (size_t)c * n_cells + j0);
+          a0 = fmaf(x[c], pv.x, a0);
+          a1 = fmaf(x[c], pv.y, a1);
+          a2 = fmaf(x[c], pv.z, a2);
+          a3 = fmaf(x[c], pv.w, a3);
+        }
+        // lower bound of ||x - p_j||^2
+        const float v0 = valid ? (xn + sn[j0]) * (1.f - kBoundSlack) - 2.f * a0 : CUDART_INF_F;
+        const float v1 = valid ? (xn + sn[j0 + 1]) * (1.f - kBoundSlack) - 2.f * a1 : CUDART_INF_F;
+        const float v2 = valid ? (xn + sn[j0 + 2]) * (1.f - kBoundSlack) - 2.f * a2 : CUDART_INF_F;
+        const float v3 = valid ? (xn + sn[j0 + 3]) * (1.f - kBoundSlack) - 2.f * a3 : CUDART_INF_F;
+        const uint32_t m0 = __reduce_min_sync(0xffffffffu, float_to_ordered(v0));
+        const uint32_t m1 = __reduce_min_sync(0xffffffffu, float_to_ordered(v1));
+        const uint32_t m2 = __reduce_min_sync(0xffffffffu, float_to_ordered(v2));
+        const uint32_t m3 = __reduce_min_sync(0xffffffffu, float_to_ordered(v3));
+        if (lane == 0) *reinterpret_cast<uint4*>(&wmin[warp][j0]) = make_uint4(m0, m1, m2, m3);
+      }
+    }
+    __syncthreads();
+    constexpr int kWarpsPerTile = kMmaTile / 32;
+    for (int i = threadIdx.x; i < kTilesPerBlock * n_cells; i += blockDim.x) {
+      const int tl = i / n_cells, c = i - tl * n_cells;
+      if (t0 + tl < n_q_tiles) {
+        uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerTile; ++w) m = min(m, wmin[tl * kWarpsPerTile + w][c]);
+        const float dmin2 = fmaxf(ordered_to_float(m), 0.f);  // +inf for a tile of padding rows only
+        const float rho = sqrtf(__uint_as_float(rad2_bits[c])) * (1.f + 1e-6f);
+        const float lb = fmaxf(sqrtf(dmin2) * (1.f - 1e-6f) - rho, 0.f);
+        lb2[(t0 + tl) * kMaxCells + c] = lb * lb * (1.f - 1e-4f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int DP>
+int launch_tile_bounds(const T* X, int64_t ld, int d, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
+                       const float* piv_norm, int nc, const unsigned int* rad2_bits, float* lb2, cudaStream_t st) {
+  const size_t smem = ((size_t)DP * nc + nc + (size_t)DP * kAssignThreads) * sizeof(float);
+  CM_CUDA_CHECK(cudaFuncSetAttribute(tile_bounds_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = ceil_div(n_q_tiles, kAssignThreads / kMmaTile);
+  const int grid = (int)(blocks < kNumSMs * 2 ? blocks : kNumSMs * 2);
+  tile_bounds_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2);
+  CM_LAUNCH_CHECK("tile_bounds_kernel");
+  return CM_OK;
+}
+template <typename T>
+int launch_tile_bounds_any(const T* X, int64_t ld, int d, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
+                           const float* piv_norm, int nc, const unsigned int* rad2_bits, float* lb2, cudaStream_t st) {
+  if (d <= 16) return launch_tile_bounds<T, 16>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 32) return launch_tile_bounds<T, 32>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 48) return launch_tile_bounds<T, 48>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  return launch_tile_bounds<T, kAssignMaxD>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
 }
 
 // without cells: queries in their own order, reference rows scrambled by a golden-ratio stride so that
@@ -476,6 +596,11 @@ __global__ void fill_perm_kernel(int32_t* __restrict__ perm, int64_t n, int64_t 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
@@ -526,15 +651,18 @@ __device__ __forceinline__ int count_below(uint32_t keys, int cnt, float piv) {
   return c;
 }
 
-// Keep window: after a compaction a row holds between k + 2 and k + 18 candidates, never fewer than k,
+// Keep window: after a compaction a row holds between k + 6 and k + 22 candidates, never fewer than k,
 // so "everything below the threshold is in the buffer" holds for ANY scan order -- the order (home
 // cell first, see "coarse cells") only decides how quickly the threshold converges.  The window is
 // wide on purpose: the 32 rows of a warp compact in lockstep, so the number of counting passes is the
 // worst row's; a 17-wide target lets the first interpolated pivot land inside most of the time, and
 // keeping few entries frees the most slots per compaction.
 __device__ __forceinline__ void keep_window(int k, int& keep_lo, int& keep_hi) {
-  keep_hi = min(k + 18, kCandOut - 2);
-  keep_lo = min(k + 2, keep_hi - 4);
+  // keep_lo = k + 6: a row fails its certificate when the (keep_lo + 1)-th smallest distance lies within the
+  // tensor-core error of the k-th; with k + 2 that happened for ~1e-3 of the rows at 1.5 M references
+  // (each costs an exhaustive float64 scan), with k + 6 it needs seven near-ties in a row
+  keep_hi = min(k + 22, kCandOut - 2);
+  keep_lo = min(k + 6, keep_hi - 4);
 }
 
 // Shrink the buffer to between keep_lo and keep_hi entries and tighten the threshold.  Selection,
@@ -699,7 +827,15 @@ struct MmaParams {
   float* debug_out;   // optional raw accumulator dump [n_q_pad][n_r_tiles*128]
   int flags;          // development probes: 1 = skip the epilogue math, 2 = skip the reference tile copies
   long long* prof_out;  // optional [grid][8] cycle counters of the MMA warp (development)
-  const int32_t* home_tile;  // [n_q_tiles] reference tile at which the scan of a query tile starts (may be null)
+  // coarse cells (all null / 0 without cells): the scan of a query tile visits the reference cell by cell,
+  // starting at the tile's home cell, and skips the cells its bounds rule out
+  int n_cells;
+  const int32_t* home_cell;    // [n_q_tiles]
+  const int32_t* cell_starts;  // [kMaxCells + 1] first image position of every reference cell
+  const float* cell_lb2;       // [n_q_tiles][kMaxCells] lower bounds of the squared distance tile <-> cell (null: no pruning)
+  const double* q_norms;       // [n_q] ||q||^2, caller's row order
+  const int32_t* perm_q;       // [n_q_pad] scan position -> query row
+  ScaleInfo* info;
 };
 
 // Append the elements of one leaf (<= 3 consecutive columns) that are below the row's threshold:
@@ -824,8 +960,11 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
   }
 }
 
+constexpr int kTileRing = 16;  // > stages + accumulator buffers + 1: the producer never laps a reader
+
 struct MmaIssueArgs {
-  int n_tiles, stages, flags, first;  // this warp issues tiles first, first + 2, ...
+  int stages, flags, first;  // this warp issues tiles first, first + 2, ...
+  uint32_t tile_ring;        // shared address of the ring of scheduled tile ids (-1 = end of the scan)
   uint32_t b_bytes, b_smem, tmem_base;
   uint32_t bar_a_full, bar_b_full0, bar_b_empty0, bar_acc_full0, bar_acc_empty0;  // consecutive barriers are 8 bytes apart
   long long* prof;
@@ -850,13 +989,20 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
   int s = a.first % a.stages, buf = a.first % kAccBufs;
   uint32_t ph = 0, aph = 0;
   long long c_acc = 0, c_b = 0, c_issue = 0, t_start = clock64();
+  int n_done = 0;
 #pragma unroll 1
-  for (int it = a.first; it < a.n_tiles; it += 2) {
+  for (int it = a.first;; it += 2) {
     const long long t0 = a.prof ? clock64() : 0;
     if (!(a.flags & 8)) mbar_wait(a.bar_acc_empty0 + 8 * buf, aph ^ 1u);  // probe 8: free-running MMA issue
     const long long t1 = a.prof ? clock64() : 0;
     mbar_wait(a.bar_b_full0 + 8 * s, ph);
     const long long t2 = a.prof ? clock64() : 0;
+    if ((int)lds_u32_volatile(a.tile_ring + 4u * (uint32_t)(it & (kTileRing - 1))) < 0) {
+      // end of the scan: wake the epilogue on the accumulator barrier it is waiting for
+      if (leader) mbar_arrive(a.bar_acc_full0 + 8 * buf);
+      break;
+    }
+    ++n_done;
     tc_fence_after();
     const uint64_t b_desc = b_desc_base + (uint64_t)(((uint32_t)s * a.b_bytes) >> 4);
     const uint32_t d_tmem = a.tmem_base + kTmemACols + (uint32_t)buf * kMmaTile;
@@ -886,7 +1032,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
   if (a.prof && leader && a.first == 0) {
     a.prof[2] = c_issue;
     a.prof[3] = clock64() - t_start;
-    a.prof[4] = a.n_tiles;
+    a.prof[4] = n_done;
   }
 }
 
@@ -895,8 +1041,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * kMaxStages + 2 * kAccBufs];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ int32_t tile_ring[kTileRing];  // tile ids in the order the producer scheduled them, -1 = end
+  __shared__ uint32_t thr_pub[4];           // per epilogue warp: ordered-uint image of its rows' largest threshold (d^2 units)
+  __shared__ float s_lb2[kMaxCells];
+  __shared__ int32_t s_starts[kMaxCells + 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // development: per-CTA timeline (cycles since CTA start) written by lane 0 of the first epilogue warp
+  long long* tl = (p.prof_out && blockIdx.x < 8192 && warp == 2 && lane == 0) ? p.prof_out + 8 * 8192 + 8 + (size_t)blockIdx.x * 8 : nullptr;
+  const long long tl0 = clock64();
   // Work items.  Whole waves of query tiles scan the full reference; the query tiles of the last,
   // partial wave are cut into `splits` reference ranges so that they fill the machine too.
   int q_tile = blockIdx.x, t_begin = 0, t_end = p.n_r_tiles;
@@ -907,13 +1060,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     const int tiles_per_split = (p.n_r_tiles + p.splits - 1) / p.splits;
     t_begin = split * tiles_per_split;
     t_end = min(p.n_r_tiles, t_begin + tiles_per_split);
-  }
-  const int n_tiles = max(0, t_end - t_begin);
-  // scan order: start at the query tile's home reference tile (its coarse cell), wrap around inside the split
-  int t_first = t_begin;
-  if (p.home_tile) {
-    const int h = p.home_tile[q_tile];
-    if (h >= t_begin && h < t_end) t_first = h;
   }
 
   const uint32_t b_bytes = (uint32_t)kMmaTile * p.kp_r * 2;
@@ -926,6 +1072,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   auto bar_b_empty = [&](int s) { return smem_u32(&bars[1 + kMaxStages + s]); };
   auto bar_acc_full = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + b]); };
   auto bar_acc_empty = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + kAccBufs + b]); };
+  const uint32_t ring_addr = smem_u32(&tile_ring[0]);
+  const uint32_t thr_pub_addr = smem_u32(&thr_pub[0]);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 4);  // one arrive per epilogue warp once its 32 query rows are in TMEM
@@ -937,6 +1085,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       mbar_init(bar_acc_full(b), 1);
       mbar_init(bar_acc_empty(b), 4);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < 4; ++i) thr_pub[i] = 0xFFFFFFFFu;  // +inf: nothing can be pruned yet
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -947,54 +1096,94 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (tl) tl[0] = clock64() - tl0;
 
   if (warp == 0) {
-    // ===== producer: bulk-async copies of whole operand tiles =====
-    if (lane == 0 && n_tiles > 0) {
+    // ===== producer: decides which reference tiles are scanned, bulk-async copies of whole operand tiles =====
+    const bool cells = p.n_cells > 0;
+    const bool prune = cells && p.cell_lb2 != nullptr && !(p.flags & 32);  // probe 32: exhaustive scan
+    if (cells) {
+      for (int i = lane; i <= kMaxCells; i += 32) s_starts[i] = p.cell_starts[i];
+      if (prune)
+        for (int i = lane; i < kMaxCells; i += 32) s_lb2[i] = p.cell_lb2[(size_t)q_tile * kMaxCells + i];
+      __syncwarp();
+    }
+    if (lane == 0) {
       const uint32_t piece = b_bytes / kLoadPieces;  // b_bytes = 4096 * dc: divisible by 4 * 16
-      int s = 0, tcur = t_first;
+      int s = 0, it = 0;
       uint32_t ph = 0;
-      for (int it = 0; it < n_tiles; ++it) {
+      auto schedule = [&](int tile) {  // tile < 0: end marker, no data
         mbar_wait(bar_b_empty(s), ph ^ 1u);
-        if (p.flags & 2) {
+        sts_u32(ring_addr + 4u * (uint32_t)(it & (kTileRing - 1)), (uint32_t)tile);
+        if (tile < 0 || (p.flags & 2)) {
           mbar_arrive(bar_b_full(s));
         } else {
           mbar_expect_tx(bar_b_full(s), b_bytes);
-          const unsigned char* src = p.r_img + (size_t)tcur * b_bytes;
+          const unsigned char* src = p.r_img + (size_t)tile * b_bytes;
           const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
 #pragma unroll
           for (int c = 0; c < kLoadPieces; ++c) bulk_g2s(dst + c * piece, src + (size_t)c * piece, piece, bar_b_full(s));
         }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
-        if (++tcur == t_end) tcur = t_begin;
+        ++it;
+      };
+      if (!cells) {
+        for (int t = t_begin; t < t_end; ++t) schedule(t);
+      } else {
+        // cell by cell, home cell first, wrapping around.  Cells are contiguous runs of the image, so the
+        // only tile two scanned cells can share is the boundary tile of neighbours: `last` / `first` keep it
+        // from being scheduled twice.
+        const int home = p.home_cell[q_tile];
+        int last = -1, first = -1;
+        for (int j = 0; j < p.n_cells; ++j) {
+          int c = home + j;
+          if (c >= p.n_cells) c -= p.n_cells;
+          const int a = s_starts[c], b = s_starts[c + 1];
+          if (a == b) continue;
+          if (prune) {
+            // the largest threshold of the tile's 128 rows; a stale (larger) value is only conservative
+            const uint32_t m = max(max(lds_u32_volatile(thr_pub_addr), lds_u32_volatile(thr_pub_addr + 4)),
+                                   max(lds_u32_volatile(thr_pub_addr + 8), lds_u32_volatile(thr_pub_addr + 12)));
+            if (float_to_ordered(s_lb2[c]) > m) continue;  // no row of this tile can take anything from cell c
+          }
+          int t0 = max(a >> 7, t_begin), t1 = min((b - 1) >> 7, t_end - 1);
+          if (t0 == last) ++t0;
+          if (c < home && first >= 0 && t1 >= first) t1 = first - 1;  // wrapped part: never revisit the first tile
+          if (t0 > t1) continue;
+          if (first < 0 && c >= home) first = t0;  // first tile scheduled before the wrap
+          for (int t = t0; t <= t1; ++t) schedule(t);
+          last = t1;
+        }
       }
+      const int n_sched = it;
+      schedule(-1);  // one end marker per MMA warp (they own alternate iterations)
+      schedule(-1);
+      if (p.info) atomicAdd(&p.info->tiles_scanned, (unsigned long long)n_sched);
     }
   } else if (warp == 1 || warp == 6) {
     // ===== MMA issuers: the whole warp runs the loop, one elected lane drives the tensor core =====
-    if (n_tiles > 0) {
-      MmaIssueArgs a;
-      a.first = warp == 1 ? 0 : 1;
-      a.n_tiles = n_tiles;
-      a.stages = p.stages;
-      a.b_bytes = b_bytes;
-      a.b_smem = smem_u32(b_smem);
-      a.tmem_base = tmem_base;
-      a.bar_a_full = bar_a_full;
-      a.bar_b_full0 = bar_b_full(0);
-      a.bar_b_empty0 = bar_b_empty(0);
-      a.bar_acc_full0 = bar_acc_full(0);
-      a.bar_acc_empty0 = bar_acc_empty(0);
-      a.flags = p.flags;
-      a.prof = p.prof_out ? p.prof_out + (size_t)blockIdx.x * 8 : nullptr;
-      switch (p.dc) {
-        case 1: mma_issue_loop<1>(a); break;
-        case 2: mma_issue_loop<2>(a); break;
-        case 3: mma_issue_loop<3>(a); break;
-        case 4: mma_issue_loop<4>(a); break;
-        case 5: mma_issue_loop<5>(a); break;
-        case 6: mma_issue_loop<6>(a); break;
-        default: mma_issue_loop<7>(a); break;
-      }
+    MmaIssueArgs a;
+    a.first = warp == 1 ? 0 : 1;
+    a.tile_ring = ring_addr;
+    a.stages = p.stages;
+    a.b_bytes = b_bytes;
+    a.b_smem = smem_u32(b_smem);
+    a.tmem_base = tmem_base;
+    a.bar_a_full = bar_a_full;
+    a.bar_b_full0 = bar_b_full(0);
+    a.bar_b_empty0 = bar_b_empty(0);
+    a.bar_acc_full0 = bar_acc_full(0);
+    a.bar_acc_empty0 = bar_acc_empty(0);
+    a.flags = p.flags;
+    a.prof = p.prof_out ? p.prof_out + (size_t)blockIdx.x * 8 : nullptr;
+    switch (p.dc) {
+      case 1: mma_issue_loop<1>(a); break;
+      case 2: mma_issue_loop<2>(a); break;
+      case 3: mma_issue_loop<3>(a); break;
+      case 4: mma_issue_loop<4>(a); break;
+      case 5: mma_issue_loop<5>(a); break;
+      case 6: mma_issue_loop<6>(a); break;
+      default: mma_issue_loop<7>(a); break;
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4, one query row per thread =====
@@ -1020,26 +1209,46 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_full);
     }
+    if (tl) tl[1] = clock64() - tl0;
+    // threshold in squared-distance units: score = s^2 (||r||^2 - 2 q.r)  ->  d^2 = score / s^2 + ||q||^2
+    float inv_s2 = 0.f, qn = -CUDART_INF_F;  // padding rows never hold a cell back
+    if (p.cell_lb2) {
+      const float sc = scale_from_absmax(p.info->absmax_bits);
+      inv_s2 = 1.f / (sc * sc);  // exact: a power of two
+      const int32_t src_row = p.perm_q[q_row];
+      if (src_row >= 0) qn = (float)p.q_norms[src_row];
+    }
+    int published = 0;
+    auto publish = [&]() {
+      if (p.cell_lb2 && rc.n_compact != published) {  // thresholds only move in compactions (warp-uniform counter)
+        published = rc.n_compact;
+        const float t2 = qn >= 0.f ? (rc.thr * inv_s2 + qn) * (1.f + 1e-6f) : -CUDART_INF_F;  // rounded up
+        const uint32_t m = __reduce_max_sync(0xffffffffu, float_to_ordered(t2));
+        if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(thr_pub_addr + 4u * quad), "r"(m) : "memory");
+      }
+    };
 
     uint32_t va[64], vb[64];  // two register sets: the next half tile's tcgen05.ld overlaps this half's math
-    if (n_tiles > 0) {
-      mbar_wait(bar_acc_full(0), 0);
+    mbar_wait(bar_acc_full(0), 0);
+    if (tl) tl[2] = clock64() - tl0;
+    int tcur = (int)lds_u32_volatile(ring_addr);
+    int n_epi_tiles = 0;
+    if (tcur >= 0) {
       tc_fence_after();
       tmem_ld_32x32b_x64(t_lane, va);
     }
-    int tcur = t_first;
 #pragma unroll 1
-    for (int it = 0; it < n_tiles; ++it) {
+    for (int it = 0; tcur >= 0; ++it) {
       const int buf = it % kAccBufs;
       const uint32_t col_base = (uint32_t)tcur * kMmaTile;
-      if (++tcur == t_end) tcur = t_begin;
       const uint32_t t_buf = t_lane + (uint32_t)buf * kMmaTile;
       float* dbg = kDebug ? p.debug_out + q_row * ((int64_t)p.n_r_tiles * kMmaTile) + col_base : nullptr;
 
       if (p.flags & 4) {  // probe: MMA pipeline alone, accumulators are never read
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty(buf));
-        if (it + 1 < n_tiles) mbar_wait(bar_acc_full((it + 1) % kAccBufs), (uint32_t)((it + 1) / kAccBufs) & 1u);
+        mbar_wait(bar_acc_full((it + 1) % kAccBufs), (uint32_t)((it + 1) / kAccBufs) & 1u);
+        tcur = (int)lds_u32_volatile(ring_addr + 4u * (uint32_t)((it + 1) & (kTileRing - 1)));
         continue;
       }
       tmem_ld_wait();                          // columns 0..63 in va
@@ -1052,16 +1261,23 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty(buf));
-      if (it + 1 < n_tiles) {
+      {
         const int nbuf = (it + 1) % kAccBufs;
         mbar_wait(bar_acc_full(nbuf), (uint32_t)((it + 1) / kAccBufs) & 1u);
-        tc_fence_after();
-        tmem_ld_32x32b_x64(t_lane + (uint32_t)nbuf * kMmaTile, va);
+        tcur = (int)lds_u32_volatile(ring_addr + 4u * (uint32_t)((it + 1) & (kTileRing - 1)));
+        if (tcur >= 0) {
+          tc_fence_after();
+          tmem_ld_32x32b_x64(t_lane + (uint32_t)nbuf * kMmaTile, va);
+        }
       }
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[64 + j] = __uint_as_float(vb[j]);
       if (!(p.flags & 1)) process_half(vb, col_base + 64, rc, p.k, p.flags);
+      publish();
+      ++n_epi_tiles;
     }
+    if (tl) tl[3] = clock64() - tl0;
     compact_row(rc, p.k);  // leave at most kCandOut entries
+    if (tl) tl[4] = clock64() - tl0;
     if (p.prof_out && lane == 0) {
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 5], (unsigned long long)rc.n_trig);
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 6], (unsigned long long)rc.n_leaf);
@@ -1076,10 +1292,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     }
     p.cand_cnt[o] = rc.cnt;
     p.cand_thr[o] = rc.thr;
+    if (tl) {
+      tl[5] = clock64() - tl0;
+      tl[6] = n_epi_tiles;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tl) tl[7] = clock64() - tl0;
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -1232,7 +1453,7 @@ __global__ void publish_stats_kernel(const ScaleInfo* info, int64_t* stats_out) 
   stats_out[0] = (int64_t)info->fail_count;
   stats_out[1] = 0;
   stats_out[2] = (int64_t)info->cand_total;
-  stats_out[3] = 0;
+  stats_out[3] = (int64_t)info->tiles_scanned;
 }
 
 struct MmaPlan {
@@ -1283,7 +1504,7 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
   pl.n_cells = n_r >= kMinRefsForCells ? kMaxCells : 0;
   const size_t b_bytes = (size_t)kMmaTile * pl.kp_r * 2;
   const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2;
-  const size_t budget = 227 * 1024 - 1024;  // 1 KB of static shared memory (barriers, TMEM slot)
+  const size_t budget = 227 * 1024 - 4096;  // 4 KB of static shared memory (barriers, TMEM slot, tile ring, cell tables)
   int stages = (int)((budget - cand_bytes) / b_bytes);
   pl.stages = stages > kMaxStages ? kMaxStages : stages;
   pl.smem_bytes = b_bytes * pl.stages + cand_bytes;
@@ -1292,7 +1513,9 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
   pl.n_full = (pl.n_q_tiles / kNumSMs) * kNumSMs;
   const int64_t tail = pl.n_q_tiles - pl.n_full;
   int64_t s = 1;
-  if (tail > 0) {
+  if (tail > 0 && !(pl.n_cells > 0 && pl.n_full > 0 && !(g_probe_flags & 32))) {
+    // (with coarse cells a pruned scan is short and needs its home cell inside its range: once there
+    // are whole waves, the tail tiles stay whole too)
     s = pl.n_full > 0 ? kNumSMs / tail : ceil_div(2 * kNumSMs, tail);
     const int64_t cap = pl.n_r_tiles / 8 > 0 ? pl.n_r_tiles / 8 : 1;
     if (s > cap) s = cap;
@@ -1317,7 +1540,9 @@ struct MmaBuffers {
   int32_t* fail_rows;
   int32_t* perm_q;      // [n_q_pad] scan position -> query row, -1 = padding
   int32_t* perm_r;      // [n_r_pad] scan position -> reference row, -1 = padding
-  int32_t* home_tile;   // [n_q_tiles]
+  int32_t* home_cell;   // [n_q_tiles]
+  unsigned int* cell_rad2;  // [kMaxCells] float bits of the squared cell radius
+  float* cell_lb2;      // [n_q_tiles][kMaxCells]
   uint8_t* q_cell;      // [n_q]
   uint8_t* r_cell;      // [n_r]
   float* piv_t;         // [d][kMaxCells]
@@ -1341,7 +1566,9 @@ MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
   b.fail_rows = ws.take<int32_t>(n_q);
   b.perm_q = ws.take<int32_t>(pl.n_q_pad);
   b.perm_r = ws.take<int32_t>(pl.n_r_pad);
-  b.home_tile = ws.take<int32_t>(pl.n_q_tiles);
+  b.home_cell = ws.take<int32_t>(pl.n_q_tiles);
+  b.cell_rad2 = ws.take<unsigned int>(kMaxCells);
+  b.cell_lb2 = ws.take<float>(pl.n_cells > 0 ? (size_t)pl.n_q_tiles * kMaxCells : 1);
   b.q_cell = ws.take<uint8_t>(n_q);
   b.r_cell = ws.take<uint8_t>(n_r);
   b.piv_t = ws.take<float>((size_t)kMaxCells * 64);
@@ -1367,13 +1594,14 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
   if (pl.n_cells > 0) {
     const int nc = pl.n_cells;
     CM_CUDA_CHECK(cudaMemsetAsync(b.cell_counts, 0, 2 * kMaxCells * sizeof(int32_t), st));
+    CM_CUDA_CHECK(cudaMemsetAsync(b.cell_rad2, 0, kMaxCells * sizeof(unsigned int), st));
     CM_CUDA_CHECK(cudaMemsetAsync(b.perm_q, 0xFF, (size_t)pl.n_q_pad * sizeof(int32_t), st));
     CM_CUDA_CHECK(cudaMemsetAsync(b.perm_r, 0xFF, (size_t)pl.n_r_pad * sizeof(int32_t), st));
     gather_pivots_kernel<T><<<ceil_div(nc, 128), 128, 0, st>>>(R, ldr, n_r / nc, d, nc, b.piv_t, b.piv_norm);
     CM_LAUNCH_CHECK("gather_pivots_kernel");
-    int rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, st);
+    int rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, b.cell_rad2, st);
     if (rc_a) return rc_a;
-    rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, st);
+    rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, nullptr, st);
     if (rc_a) return rc_a;
     cell_scan_kernel<<<1, 32, 0, st>>>(b.cell_counts, nc, b.cell_starts, b.cell_cursor);
     CM_LAUNCH_CHECK("cell_scan_kernel");
@@ -1383,9 +1611,10 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     CM_LAUNCH_CHECK("cell_scatter_kernel(R)");
     cell_scatter_kernel<<<gs_q, kAssignThreads, 0, st>>>(b.q_cell, n_q, b.cell_cursor + kMaxCells, b.perm_q);
     CM_LAUNCH_CHECK("cell_scatter_kernel(Q)");
-    home_tile_kernel<<<(unsigned)ceil_div(pl.n_q_tiles, 128), 128, 0, st>>>(b.perm_q, b.q_cell, b.cell_starts,
-                                                                           (int)pl.n_q_tiles, b.home_tile);
-    CM_LAUNCH_CHECK("home_tile_kernel");
+    home_cell_kernel<<<(unsigned)ceil_div(pl.n_q_tiles, 128), 128, 0, st>>>(b.perm_q, b.q_cell, (int)pl.n_q_tiles, b.home_cell);
+    CM_LAUNCH_CHECK("home_cell_kernel");
+    rc_a = launch_tile_bounds_any<T>(Q, ldq, d, b.perm_q, pl.n_q_tiles, b.piv_t, b.piv_norm, nc, b.cell_rad2, b.cell_lb2, st);
+    if (rc_a) return rc_a;
   } else {
     fill_perm_kernel<<<(unsigned)(ceil_div(pl.n_q_pad, 256) < kNumSMs * 8 ? ceil_div(pl.n_q_pad, 256) : kNumSMs * 8), 256, 0, st>>>(
         b.perm_q, n_q, pl.n_q_pad, 0ULL);
@@ -1426,7 +1655,13 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.debug_out = debug_out;
   p.flags = g_probe_flags;
   p.prof_out = g_probe_prof;
-  p.home_tile = pl.n_cells > 0 ? b.home_tile : nullptr;
+  p.n_cells = pl.n_cells;
+  p.home_cell = pl.n_cells > 0 ? b.home_cell : nullptr;
+  p.cell_starts = pl.n_cells > 0 ? b.cell_starts : nullptr;
+  p.cell_lb2 = (pl.n_cells > 0 && !(g_probe_flags & 32)) ? b.cell_lb2 : nullptr;
+  p.q_norms = b.q_norms;
+  p.perm_q = b.perm_q;
+  p.info = b.info;
   const int64_t grid = pl.n_items;
   if (debug_out) {
     CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));

@@ -11,7 +11,7 @@ def run(n_q, n_r, d, flags, k=30, reps=3):
     q = torch.from_numpy(xq).cuda(); r = torch.from_numpy(xr).cuda()
     lib = _lib.load(); lib.cm_profile_enable(1)
     buf = (ctypes.c_float * 4)()
-    prof = torch.zeros(8 * 8192 + 8, dtype=torch.int64, device='cuda')
+    prof = torch.zeros(8 * 8192 + 8 + 8 * 8192, dtype=torch.int64, device='cuda')
     lib.cm_debug_probe_prof(prof.data_ptr())
     for f in flags:
         lib.cm_debug_probe_flags(f)
@@ -22,7 +22,9 @@ def run(n_q, n_r, d, flags, k=30, reps=3):
             lib.cm_profile_last_knn_ms(buf)
             if i: out.append(list(buf))
         ph = np.mean(out, 0)
-        cd = prof.cpu().numpy()[8 * 8192:]
+        cd = prof.cpu().numpy()[8 * 8192:8 * 8192 + 8]
+        tl = prof.cpu().numpy()[8 * 8192 + 8:].reshape(-1, 8); tl = tl[tl[:, 7] > 0]
+        print('timeline (mean cycles since CTA start): setup %.0f  q_stored %.0f  first_acc %.0f  loop_done %.0f  final_compact %.0f  writeout %.0f  tiles %.1f  cta_end %.0f  (n=%d)' % (*tl.mean(0), len(tl)))
         pr = prof.cpu().numpy()[:8 * 8192].reshape(-1, 8); pr = pr[pr[:, 4] > 0]
         per = pr[:, :4].sum(0) / pr[:, 4].sum()
         ev = pr[:, 5:8].sum(0) / (4 * 2 * pr[:, 4].sum())  # per epilogue warp and tile (tiles counted for warp 1 = half)
