@@ -12,7 +12,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "lib", "libcellmapper_b200.so")
+LIBPATH = os.environ.get("CM_LIBPATH") or os.path.join(HERE, "lib", "libcellmapper_b200.so")  # CM_LIBPATH: development builds (tools/)
 
 # enum mirrors
 F32, F64 = 0, 1

@@ -31,7 +31,10 @@ static inline int mma_seg_chunks(int d) { return (d + 3 + 7) / 8; }
 static inline int mma_kp_q(int d) { return 8 * ((3 * mma_seg_chunks(d) + 1) / 2 * 2); }  // even chunk count
 static inline int mma_kp_r(int d) { return 8 * 2 * mma_seg_chunks(d); }
 constexpr int kMmaMaxK = 40;     // neighbours supported by the candidate buffers
-constexpr int kCandCap = 128;    // per-row candidate slots in shared memory
+#ifndef CM_CAND_CAP
+#define CM_CAND_CAP 116
+#endif
+constexpr int kCandCap = CM_CAND_CAP;    // per-row candidate slots in shared memory
 constexpr int kKeepLo = 44;      // after compaction a row keeps between kKeepLo ..
 constexpr int kKeepHi = 60;      // .. and kKeepHi candidates
 constexpr int kCandOut = kKeepHi;

@@ -27,6 +27,14 @@
 #include "common.cuh"
 #include "knn_internal.cuh"
 
+// Development probes (cycle counters, per-CTA timelines) cost ~12 registers in the epilogue threads;
+// they are compiled in only with -DCM_DEV_PROBES (tools/probe_mma.py needs such a build).
+#ifdef CM_DEV_PROBES
+#define CM_PROBE(...) __VA_ARGS__
+#else
+#define CM_PROBE(...)
+#endif
+
 namespace cm {
 namespace {
 
@@ -603,6 +611,12 @@ __device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -611,11 +625,12 @@ constexpr uint32_t kCandStride = 32 * 4;  // bytes between consecutive entries o
 struct RowCand {
   uint32_t keys;     // shared address of this row's key column (ordered-uint image of the fp32 value)
   uint32_t idx;      // shared address of this row's index column
+  uint32_t dump;     // shared address of this thread's private half-tile copy (slow path)
   int cnt;
   uint32_t thr_key;  // every element seen so far with key < thr_key is in the buffer
   float thr;         // the same threshold as a float; +inf at start
-  int n_trig, n_leaf, n_compact;  // development counters (warp-uniform)
-  long long c_slow, c_compact;    // cycles inside the slow path / inside compactions (only with a probe buffer)
+  int n_compact;                  // compactions so far (warp-uniform)
+  CM_PROBE(int n_trig, n_leaf; long long c_slow, c_compact;)  // development counters
 };
 
 __device__ long long* g_compact_dbg = nullptr;  // development: per-lane compaction statistics
@@ -661,7 +676,7 @@ __device__ __forceinline__ void keep_window(int k, int& keep_lo, int& keep_hi) {
   // keep_lo = k + 6: a row fails its certificate when the (keep_lo + 1)-th smallest distance lies within the
   // tensor-core error of the k-th; with k + 2 that happened for ~1e-3 of the rows at 1.5 M references
   // (each costs an exhaustive float64 scan), with k + 6 it needs seven near-ties in a row
-  keep_hi = min(k + 22, kCandOut - 2);
+  keep_hi = min(k + CM_KEEP_HI, kCandOut - 2);
   keep_lo = min(k + 6, keep_hi - 4);
 }
 
@@ -675,11 +690,11 @@ __device__ __forceinline__ void keep_window(int k, int& keep_lo, int& keep_hi) {
 // Returns (new count) | (new threshold key << 32).
 __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint32_t idx, int cnt, uint32_t thr_key,
                                                             int k, long long* dbg) {
-  const long long tc0 = clock64();
+  CM_PROBE(const long long tc0 = clock64();)
   int keep_lo, keep_hi;
   keep_window(k, keep_lo, keep_hi);
   if (cnt <= keep_hi) return (unsigned long long)(uint32_t)cnt | ((unsigned long long)thr_key << 32);
-  int n_iter = 0;
+  CM_PROBE(int n_iter = 0;)
   float mn = CUDART_INF_F, mx = -CUDART_INF_F;
   {
     int e = 0;
@@ -702,7 +717,7 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
       mx = fmaxf(mx, kx);
     }
   }
-  const long long tc1 = clock64();
+  CM_PROBE(const long long tc1 = clock64();)
   // bracket in the ordered domain: count(key < lo) = c_lo < keep_lo ; count(key < hi) = c_hi > keep_hi
   uint32_t lo = float_to_ordered(mn), hi = float_to_ordered(mx) + 1u;  // keys are finite: no wrap
   int c_lo = 0, c_hi = cnt;
@@ -724,7 +739,7 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
       piv = lo + ((hi - lo) >> 1);
     }
     const int c = count_below(keys, cnt, ordered_to_float(piv));
-    ++n_iter;
+    CM_PROBE(++n_iter;)
     if (c < keep_lo) {
       lo = piv;
       c_lo = c;
@@ -743,7 +758,7 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
     c_tl = c_lo;
     tie = true;
   }
-  const long long tc2 = clock64();
+  CM_PROBE(const long long tc2 = clock64();)
   const float tl_f = ordered_to_float(tl);
   int extra = tie ? keep_hi - c_tl : 0;
   const uint32_t idx_off = idx - keys;
@@ -777,6 +792,7 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
   }
   for (; e < cnt; ++e) put(lds_u32(keys + e * kCandStride), lds_u32(idx + e * kCandStride));
   const int w = (int)((wa - keys) / kCandStride);
+#ifdef CM_DEV_PROBES
   if (dbg) {
     const long long tc3 = clock64();
     atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)n_iter);
@@ -786,20 +802,30 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
     atomicAdd((unsigned long long*)&dbg[4], 1ULL);
     atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)cnt);
   }
+#endif
   return (unsigned long long)(uint32_t)w | ((unsigned long long)tl << 32);
 }
 
 __device__ __forceinline__ void compact_row(RowCand& rc, int k) {
-  const long long t0 = clock64();
+  CM_PROBE(const long long t0 = clock64();)
   const unsigned long long r = compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, k, g_compact_dbg);
-  rc.c_compact += clock64() - t0;
+  CM_PROBE(rc.c_compact += clock64() - t0;)
   rc.cnt = (int)(uint32_t)r;
   rc.thr_key = (uint32_t)(r >> 32);
   rc.thr = rc.thr_key == 0xFFFFFFFFu ? CUDART_INF_F : ordered_to_float(rc.thr_key);
 }
 
-constexpr int kCandTrigger = kCandCap - 27;
-constexpr int kDenseLeaves = 8;  // flagged leaves (of 22) from which a half tile is appended without per-leaf branches  // a compaction check follows every <= 27 appended columns
+#ifndef CM_KEEP_HI
+#define CM_KEEP_HI 22
+#endif
+constexpr int kCandSlack = 22;   // a compaction check follows every <= 22 appended columns
+constexpr int kCandTrigger = kCandCap - kCandSlack;
+// private leaf queue of every epilogue thread (slow path): kQueueLeaves entries of 4 values + first column
+constexpr int kQueueLeaves = 5;
+constexpr uint32_t kQueueEntry = 32;  // bytes; 20 used, 32 keeps the 16-byte stores aligned
+static_assert(4 * kQueueLeaves <= kCandSlack, "the leaf queue is drained without an intermediate capacity check");
+constexpr uint32_t kDumpStride = kQueueEntry * kQueueLeaves + 16;  // +16: consecutive lanes start 4 banks apart... 
+constexpr size_t kDumpBytes = 4 * 32 * kDumpStride;
 
 // ------------------------------------------------------------------------------------------------
 // the tensor-core kernel
@@ -861,53 +887,48 @@ __device__ __forceinline__ void append_leaf(const uint32_t* v, uint32_t c0, RowC
   rc.cnt += added;
 }
 
-// One 64-column half tile of one query row (thread = row).  Fast path: a depth-4 tree of 3-input
-// minima and ONE warp vote.  Slow path: every lane marks which of its 22 leaves (3 columns each) hold a
-// passing element, one REDUX.OR turns that into a warp-uniform leaf mask, and the append code of a leaf
-// runs only if its bit is set.  All tests of the descent read that one ready register -- the epilogue
-// has a single warp per scheduler, so a chain of compare -> vote -> branch per tree node would run at
-// branch latency, not at issue rate.
+// One 64-column half tile of one query row (thread = row).  Fast path: a tree of minima over 16 leaves of
+// 4 columns and ONE warp vote.  Slow path (some row of the warp has an element below its threshold):
+// every lane queues ITS OWN flagged leaves in a private strip of shared memory -- a leaf is an aligned
+// register quad, so queueing it is one predicated 16-byte store plus the leaf number -- and then walks
+// that queue.  Registers cannot be indexed dynamically, and the earlier warp-uniform walk over the union
+// of all lanes' leaves (a 22-way switch per leaf) ran at branch latency: ~4.5 serial iterations per half
+// tile inside a query's own cluster, against ~2 here (the largest per-lane count), with no indirect
+// branch.  Halves in which some lane has more than kQueueLeaves flagged leaves (the first tiles of a
+// scan, before the thresholds are finite) take the straight-line path: predicated appends of all 64
+// columns.
 __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c0, RowCand& rc, int k, int flags) {
-  float t[22];
+  float t[16];
 #pragma unroll
-  for (int g = 0; g < 21; ++g)
-    t[g] = fminf(fminf(__uint_as_float(v[3 * g]), __uint_as_float(v[3 * g + 1])), __uint_as_float(v[3 * g + 2]));
-  t[21] = __uint_as_float(v[63]);
-  float u[8];
+  for (int g = 0; g < 16; ++g)
+    t[g] = fminf(fminf(fminf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), __uint_as_float(v[4 * g + 2])),
+                 __uint_as_float(v[4 * g + 3]));
+  float u[6];
 #pragma unroll
-  for (int g = 0; g < 7; ++g) u[g] = fminf(fminf(t[3 * g], t[3 * g + 1]), t[3 * g + 2]);
-  u[7] = t[21];
-  const float w0 = fminf(fminf(u[0], u[1]), u[2]);
-  const float w1 = fminf(fminf(u[3], u[4]), u[5]);
-  const float w2 = fminf(u[6], u[7]);
-  const float m = fminf(fminf(w0, w1), w2);
+  for (int g = 0; g < 5; ++g) u[g] = fminf(fminf(t[3 * g], t[3 * g + 1]), t[3 * g + 2]);
+  u[5] = t[15];
+  const float m = fminf(fminf(fminf(u[0], u[1]), u[2]), fminf(fminf(u[3], u[4]), u[5]));
   if (__any_sync(0xffffffffu, m < rc.thr) && !(flags & 16)) {  // probe 16: fast path only
     const float thr0 = rc.thr;
-    ++rc.n_trig;
-    const long long t_slow0 = clock64();
-    // three partial masks so the bit-insert chains are 8 deep instead of 22
-    uint32_t ma = 0, mb = 0, mc = 0;
+    CM_PROBE(++rc.n_trig; const long long t_slow0 = clock64();)
+    const uint32_t idx_off = rc.idx - rc.keys;
+    // this lane's flagged leaves; two partial masks so the bit-insert chains are 8 deep
+    uint32_t ma = 0, mb = 0;
 #pragma unroll
     for (int T = 0; T < 8; ++T) ma |= (t[T] < thr0) ? (1u << T) : 0u;
 #pragma unroll
     for (int T = 8; T < 16; ++T) mb |= (t[T] < thr0) ? (1u << T) : 0u;
+    const uint32_t mine = ma | mb;
+    const int n_mine = __popc(mine);
+    const int n_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)n_mine);
+    if (n_max > kQueueLeaves) {
+      // straight-line predicated appends of all 64 columns, a compaction check every kCandSlack columns
 #pragma unroll
-    for (int T = 16; T < 22; ++T) mc |= (t[T] < thr0) ? (1u << T) : 0u;
-    uint32_t leaves = __reduce_or_sync(0xffffffffu, ma | mb | mc);
-    // Loop over the flagged leaves only.  The switch just moves the leaf's three values into fixed
-    // registers (22 tiny cases behind one indexed branch); the append code exists once.  An unrolled
-    // `if (leaves & bit)` ladder costs a taken branch per skipped leaf and ran at instruction-fetch
-    // latency (ncu r1c: 62% "no instruction" stalls on those branches).
-    if (__popc(leaves) >= kDenseLeaves) {
-      // Dense half (the scan is inside the query's own neighbourhood: most leaves hold a passing element):
-      // straight-line predicated appends of all 64 columns, no per-leaf control flow.
-#pragma unroll
-      for (int W = 0; W < 3; ++W) {
+      for (int e0 = 0; e0 < 64; e0 += kCandSlack) {
         const float thr = rc.thr;
-        const uint32_t idx_off = rc.idx - rc.keys;
         uint32_t w = rc.keys + (uint32_t)rc.cnt * kCandStride;
 #pragma unroll
-        for (int e = 27 * W; e < 27 * W + 27 && e < 64; ++e) {
+        for (int e = e0; e < e0 + kCandSlack && e < 64; ++e) {
           const bool pass = __uint_as_float(v[e]) < thr;
           if (pass) { sts_u32(w, v[e]); sts_u32(w + idx_off, c0 + e); }
           w += pass ? kCandStride : 0u;
@@ -918,45 +939,45 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
           compact_row(rc, k);
         }
       }
-      rc.n_leaf += 22;
-      rc.c_slow += clock64() - t_slow0;
-      return;
-    }
-    int since_check = 0;
-    while (leaves) {
-      const int T = __ffs((int)leaves) - 1;
-      leaves &= leaves - 1;
-      ++rc.n_leaf;
-      uint32_t x0, x1, x2;
-      switch (T) {
-#define CM_LEAF(i) case i: x0 = v[3 * i]; x1 = v[3 * i + 1]; x2 = v[3 * i + 2]; break;
-        CM_LEAF(0) CM_LEAF(1) CM_LEAF(2) CM_LEAF(3) CM_LEAF(4) CM_LEAF(5) CM_LEAF(6) CM_LEAF(7) CM_LEAF(8) CM_LEAF(9)
-        CM_LEAF(10) CM_LEAF(11) CM_LEAF(12) CM_LEAF(13) CM_LEAF(14) CM_LEAF(15) CM_LEAF(16) CM_LEAF(17) CM_LEAF(18)
-        CM_LEAF(19) CM_LEAF(20)
-#undef CM_LEAF
-        default: x0 = v[63]; x1 = x2 = 0x7F800000u; break;  // leaf 21 is the single column 63 (+inf never passes)
-      }
-      const float thr = rc.thr;  // may have been tightened by a compaction since the mask was built
-      const bool p0 = __uint_as_float(x0) < thr, p1 = __uint_as_float(x1) < thr, p2 = __uint_as_float(x2) < thr;
-      const uint32_t w0 = rc.keys + (uint32_t)rc.cnt * kCandStride;
-      const uint32_t w1 = w0 + (p0 ? kCandStride : 0u);
-      const uint32_t w2 = w1 + (p1 ? kCandStride : 0u);
-      const uint32_t idx_off = rc.idx - rc.keys;
-      const uint32_t col = c0 + 3u * (uint32_t)T;
-      if (p0) { sts_u32(w0, x0); sts_u32(w0 + idx_off, col); }
-      if (p1) { sts_u32(w1, x1); sts_u32(w1 + idx_off, col + 1); }
-      if (p2) { sts_u32(w2, x2); sts_u32(w2 + idx_off, col + 2); }
-      rc.cnt += (int)p0 + (int)p1 + (int)p2;
-      // at most 27 appends between checks: cnt <= kCandTrigger + 27 <= kCandCap
-      if (++since_check == 9 || leaves == 0) {
-        since_check = 0;
-        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
-          ++rc.n_compact;
-          compact_row(rc, k);
+      CM_PROBE(rc.n_leaf += 16;)
+    } else {
+      // queue the flagged leaves (at most kQueueLeaves per lane)
+      uint32_t cur = rc.dump;
+#pragma unroll
+      for (int T = 0; T < 16; ++T)
+        if (mine & (1u << T)) {
+          sts_v4(cur, v[4 * T], v[4 * T + 1], v[4 * T + 2], v[4 * T + 3]);
+          sts_u32(cur + 16, (uint32_t)(4 * T));
+          cur += kQueueEntry;
+        }
+      for (int j = 0; j < n_max; ++j) {
+        CM_PROBE(++rc.n_leaf;)
+        if (j < n_mine) {
+          uint32_t x0, x1, x2, x3;
+          const uint32_t qa = rc.dump + kQueueEntry * (uint32_t)j;
+          lds_v4(qa, x0, x1, x2, x3);
+          const uint32_t col = c0 + lds_u32(qa + 16);
+          const float thr = rc.thr;
+          const bool p0 = __uint_as_float(x0) < thr, p1 = __uint_as_float(x1) < thr, p2 = __uint_as_float(x2) < thr,
+                     p3 = __uint_as_float(x3) < thr;
+          const uint32_t wa0 = rc.keys + (uint32_t)rc.cnt * kCandStride;
+          const uint32_t wa1 = wa0 + (p0 ? kCandStride : 0u);
+          const uint32_t wa2 = wa1 + (p1 ? kCandStride : 0u);
+          const uint32_t wa3 = wa2 + (p2 ? kCandStride : 0u);
+          if (p0) { sts_u32(wa0, x0); sts_u32(wa0 + idx_off, col); }
+          if (p1) { sts_u32(wa1, x1); sts_u32(wa1 + idx_off, col + 1); }
+          if (p2) { sts_u32(wa2, x2); sts_u32(wa2 + idx_off, col + 2); }
+          if (p3) { sts_u32(wa3, x3); sts_u32(wa3 + idx_off, col + 3); }
+          rc.cnt += (int)p0 + (int)p1 + (int)p2 + (int)p3;
         }
       }
+      // at most 4 * kQueueLeaves <= kCandSlack appends per row since the last check: cnt <= kCandCap
+      if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
+        ++rc.n_compact;
+        compact_row(rc, k);
+      }
     }
-    rc.c_slow += clock64() - t_slow0;
+    CM_PROBE(rc.c_slow += clock64() - t_slow0;)
   }
 }
 
@@ -1048,8 +1069,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // development: per-CTA timeline (cycles since CTA start) written by lane 0 of the first epilogue warp
-  long long* tl = (p.prof_out && blockIdx.x < 8192 && warp == 2 && lane == 0) ? p.prof_out + 8 * 8192 + 8 + (size_t)blockIdx.x * 8 : nullptr;
-  const long long tl0 = clock64();
+  CM_PROBE(long long* tl = (p.prof_out && blockIdx.x < 8192 && warp == 2 && lane == 0) ? p.prof_out + 8 * 8192 + 8 + (size_t)blockIdx.x * 8 : nullptr;
+           const long long tl0 = clock64();)
   // Work items.  Whole waves of query tiles scan the full reference; the query tiles of the last,
   // partial wave are cut into `splits` reference ranges so that they fill the machine too.
   int q_tile = blockIdx.x, t_begin = 0, t_end = p.n_r_tiles;
@@ -1066,6 +1087,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   unsigned char* b_smem = smem;
   uint32_t* cand_keys = reinterpret_cast<uint32_t*>(smem + b_bytes * p.stages);
   uint32_t* cand_idx = cand_keys + 4 * kCandCap * 32;
+  unsigned char* dump_base = reinterpret_cast<unsigned char*>(cand_idx + 4 * kCandCap * 32);
 
   const uint32_t bar_a_full = smem_u32(&bars[0]);
   auto bar_b_full = [&](int s) { return smem_u32(&bars[1 + s]); };
@@ -1096,7 +1118,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  if (tl) tl[0] = clock64() - tl0;
+  CM_PROBE(if (tl) tl[0] = clock64() - tl0;)
 
   if (warp == 0) {
     // ===== producer: decides which reference tiles are scanned, bulk-async copies of whole operand tiles =====
@@ -1192,11 +1214,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     RowCand rc;
     rc.keys = smem_u32(cand_keys + quad * kCandCap * 32 + lane);
     rc.idx = smem_u32(cand_idx + quad * kCandCap * 32 + lane);
+    rc.dump = smem_u32(dump_base + (size_t)(quad * 32 + lane) * kDumpStride);
     rc.cnt = 0;
     rc.thr_key = 0xFFFFFFFFu;
     rc.thr = CUDART_INF_F;
-    rc.n_trig = rc.n_leaf = rc.n_compact = 0;
-    rc.c_slow = rc.c_compact = 0;
+    rc.n_compact = 0;
+    CM_PROBE(rc.n_trig = rc.n_leaf = 0; rc.c_slow = rc.c_compact = 0;)
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
     const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t t_lane = t_lane_a + kTmemACols;
@@ -1209,7 +1232,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_full);
     }
-    if (tl) tl[1] = clock64() - tl0;
+    CM_PROBE(if (tl) tl[1] = clock64() - tl0;)
     // threshold in squared-distance units: score = s^2 (||r||^2 - 2 q.r)  ->  d^2 = score / s^2 + ||q||^2
     float inv_s2 = 0.f, qn = -CUDART_INF_F;  // padding rows never hold a cell back
     if (p.cell_lb2) {
@@ -1230,9 +1253,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
 
     uint32_t va[64], vb[64];  // two register sets: the next half tile's tcgen05.ld overlaps this half's math
     mbar_wait(bar_acc_full(0), 0);
-    if (tl) tl[2] = clock64() - tl0;
+    CM_PROBE(if (tl) tl[2] = clock64() - tl0;)
     int tcur = (int)lds_u32_volatile(ring_addr);
-    int n_epi_tiles = 0;
+    CM_PROBE(int n_epi_tiles = 0;)
     if (tcur >= 0) {
       tc_fence_after();
       tmem_ld_32x32b_x64(t_lane, va);
@@ -1273,11 +1296,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[64 + j] = __uint_as_float(vb[j]);
       if (!(p.flags & 1)) process_half(vb, col_base + 64, rc, p.k, p.flags);
       publish();
-      ++n_epi_tiles;
+      CM_PROBE(++n_epi_tiles;)
     }
-    if (tl) tl[3] = clock64() - tl0;
+    CM_PROBE(if (tl) tl[3] = clock64() - tl0;)
     compact_row(rc, p.k);  // leave at most kCandOut entries
-    if (tl) tl[4] = clock64() - tl0;
+    CM_PROBE(if (tl) tl[4] = clock64() - tl0;)
+#ifdef CM_DEV_PROBES
     if (p.prof_out && lane == 0) {
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 5], (unsigned long long)rc.n_trig);
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 6], (unsigned long long)rc.n_leaf);
@@ -1285,6 +1309,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 0], (unsigned long long)rc.c_slow);
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 1], (unsigned long long)rc.c_compact);
     }
+#endif
     const int64_t o = (int64_t)blockIdx.x * kMmaTile + row_in_tile;
     for (int e = 0; e < rc.cnt; ++e) {
       p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
@@ -1292,15 +1317,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     }
     p.cand_cnt[o] = rc.cnt;
     p.cand_thr[o] = rc.thr;
-    if (tl) {
-      tl[5] = clock64() - tl0;
-      tl[6] = n_epi_tiles;
-    }
+    CM_PROBE(if (tl) { tl[5] = clock64() - tl0; tl[6] = n_epi_tiles; })
   }
 
   tc_fence_before();
   __syncthreads();
-  if (tl) tl[7] = clock64() - tl0;
+  CM_PROBE(if (tl) tl[7] = clock64() - tl0;)
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -1503,7 +1525,7 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
   pl.perm_mul = scramble_multiplier(pl.n_r_pad);
   pl.n_cells = n_r >= kMinRefsForCells ? kMaxCells : 0;
   const size_t b_bytes = (size_t)kMmaTile * pl.kp_r * 2;
-  const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2;
+  const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2 + kDumpBytes;
   const size_t budget = 227 * 1024 - 4096;  // 4 KB of static shared memory (barriers, TMEM slot, tile ring, cell tables)
   int stages = (int)((budget - cand_bytes) / b_bytes);
   pl.stages = stages > kMaxStages ? kMaxStages : stages;
