@@ -29,6 +29,9 @@
 
 // Development probes (cycle counters, per-CTA timelines) cost ~12 registers in the epilogue threads;
 // they are compiled in only with -DCM_DEV_PROBES (tools/probe_mma.py needs such a build).
+#ifndef CM_KEEP_HI
+#define CM_KEEP_HI 22  // upper end of the keep window above k (tuning builds override it)
+#endif
 #ifdef CM_DEV_PROBES
 #define CM_PROBE(...) __VA_ARGS__
 #else
@@ -625,7 +628,8 @@ constexpr uint32_t kCandStride = 32 * 4;  // bytes between consecutive entries o
 struct RowCand {
   uint32_t keys;     // shared address of this row's key column (ordered-uint image of the fp32 value)
   uint32_t idx;      // shared address of this row's index column
-  uint32_t dump;     // shared address of this thread's private half-tile copy (slow path)
+  uint32_t dump;     // shared address of this thread's private leaf queue (slow path)
+  int qn;            // entries in the leaf queue
   int cnt;
   uint32_t thr_key;  // every element seen so far with key < thr_key is in the buffer
   float thr;         // the same threshold as a float; +inf at start
@@ -815,16 +819,15 @@ __device__ __forceinline__ void compact_row(RowCand& rc, int k) {
   rc.thr = rc.thr_key == 0xFFFFFFFFu ? CUDART_INF_F : ordered_to_float(rc.thr_key);
 }
 
-#ifndef CM_KEEP_HI
-#define CM_KEEP_HI 22
-#endif
 constexpr int kCandSlack = 22;   // a compaction check follows every <= 22 appended columns
 constexpr int kCandTrigger = kCandCap - kCandSlack;
-// private leaf queue of every epilogue thread (slow path): kQueueLeaves entries of 4 values + first column
-constexpr int kQueueLeaves = 5;
-constexpr uint32_t kQueueEntry = 32;  // bytes; 20 used, 32 keeps the 16-byte stores aligned
-static_assert(4 * kQueueLeaves <= kCandSlack, "the leaf queue is drained without an intermediate capacity check");
-constexpr uint32_t kDumpStride = kQueueEntry * kQueueLeaves + 16;  // +16: consecutive lanes start 4 banks apart... 
+// private leaf queue of every epilogue thread (slow path): kQueueCap entries of 4 values (16 bytes) followed
+// by their kQueueCap first-column numbers; +16 so that consecutive lanes start 4 banks apart
+#ifndef CM_QUEUE_CAP
+#define CM_QUEUE_CAP 8
+#endif
+constexpr int kQueueCap = CM_QUEUE_CAP;
+constexpr uint32_t kDumpStride = 20 * kQueueCap + 16;
 constexpr size_t kDumpBytes = 4 * 32 * kDumpStride;
 
 // ------------------------------------------------------------------------------------------------
@@ -887,16 +890,56 @@ __device__ __forceinline__ void append_leaf(const uint32_t* v, uint32_t c0, RowC
   rc.cnt += added;
 }
 
+// Drain the per-lane leaf queues into the candidate buffers: iteration j handles entry j of every lane
+// that has one, so the trip count is the longest queue of the warp.
+__device__ __forceinline__ void drain_queue(RowCand& rc, int k) {
+  const int n_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)rc.qn);
+  const uint32_t idx_off = rc.idx - rc.keys;
+  int since_check = 0;
+  for (int j = 0; j < n_max; ++j) {
+    CM_PROBE(++rc.n_leaf;)
+    if (j < rc.qn) {
+      uint32_t x0, x1, x2, x3;
+      lds_v4(rc.dump + 16u * (uint32_t)j, x0, x1, x2, x3);
+      const uint32_t col = lds_u32(rc.dump + 16u * kQueueCap + 4u * (uint32_t)j);
+      const float thr = rc.thr;
+      const bool p0 = __uint_as_float(x0) < thr, p1 = __uint_as_float(x1) < thr, p2 = __uint_as_float(x2) < thr,
+                 p3 = __uint_as_float(x3) < thr;
+      const uint32_t wa0 = rc.keys + (uint32_t)rc.cnt * kCandStride;
+      const uint32_t wa1 = wa0 + (p0 ? kCandStride : 0u);
+      const uint32_t wa2 = wa1 + (p1 ? kCandStride : 0u);
+      const uint32_t wa3 = wa2 + (p2 ? kCandStride : 0u);
+      if (p0) { sts_u32(wa0, x0); sts_u32(wa0 + idx_off, col); }
+      if (p1) { sts_u32(wa1, x1); sts_u32(wa1 + idx_off, col + 1); }
+      if (p2) { sts_u32(wa2, x2); sts_u32(wa2 + idx_off, col + 2); }
+      if (p3) { sts_u32(wa3, x3); sts_u32(wa3 + idx_off, col + 3); }
+      rc.cnt += (int)p0 + (int)p1 + (int)p2 + (int)p3;
+    }
+    // at most kCandSlack appends per row between checks: cnt <= kCandTrigger + kCandSlack = kCandCap
+    if (++since_check == kCandSlack / 4 || j + 1 == n_max) {
+      since_check = 0;
+      if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
+        ++rc.n_compact;
+        compact_row(rc, k);
+      }
+    }
+  }
+  rc.qn = 0;
+}
+
 // One 64-column half tile of one query row (thread = row).  Fast path: a tree of minima over 16 leaves of
 // 4 columns and ONE warp vote.  Slow path (some row of the warp has an element below its threshold):
-// every lane queues ITS OWN flagged leaves in a private strip of shared memory -- a leaf is an aligned
-// register quad, so queueing it is one predicated 16-byte store plus the leaf number -- and then walks
-// that queue.  Registers cannot be indexed dynamically, and the earlier warp-uniform walk over the union
-// of all lanes' leaves (a 22-way switch per leaf) ran at branch latency: ~4.5 serial iterations per half
-// tile inside a query's own cluster, against ~2 here (the largest per-lane count), with no indirect
-// branch.  Halves in which some lane has more than kQueueLeaves flagged leaves (the first tiles of a
-// scan, before the thresholds are finite) take the straight-line path: predicated appends of all 64
-// columns.
+// every lane pushes ITS OWN flagged leaves onto a private queue in shared memory -- a leaf is an aligned
+// register quad, so a push is one predicated 16-byte store plus the leaf's first column -- and moves on.
+// The queues are drained (drain_queue) only when one of them could overflow: the serial part of the slow
+// path, with its shared-memory round trips, votes and compactions, then runs once per ~20 half tiles
+// with most lanes busy, instead of once per half tile for one or two lanes.  (Registers cannot be
+// indexed dynamically; the first version walked the union of all lanes' leaves through a 22-way switch
+// and ran at branch latency.)  An element is tested against the threshold of the moment it is drained,
+// which is at most as large as the one it was queued under, so the invariant "everything seen below the
+// threshold is in the buffer or in the queue" holds.  Halves in which one lane alone has more than a
+// queue of flagged leaves (the first tiles of a scan, before the thresholds are finite) take the
+// straight-line path: predicated appends of all 64 columns.
 __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c0, RowCand& rc, int k, int flags) {
   float t[16];
 #pragma unroll
@@ -911,7 +954,6 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
   if (__any_sync(0xffffffffu, m < rc.thr) && !(flags & 16)) {  // probe 16: fast path only
     const float thr0 = rc.thr;
     CM_PROBE(++rc.n_trig; const long long t_slow0 = clock64();)
-    const uint32_t idx_off = rc.idx - rc.keys;
     // this lane's flagged leaves; two partial masks so the bit-insert chains are 8 deep
     uint32_t ma = 0, mb = 0;
 #pragma unroll
@@ -920,63 +962,43 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     for (int T = 8; T < 16; ++T) mb |= (t[T] < thr0) ? (1u << T) : 0u;
     const uint32_t mine = ma | mb;
     const int n_mine = __popc(mine);
-    const int n_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)n_mine);
-    if (n_max > kQueueLeaves) {
-      // straight-line predicated appends of all 64 columns, a compaction check every kCandSlack columns
+    if (__any_sync(0xffffffffu, rc.qn + n_mine > kQueueCap)) {
+      drain_queue(rc, k);
+      if (__any_sync(0xffffffffu, n_mine > kQueueCap)) {
+        // straight-line predicated appends of all 64 columns, a compaction check every kCandSlack columns
+        const uint32_t idx_off = rc.idx - rc.keys;
 #pragma unroll
-      for (int e0 = 0; e0 < 64; e0 += kCandSlack) {
-        const float thr = rc.thr;
-        uint32_t w = rc.keys + (uint32_t)rc.cnt * kCandStride;
-#pragma unroll
-        for (int e = e0; e < e0 + kCandSlack && e < 64; ++e) {
-          const bool pass = __uint_as_float(v[e]) < thr;
-          if (pass) { sts_u32(w, v[e]); sts_u32(w + idx_off, c0 + e); }
-          w += pass ? kCandStride : 0u;
-        }
-        rc.cnt = (int)((w - rc.keys) / kCandStride);
-        if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
-          ++rc.n_compact;
-          compact_row(rc, k);
-        }
-      }
-      CM_PROBE(rc.n_leaf += 16;)
-    } else {
-      // queue the flagged leaves (at most kQueueLeaves per lane)
-      uint32_t cur = rc.dump;
-#pragma unroll
-      for (int T = 0; T < 16; ++T)
-        if (mine & (1u << T)) {
-          sts_v4(cur, v[4 * T], v[4 * T + 1], v[4 * T + 2], v[4 * T + 3]);
-          sts_u32(cur + 16, (uint32_t)(4 * T));
-          cur += kQueueEntry;
-        }
-      for (int j = 0; j < n_max; ++j) {
-        CM_PROBE(++rc.n_leaf;)
-        if (j < n_mine) {
-          uint32_t x0, x1, x2, x3;
-          const uint32_t qa = rc.dump + kQueueEntry * (uint32_t)j;
-          lds_v4(qa, x0, x1, x2, x3);
-          const uint32_t col = c0 + lds_u32(qa + 16);
+        for (int e0 = 0; e0 < 64; e0 += kCandSlack) {
           const float thr = rc.thr;
-          const bool p0 = __uint_as_float(x0) < thr, p1 = __uint_as_float(x1) < thr, p2 = __uint_as_float(x2) < thr,
-                     p3 = __uint_as_float(x3) < thr;
-          const uint32_t wa0 = rc.keys + (uint32_t)rc.cnt * kCandStride;
-          const uint32_t wa1 = wa0 + (p0 ? kCandStride : 0u);
-          const uint32_t wa2 = wa1 + (p1 ? kCandStride : 0u);
-          const uint32_t wa3 = wa2 + (p2 ? kCandStride : 0u);
-          if (p0) { sts_u32(wa0, x0); sts_u32(wa0 + idx_off, col); }
-          if (p1) { sts_u32(wa1, x1); sts_u32(wa1 + idx_off, col + 1); }
-          if (p2) { sts_u32(wa2, x2); sts_u32(wa2 + idx_off, col + 2); }
-          if (p3) { sts_u32(wa3, x3); sts_u32(wa3 + idx_off, col + 3); }
-          rc.cnt += (int)p0 + (int)p1 + (int)p2 + (int)p3;
+          uint32_t w = rc.keys + (uint32_t)rc.cnt * kCandStride;
+#pragma unroll
+          for (int e = e0; e < e0 + kCandSlack && e < 64; ++e) {
+            const bool pass = __uint_as_float(v[e]) < thr;
+            if (pass) { sts_u32(w, v[e]); sts_u32(w + idx_off, c0 + e); }
+            w += pass ? kCandStride : 0u;
+          }
+          rc.cnt = (int)((w - rc.keys) / kCandStride);
+          if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
+            ++rc.n_compact;
+            compact_row(rc, k);
+          }
         }
-      }
-      // at most 4 * kQueueLeaves <= kCandSlack appends per row since the last check: cnt <= kCandCap
-      if (__any_sync(0xffffffffu, rc.cnt > kCandTrigger)) {
-        ++rc.n_compact;
-        compact_row(rc, k);
+        CM_PROBE(rc.n_leaf += 16; rc.c_slow += clock64() - t_slow0;)
+        return;
       }
     }
+    // push the flagged leaves (the queue has room for all of them)
+    uint32_t cur = rc.dump + 16u * (uint32_t)rc.qn;
+    uint32_t ccur = rc.dump + 16u * kQueueCap + 4u * (uint32_t)rc.qn;
+#pragma unroll
+    for (int T = 0; T < 16; ++T)
+      if (mine & (1u << T)) {
+        sts_v4(cur, v[4 * T], v[4 * T + 1], v[4 * T + 2], v[4 * T + 3]);
+        sts_u32(ccur, c0 + (uint32_t)(4 * T));
+        cur += 16;
+        ccur += 4;
+      }
+    rc.qn += n_mine;
     CM_PROBE(rc.c_slow += clock64() - t_slow0;)
   }
 }
@@ -1216,6 +1238,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     rc.idx = smem_u32(cand_idx + quad * kCandCap * 32 + lane);
     rc.dump = smem_u32(dump_base + (size_t)(quad * 32 + lane) * kDumpStride);
     rc.cnt = 0;
+    rc.qn = 0;
     rc.thr_key = 0xFFFFFFFFu;
     rc.thr = CUDART_INF_F;
     rc.n_compact = 0;
@@ -1299,6 +1322,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       CM_PROBE(++n_epi_tiles;)
     }
     CM_PROBE(if (tl) tl[3] = clock64() - tl0;)
+    drain_queue(rc, p.k);
     compact_row(rc, p.k);  // leave at most kCandOut entries
     CM_PROBE(if (tl) tl[4] = clock64() - tl0;)
 #ifdef CM_DEV_PROBES
