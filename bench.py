@@ -6,9 +6,11 @@
 
 A *step* is one pass of the hot path over one batch of synthetic input:
 search (k=30) -> gaussian kernel -> row-normalised mapping matrix -> celltype vote + X_umap SpMM.
-Workload at N=1: BASELINE config 2 (100k query -> 100k reference, d=50).  For N>1 every rank keeps
-the same per-GPU work (its own 100k queries, the 100k reference replicated): weak scaling, the only
-collective is the all-reduce of the kernel bandwidth statistics.
+Default workload: the configuration BASELINE.json's metric is quoted on, C3 = 1.5M query -> 1.5M
+reference, d=50 (it fits one B200).  For N>1 the 1.5M queries are sharded over the ranks and the
+reference is replicated (north_star's default partitioning): the job is the same at every N, i.e.
+STRONG scaling; the only collective on the data path is the all-reduce of the three kernel-bandwidth
+statistics.  `--workload C2` runs BASELINE config 2 (100k -> 100k) the same way.
 
 `value`  : whole-job cells/s with inputs resident in HBM (CUDA events, L2 flushed between steps).
 `e2e`    : the same metric through the public `CellMapper.map()` API with HOST buffers (pinned),
@@ -50,13 +52,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def make_inputs(name: str, rank: int):
+def make_inputs(name: str, rank: int = 0, world: int = 1):
+    """Synthetic Gaussian-mixture embeddings of the named shape; every rank draws the
+    same arrays and keeps its contiguous block of query rows."""
     from cellmapper_b200 import synth
+    from cellmapper_b200.dist import shard_bounds
 
     n_q, n_r, d, n_comp = WORKLOADS[name]
     centres = synth.mixture_centres(n_comp, d)
     xr, cr = synth.mixture_embedding(n_r, centres, seed=1)
-    xq, _ = synth.mixture_embedding(n_q, centres, seed=2 + rank)
+    xq, _ = synth.mixture_embedding(n_q, centres, seed=2)
+    lo, hi = shard_bounds(n_q, world, rank)
+    xq = np.ascontiguousarray(xq[lo:hi])
     labels = synth.celltype_names(cr)
     umap = synth.umap_like(n_r, UMAP_DIMS)
     return xr, xq, cr, labels, umap
@@ -157,7 +164,7 @@ def reference_arm(args):
     if rank != 0:
         return
     name = args.workload
-    xr, xq, cr, labels, umap = make_inputs(name, 0)
+    xr, xq, cr, labels, umap = make_inputs(name)
     ns = cpu_sample_queries(name)
     xs = xq[:ns]
     times = []
@@ -178,11 +185,11 @@ def reference_arm(args):
         "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{name}: {n_q} query -> {n_r} reference, d={d}, k={K}, gaussian, celltype + X_umap transfer", "sample": f"first {ns} queries against the full reference"},
+        "config": {"workload": f"{name}: {n_q} query -> {n_r} reference, d={d}, k={K}, gaussian kernel, celltype + X_umap transfer", "sample": f"first {ns} queries against the full reference"},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cpu_threads(), "kind": "port", "sample": f"{ns} of {n_q} queries x full {n_r} reference per step"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -213,8 +220,9 @@ def b200_arm(args):
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
     name = args.workload
-    n_q, n_r, d, _ = WORKLOADS[name]
-    xr, xq, cr, labels, umap = make_inputs(name, rank)
+    n_q_total, n_r, d, _ = WORKLOADS[name]
+    xr, xq, cr, labels, umap = make_inputs(name, rank, world)
+    n_q = xq.shape[0]  # this rank's block of query rows
 
     # pinned host buffers (the e2e arm copies from these every step)
     def pin(a):
@@ -241,6 +249,7 @@ def b200_arm(args):
     umap_d, codes_d = umap_t.to(dev), codes_t.to(dev)
 
     PHASES = ["search", "edge_stats", "kernel_to_csr", "vote", "spmm"]
+    search_stats = []  # device int64[4] per search: [fallback rows, -, candidates re-ranked, (query tile, reference tile) pairs evaluated]
 
     def device_step(marks=None):
         def mark():
@@ -250,7 +259,8 @@ def b200_arm(args):
                 marks.append(e)
 
         mark()
-        dd, ii = device.knn_search(xq_d, xr_d, K, dist_mode=mode)
+        dd, ii, st_search = device.knn_search(xq_d, xr_d, K, dist_mode=mode, return_stats=True)
+        search_stats.append(st_search)
         mark()
         st = device.edge_stats(dd, ii, allreduce=allreduce, need_std=False)
         mark()
@@ -277,6 +287,7 @@ def b200_arm(args):
 
     buf4 = (ctypes.c_float * 4)()
     step_marks = []
+    search_stats.clear()
     for s in range(args.steps):
         flush.zero_()
         ev[s][0].record()
@@ -293,14 +304,17 @@ def b200_arm(args):
     lib.cm_profile_enable(0)
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    st_host = torch.stack(search_stats).double().mean(0).cpu().numpy()
+    tiles_scanned, fallback_rows = float(st_host[3]), float(st_host[0])
     path_ms = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in step_marks])) for i, n in enumerate(PHASES)}
     phase_ms /= args.steps
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
     t_dev = float(tt.item())
-    value = n_q * world * args.steps / t_dev
+    value = n_q_total * args.steps / t_dev
     dd, ii, code, conf, emb = res
+
 
     # ---------------- end-to-end arm: public API, host buffers ----------------
     ref_ad = AnnData(
@@ -330,19 +344,26 @@ def b200_arm(args):
     if world > 1:
         tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
     t_e2e = float(tt.item())
-    e2e_value = n_q * world * args.steps / t_e2e
-    h2d = xr.nbytes + xq.nbytes + codes.nbytes + umap.nbytes
-    d2h = n_q * 4 + n_q * 4 + n_q * UMAP_DIMS * 4 + 8
+    e2e_value = n_q_total * args.steps / t_e2e
+    # whole job, all ranks: every rank uploads the replicated reference side and its own query block
+    h2d = world * (xr.nbytes + codes.nbytes + umap.nbytes) + n_q_total * d * 4
+    d2h = n_q_total * (4 + 4 + UMAP_DIMS * 4) + 8 * world
 
     if rank != 0:
         return
 
     # ---------------- roofline of the dominant kernel (mma_topk: tensor pipe) ----------------
+    # The search is exact but pruned: whole reference cells whose triangle-inequality lower bound exceeds
+    # every threshold of a query tile are never multiplied.  `achieved` counts the
+    # algorithmic flops of the pairs the kernel actually evaluated (2*d per pair, un-padded d, one
+    # fp32-equivalent product per pair-dimension); `brute_force_equivalent` is 2*n_q*n_r*d over the same
+    # time, the figure comparable with an exhaustive scan (it may exceed the peak: work not done).
     peaks = measured_peaks()
-    flops = 2.0 * n_q * n_r * d  # algorithmic: un-padded d, one fp32-equivalent product per pair-dim
-    t_mma = phase_ms[1] / 1e3
-    achieved = flops / t_mma / 1e12 if t_mma > 0 else None
     peak = peaks["bf16_tflops"] / 3.0  # three fp16 passes per fp32-accurate product
+    t_mma = phase_ms[1] / 1e3
+    pairs = tiles_scanned * 128.0 * 128.0
+    achieved = 2.0 * pairs * d / t_mma / 1e12 if t_mma > 0 else None
+    n_pairs_all = float(-(-n_q // 128)) * float(-(-n_r // 128))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -357,8 +378,28 @@ def b200_arm(args):
         "traffic": traffic,
         "peak_source": f"{peaks['source']} cuBLAS bf16 burst {peaks['bf16_tflops']} TFLOP/s / 3 split-precision passes",
         "avg_launch_ms": phase_ms[1],
+        "pairs_evaluated_frac": tiles_scanned / n_pairs_all,
+        "brute_force_equivalent": {"tflops": 2.0 * n_q * n_r * d / t_mma / 1e12, "frac_of_peak": 2.0 * n_q * n_r * d / t_mma / 1e12 / peak},
         "phases_ms": {"prep": phase_ms[0], "mma_topk": phase_ms[1], "rerank": phase_ms[2], "exact_fallback": phase_ms[3]},
+        "fallback_rows": fallback_rows,
     }
+    # the same kernel with pruning switched off (exhaustive scan) on a slice of whole waves of query tiles:
+    # the tensor-pipe figure of the kernel itself, outside the timed region
+    if not args.no_exhaustive_probe:
+        n_slice = min(n_q, 2 * 148 * 128)
+        lib.cm_debug_probe_flags(32)
+        lib.cm_profile_enable(1)
+        ex_ms = []
+        for i in range(3):
+            device.knn_search(xq_d[:n_slice], xr_d, K, dist_mode=mode)
+            if lib.cm_profile_last_knn_ms(buf4) == 0 and i:
+                ex_ms.append(buf4[1])
+        lib.cm_profile_enable(0)
+        lib.cm_debug_probe_flags(0)
+        if ex_ms:
+            t_ex = float(np.mean(ex_ms)) / 1e3
+            ach_ex = 2.0 * n_slice * n_r * d / t_ex / 1e12
+            roofline["exhaustive_scan_probe"] = {"queries": n_slice, "ms": t_ex * 1e3, "achieved": ach_ex, "frac": ach_ex / peak}
     # HBM-side phases: algorithmic bytes per query (SURVEY.md 8d / DESIGN.md 4) over the CUDA-event time of the call
     hbm_bytes = {"edge_stats": K * 16.0, "kernel_to_csr": 484.0, "vote": 368.0, "spmm": K * 8.0 + K * UMAP_DIMS * 4.0 + UMAP_DIMS * 4.0}
     hbm_phases = {
@@ -373,7 +414,7 @@ def b200_arm(args):
         ns = cpu_sample_queries(name)
         run_cpu_path(xr, xq[: min(ns, 2000)], labels, umap)  # warm-up, discarded
         dt, out = run_cpu_path(xr, xq[:ns], labels, umap)
-        cpu = {"value": ns / dt, "unit": "cells/s", "cores": cpu_threads(), "kind": "port", "sample": f"first {ns} of {n_q} queries x full {n_r} reference, 1 run after warm-up", "phases_s": out["seconds"]}
+        cpu = {"value": ns / dt, "unit": "cells/s", "cores": cpu_threads(), "kind": "port", "sample": f"first {ns} of {n_q_total} queries x full {n_r} reference, 1 run after warm-up", "phases_s": out["seconds"]}
         got = ii[:ns].cpu().numpy()
         want = out["indices"]
         hits = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(got, want))
@@ -389,12 +430,12 @@ def b200_arm(args):
         "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32 (fp16x3 split tensor-core candidates, f64 exact re-rank)",
         "data": "synthetic",
         "config": {
-            "workload": f"{name}: {n_q} query/GPU -> {n_r} reference (replicated), d={d}, k={K}, gaussian, celltype + X_umap transfer",
+            "workload": f"{name}: {n_q_total} query -> {n_r} reference, d={d}, k={K}, gaussian kernel, celltype + X_umap transfer; queries sharded over the ranks ({n_q} on rank 0), reference replicated",
             "l2": "flushed between timed steps (256 MB write)",
             "parallelism": f"query-sharded x{world}",
         },
@@ -419,8 +460,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exhaustive-probe", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
