@@ -24,6 +24,8 @@
 //   fallback   : rows whose certificate fails are recomputed by the exact float64 SIMT kernel.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "knn_internal.cuh"
 
@@ -1495,6 +1497,128 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
   }
 }
 
+// Register-resident re-rank for queries with at most 64 candidates (every query whose tile was scanned
+// by ONE CTA: <= kCandOut = 60).  Lane l owns candidates l and l + 32: it reads its two candidate rows
+// itself (no staging, all lanes busy), the query row is broadcast from shared memory, and the 64
+// (d2, index) pairs are sorted by a bitonic network over shuffles -- no shared-memory round trips, no
+// index arithmetic with divisions.  Same outputs and the same certificate as rerank_kernel.
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), m), __shfl_xor_sync(0xffffffffu, __double2loint(v), m));
+}
+__device__ __forceinline__ double shfl_f64_idx(double v, int src) {
+  return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+__device__ __forceinline__ bool pair_before(double ka, int va, double kb, int vb) { return ka < kb || (ka == kb && va < vb); }
+
+template <typename T>
+__global__ void __launch_bounds__(kRerankWarps * 32)
+rerank64_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int64_t ldr, int64_t n_q, int64_t n_r, int d,
+                int k, const double* __restrict__ q_norms, const int32_t* __restrict__ cand_i,
+                const int32_t* __restrict__ cand_cnt, const float* __restrict__ cand_thr, ScaleInfo* info,
+                const int32_t* __restrict__ perm_q, const int32_t* __restrict__ perm_r, int64_t r_index_offset,
+                int dist_mode, double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dp = (d + 1) & ~1;
+  double* qrow = reinterpret_cast<double*>(smem_raw) + (size_t)warp * dp;
+  const double scale = (double)scale_from_absmax(info->absmax_bits);
+  const double max_rnorm = __longlong_as_double((long long)info->max_rnorm_bits);
+  unsigned long long cand_sum = 0;
+
+  for (int64_t qs = (int64_t)blockIdx.x * kRerankWarps + warp; qs < n_q; qs += (int64_t)gridDim.x * kRerankWarps) {
+    const int64_t q = perm_q[qs];
+    const int total = cand_cnt[qs];  // item == query tile: candidate row index == scan position
+    const float thr = cand_thr[qs];
+    int id0 = -1, id1 = -1;
+    if (lane < total) id0 = perm_r[cand_i[qs * kCandOut + lane]];
+    if (lane + 32 < total) id1 = perm_r[cand_i[qs * kCandOut + lane + 32]];
+    __syncwarp();  // the previous query's reads of qrow are done
+    for (int c = lane; c < dp; c += 32) qrow[c] = c < d ? (double)Q[q * ldq + c] : 0.0;
+    __syncwarp();
+    const bool ok0 = id0 >= 0 && id0 < n_r, ok1 = id1 >= 0 && id1 < n_r;
+    const T* r0 = R + (int64_t)(ok0 ? id0 : 0) * ldr;
+    const T* r1 = R + (int64_t)(ok1 ? id1 : 0) * ldr;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    int c = 0;
+    if (((reinterpret_cast<uintptr_t>(R) | (uintptr_t)(ldr * sizeof(T))) & (2 * sizeof(T) - 1)) == 0) {
+      // rows are aligned to two elements: paired loads
+      using T2 = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+      for (; c + 2 <= d; c += 2) {
+        const T2 x0 = *reinterpret_cast<const T2*>(r0 + c), x1 = *reinterpret_cast<const T2*>(r1 + c);
+        const double2 qq = *reinterpret_cast<const double2*>(qrow + c);
+        const double e0 = (double)x0.x - qq.x, e1 = (double)x0.y - qq.y, f0 = (double)x1.x - qq.x, f1 = (double)x1.y - qq.y;
+        a0 = fma(e0, e0, a0);
+        a1 = fma(e1, e1, a1);
+        b0 = fma(f0, f0, b0);
+        b1 = fma(f1, f1, b1);
+      }
+    } else {
+      for (; c + 2 <= d; c += 2) {
+        const double e0 = (double)r0[c] - qrow[c], e1 = (double)r0[c + 1] - qrow[c + 1];
+        const double f0 = (double)r1[c] - qrow[c], f1 = (double)r1[c + 1] - qrow[c + 1];
+        a0 = fma(e0, e0, a0);
+        a1 = fma(e1, e1, a1);
+        b0 = fma(f0, f0, b0);
+        b1 = fma(f1, f1, b1);
+      }
+    }
+    if (c < d) {
+      const double e0 = (double)r0[c] - qrow[c], f0 = (double)r1[c] - qrow[c];
+      a0 = fma(e0, e0, a0);
+      b0 = fma(f0, f0, b0);
+    }
+    // same summation order as rerank_kernel: even and odd dimensions in two accumulators
+    double ka = ok0 ? a0 + a1 : CUDART_INF, kb = ok1 ? b0 + b1 : CUDART_INF;
+    int va = ok0 ? id0 : INT32_MAX, vb = ok1 ? id1 : INT32_MAX;
+    // bitonic sort of 64 pairs; element index i = lane (a) / lane + 32 (b)
+#pragma unroll
+    for (int size = 2; size <= 64; size <<= 1) {
+      if (size == 64) {  // stride 32: inside the thread, ascending
+        if (pair_before(kb, vb, ka, va)) { const double tk = ka; ka = kb; kb = tk; const int tv = va; va = vb; vb = tv; }
+      }
+#pragma unroll
+      for (int stride = (size == 64 ? 16 : size >> 1); stride >= 1; stride >>= 1) {
+        const bool lower = (lane & stride) == 0;
+        // direction of the block this element belongs to (size 32: a ascending, b descending; size 64: all ascending)
+        const bool up_a = size >= 32 ? true : (lane & size) == 0;
+        const bool up_b = size == 32 ? false : (size == 64 ? true : (lane & size) == 0);
+        {
+          const double ok_ = shfl_xor_f64(ka, stride);
+          const int ov = __shfl_xor_sync(0xffffffffu, va, stride);
+          const bool take_min = (lower == up_a);
+          if (take_min ? pair_before(ok_, ov, ka, va) : pair_before(ka, va, ok_, ov)) { ka = ok_; va = ov; }
+        }
+        {
+          const double ok_ = shfl_xor_f64(kb, stride);
+          const int ov = __shfl_xor_sync(0xffffffffu, vb, stride);
+          const bool take_min = (lower == up_b);
+          if (take_min ? pair_before(ok_, ov, kb, vb) : pair_before(kb, vb, ok_, ov)) { kb = ok_; vb = ov; }
+        }
+      }
+    }
+    // certificate (all lanes compute the same thing)
+    const double qn = q_norms[q];
+    const double kth = k <= 32 ? shfl_f64_idx(ka, k - 1) : shfl_f64_idx(kb, k - 33);
+    const double err = ldexp(qn + max_rnorm, -18);
+    const double d2_thr = isinf(thr) ? CUDART_INF : (double)thr / (scale * scale) + qn;
+    const bool ok = isfinite(kth) && (kth + 2.0 * err <= d2_thr);
+    if (lane == 0 && !ok) {
+      unsigned long long pos = atomicAdd(&info->fail_count, 1ULL);
+      fail_rows[pos] = (int32_t)q;
+    }
+    cand_sum += (unsigned long long)total;
+    if (lane < k) {
+      out_dist[q * k + lane] = finish_distance(ka, dist_mode);
+      out_idx[q * k + lane] = isfinite(ka) ? (int64_t)va + r_index_offset : -1;
+    }
+    if (lane + 32 < k) {
+      out_dist[q * k + lane + 32] = finish_distance(kb, dist_mode);
+      out_idx[q * k + lane + 32] = isfinite(kb) ? (int64_t)vb + r_index_offset : -1;
+    }
+  }
+  if (lane == 0 && cand_sum) atomicAdd(&info->cand_total, cand_sum);
+}
+
 __global__ void publish_stats_kernel(const ScaleInfo* info, int64_t* stats_out) {
   stats_out[0] = (int64_t)info->fail_count;
   stats_out[1] = 0;
@@ -1724,6 +1848,17 @@ template <typename T>
 int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int64_t ldr, int d, int k,
                const MmaPlan& pl, const MmaBuffers& b, int64_t r_off, int dist_mode, double* out_dist,
                int64_t* out_idx, cudaStream_t st) {
+  if (pl.n_items == pl.n_q_tiles) {
+    // every query tile was scanned by one CTA: at most kCandOut <= 64 candidates per query
+    const size_t smem64 = (size_t)kRerankWarps * ((d + 1) & ~1) * sizeof(double);
+    int64_t blocks64 = ceil_div(n_q, kRerankWarps);
+    int grid64 = (int)(blocks64 < (int64_t)kNumSMs * 16 ? blocks64 : (int64_t)kNumSMs * 16);
+    rerank64_kernel<T><<<grid64, kRerankWarps * 32, smem64, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, b.q_norms, b.cand_i, b.cand_cnt,
+                                                                 b.cand_thr, b.info, b.perm_q, b.perm_r, r_off, dist_mode,
+                                                                 out_dist, out_idx, b.fail_rows);
+    CM_LAUNCH_CHECK("rerank64_kernel");
+    return CM_OK;
+  }
   int np_max = 64;  // power of two >= the candidates one query can have and >= kMmaMaxK
   while (np_max < (pl.n_items > pl.n_full ? pl.splits : 1) * kCandOut) np_max <<= 1;
   size_t smem = (size_t)kRerankWarps * (np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double) +
