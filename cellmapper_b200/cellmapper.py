@@ -107,6 +107,7 @@ class CellMapper:
         self.expression_transfer_metrics: dict[str, Any] | None = None
         #: last imputed layer as device CSR / dense tensor (kept for callers that stay on the GPU)
         self.imputed_device = None
+        self._prefetched: dict = {}
 
     def __repr__(self):
         query_summary = f"AnnData(n_obs={self.query.n_obs:,}, n_vars={self.query.n_vars:,})"
@@ -241,6 +242,22 @@ class CellMapper:
     # ------------------------------------------------------------------------------------------
     # transfers
     # ------------------------------------------------------------------------------------------
+    def _prefetch_payloads(self, obs_keys, obsm_keys) -> None:
+        """Host-side preparation that does not depend on the neighbours (category codes of the reference
+        labels in OneHotEncoder order, upload of the dense payloads), done while the search kernels run.
+        Entries are consumed by the next map_obs / map_obsm call for the same key."""
+        self._prefetched.clear()
+        for key in ([obs_keys] if isinstance(obs_keys, str) else (obs_keys or [])):
+            if key not in self.reference.obs.columns:
+                continue  # map_obs raises the KeyError
+            col = self.reference.obs[key]
+            if isinstance(col.dtype, pd.CategoricalDtype) or pd.api.types.is_object_dtype(col) or pd.api.types.is_string_dtype(col):
+                cats, codes = sorted_category_codes(col)
+                self._prefetched[("obs", key)] = (cats, _to_device(codes))
+        for key in ([obsm_keys] if isinstance(obsm_keys, str) else (obsm_keys or [])):
+            if key in self.reference.obsm:
+                self._prefetched[("obsm", key)] = _to_device(np.asarray(self.reference.obsm[key]))
+
     def _require_mapping(self) -> _DeviceCSR:
         if self._mapping is None:
             raise ValueError("Mapping matrix has not been computed. Call compute_mapping_matrix() first.")
@@ -250,8 +267,10 @@ class CellMapper:
         """reference: cellmapper.py:307-344."""
         m = self._require_mapping()
         logger.info("Mapping embeddings for key '%s'.", key)
-        emb = np.asarray(self.reference.obsm[key])
-        out = device.spmm(m.indptr, m.cols, m.vals, _to_device(emb))
+        emb_dev = self._prefetched.pop(("obsm", key), None)
+        if emb_dev is None:
+            emb_dev = _to_device(np.asarray(self.reference.obsm[key]))
+        out = device.spmm(m.indptr, m.cols, m.vals, emb_dev)
         output_key = f"{key}_{prediction_postfix}"
         self.query.obsm[output_key] = out.cpu().numpy()
         logger.info("Embeddings mapped and stored in query.obsm['%s'].", output_key)
@@ -368,8 +387,13 @@ class CellMapper:
         """reference: cellmapper.py:589-623 (weighted vote + argmax on the device)."""
         m = self._require_mapping()
         ref_col = self.reference.obs[key]
-        cats, codes = sorted_category_codes(ref_col)
-        code_dev, conf_dev = device.vote_argmax(m.indptr, m.cols, m.vals, _to_device(codes), len(cats))
+        pre = self._prefetched.pop(("obs", key), None)
+        if pre is None:
+            cats, codes = sorted_category_codes(ref_col)
+            codes_dev = _to_device(codes)
+        else:
+            cats, codes_dev = pre
+        code_dev, conf_dev = device.vote_argmax(m.indptr, m.cols, m.vals, codes_dev, len(cats))
         pred_codes = code_dev.cpu().numpy()
         conf = conf_dev.cpu().numpy()
         if isinstance(ref_col.dtype, pd.CategoricalDtype):
@@ -412,6 +436,8 @@ class CellMapper:
     ) -> "CellMapper":
         """reference: cellmapper.py:426-491."""
         self.compute_neighbors(n_neighbors=n_neighbors, use_rep=use_rep, method=knn_method, metric=metric, only_yx=only_yx)
+        # the search is running on the device: use the wait to encode the labels and stage the payloads
+        self._prefetch_payloads(obs_keys, obsm_keys)
         self.compute_mapping_matrix(method=mapping_method)
         if obs_keys is not None:
             for obs_key in [obs_keys] if isinstance(obs_keys, str) else obs_keys:

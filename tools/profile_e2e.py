@@ -6,7 +6,7 @@ from scipy.sparse import csr_matrix
 from cellmapper_b200 import CellMapper, synth
 from cellmapper_b200._anndata import AnnData
 
-n_q = n_r = 100_000; d = 50
+n_q = n_r = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000; d = 50
 centres = synth.mixture_centres(32, d)
 xr, cr = synth.mixture_embedding(n_r, centres, seed=1)
 xq, _ = synth.mixture_embedding(n_q, centres, seed=2)
