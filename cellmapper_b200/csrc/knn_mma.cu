@@ -206,9 +206,26 @@ struct ScaleInfo {
   unsigned long long tiles_scanned;    // (query tile, reference tile) pairs the tensor-core kernel evaluated
 };
 
+// Origin of the tensor-core arithmetic: mu = mean of <= 256 reference rows at a fixed stride (a
+// deterministic sample).  Distances do not depend on the origin, but the split-fp16 products, the
+// float32 cell bounds and the certificate's error bound all scale with ||x - mu||^2: data far from the
+// origin (un-centred embeddings) would otherwise fail every certificate and fall back to the float64
+// kernel.  Only the approximate scores see mu; the re-rank works on the caller's values.
+constexpr int kCentreRows = 256;
 template <typename T>
-__global__ void rowstats_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, double* __restrict__ norms,
-                                ScaleInfo* info, int is_ref) {
+__global__ void centre_kernel(const T* __restrict__ R, int64_t ldr, int64_t n_r, int d, double* __restrict__ mu) {
+  const int64_t n_s = n_r < kCentreRows ? n_r : kCentreRows;
+  const int64_t stride = n_r / n_s;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double s = 0.0;
+    for (int64_t j = 0; j < n_s; ++j) s += (double)R[j * stride * ldr + c];
+    mu[c] = s / (double)n_s;
+  }
+}
+
+template <typename T>
+__global__ void rowstats_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const double* __restrict__ mu,
+                                double* __restrict__ norms, ScaleInfo* info, int is_ref) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   float amax = 0.f;
@@ -217,7 +234,7 @@ __global__ void rowstats_kernel(const T* __restrict__ X, int64_t ld, int64_t n, 
        row += (int64_t)gridDim.x * warps_per_block) {
     double s = 0.0;
     for (int c = lane; c < d; c += 32) {
-      const double v = (double)X[row * ld + c];
+      const double v = (double)X[row * ld + c] - mu[c];
       s = fma(v, v, s);
       amax = fmaxf(amax, fabsf((float)v));
     }
@@ -252,8 +269,9 @@ constexpr float kNormColumn = 256.f;  // the constant c in the three norm column
 //   reference seg0:    hi(x) for cs<d, n1 n2 n3 at d..d+2   seg1:    lo(x)
 template <typename T>
 __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int64_t n_pad, int d, int kp, int dc,
-                            const double* __restrict__ norms, const ScaleInfo* __restrict__ info, int is_query,
-                            const int32_t* __restrict__ perm, uint4* __restrict__ img) {
+                            const double* __restrict__ mu, const double* __restrict__ norms,
+                            const ScaleInfo* __restrict__ info, int is_query, const int32_t* __restrict__ perm,
+                            uint4* __restrict__ img) {
   const int chunks = kp >> 3;
   const float scale = scale_from_absmax(info->absmax_bits);
   const int64_t total = n_pad * chunks;
@@ -276,7 +294,7 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
       if (seg < n_seg) {
         if (row < n) {
           if (cs < d) {
-            const float xs = (float)((double)X[row * ld + cs] * (double)scale);
+            const float xs = (float)(((double)X[row * ld + cs] - mu[cs]) * (double)scale);
             const __half hi = __float2half_rn(xs);
             const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
             if (is_query)
@@ -335,14 +353,14 @@ constexpr float kBoundSlack = 1.52587890625e-05f;
 
 // pivot j = reference row j * stride; stored transposed [d][n_cells] so 4 pivots are one 16-byte read
 template <typename T>
-__global__ void gather_pivots_kernel(const T* __restrict__ R, int64_t ldr, int64_t stride, int d, int n_cells,
+__global__ void gather_pivots_kernel(const T* __restrict__ R, int64_t ldr, int64_t stride, int d, int n_cells, const double* __restrict__ mu,
                                      float* __restrict__ piv_t, float* __restrict__ piv_norm) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_cells) return;
   const T* row = R + (int64_t)j * stride * ldr;
   float nn = 0.f;
   for (int c = 0; c < d; ++c) {
-    const float v = (float)row[c];
+    const float v = (float)((double)row[c] - mu[c]);
     piv_t[(size_t)c * n_cells + j] = v;
     nn = fmaf(v, v, nn);
   }
@@ -354,7 +372,7 @@ __global__ void gather_pivots_kernel(const T* __restrict__ R, int64_t ldr, int64
 // registers and every 4 FMAs cost one broadcast 16-byte read of the pivot table in shared memory.
 template <typename T, int DP>
 __global__ void __launch_bounds__(kAssignThreads)
-assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const float* __restrict__ piv_t,
+assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const double* __restrict__ mu, const float* __restrict__ piv_t,
                     const float* __restrict__ piv_norm, int n_cells, uint8_t* __restrict__ cell,
                     int32_t* __restrict__ counts, unsigned int* __restrict__ rad2_bits) {
   extern __shared__ __align__(16) float asm_smem[];
@@ -373,7 +391,7 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
     const int rows_here = (int)min((int64_t)blockDim.x, n - base);
     for (int i = threadIdx.x; i < rows_here * d; i += blockDim.x) {
       const int r = i / d, c = i - r * d;
-      sx[c * kAssignThreads + r] = (float)X[(base + r) * ld + c];
+      sx[c * kAssignThreads + r] = (float)((double)X[(base + r) * ld + c] - mu[c]);
     }
     __syncthreads();
     if (threadIdx.x < rows_here) {
@@ -419,22 +437,22 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
 }
 
 template <typename T, int DP>
-int launch_assign(const T* X, int64_t ld, int64_t n, int d, const float* piv_t, const float* piv_norm, int nc, uint8_t* cell,
+int launch_assign(const T* X, int64_t ld, int64_t n, int d, const double* mu, const float* piv_t, const float* piv_norm, int nc, uint8_t* cell,
                   int32_t* counts, unsigned int* rad2_bits, cudaStream_t st) {
   const size_t smem = ((size_t)DP * nc + nc + (size_t)DP * kAssignThreads) * sizeof(float);
   CM_CUDA_CHECK(cudaFuncSetAttribute(assign_cells_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(ceil_div(n, kAssignThreads) < kNumSMs * 2 ? ceil_div(n, kAssignThreads) : kNumSMs * 2);
-  assign_cells_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits);
+  assign_cells_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits);
   CM_LAUNCH_CHECK("assign_cells_kernel");
   return CM_OK;
 }
 template <typename T>
-int launch_assign_any(const T* X, int64_t ld, int64_t n, int d, const float* piv_t, const float* piv_norm, int nc,
+int launch_assign_any(const T* X, int64_t ld, int64_t n, int d, const double* mu, const float* piv_t, const float* piv_norm, int nc,
                       uint8_t* cell, int32_t* counts, unsigned int* rad2_bits, cudaStream_t st) {
-  if (d <= 16) return launch_assign<T, 16>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
-  if (d <= 32) return launch_assign<T, 32>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
-  if (d <= 48) return launch_assign<T, 48>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
-  return launch_assign<T, kAssignMaxD>(X, ld, n, d, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 16) return launch_assign<T, 16>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 32) return launch_assign<T, 32>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 48) return launch_assign<T, 48>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  return launch_assign<T, kAssignMaxD>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
 }
 
 // exclusive scan of the two count arrays -> cell starts (+ a copy used as scatter cursor)
@@ -498,7 +516,7 @@ __global__ void home_cell_kernel(const int32_t* __restrict__ perm_q, const uint8
 // assign_cells_kernel), redux.min over the rows of a warp, then over the tile's four warps.
 template <typename T, int DP>
 __global__ void __launch_bounds__(kAssignThreads)
-tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const int32_t* __restrict__ perm_q, int64_t n_q_tiles,
+tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const double* __restrict__ mu, const int32_t* __restrict__ perm_q, int64_t n_q_tiles,
                    const float* __restrict__ piv_t, const float* __restrict__ piv_norm, int n_cells,
                    const unsigned int* __restrict__ rad2_bits, float* __restrict__ lb2) {
   extern __shared__ __align__(16) float asm_smem[];
@@ -520,7 +538,7 @@ tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const int32_t* __
     for (int i = threadIdx.x; i < kAssignThreads * d; i += blockDim.x) {
       const int r = i / d, c = i - r * d;
       const int32_t row = srow[r];
-      sx[c * kAssignThreads + r] = row >= 0 ? (float)X[(int64_t)row * ld + c] : 0.f;
+      sx[c * kAssignThreads + r] = row >= 0 ? (float)((double)X[(int64_t)row * ld + c] - mu[c]) : 0.f;
     }
     __syncthreads();
     {
@@ -573,23 +591,23 @@ tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const int32_t* __
 }
 
 template <typename T, int DP>
-int launch_tile_bounds(const T* X, int64_t ld, int d, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
+int launch_tile_bounds(const T* X, int64_t ld, int d, const double* mu, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
                        const float* piv_norm, int nc, const unsigned int* rad2_bits, float* lb2, cudaStream_t st) {
   const size_t smem = ((size_t)DP * nc + nc + (size_t)DP * kAssignThreads) * sizeof(float);
   CM_CUDA_CHECK(cudaFuncSetAttribute(tile_bounds_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = ceil_div(n_q_tiles, kAssignThreads / kMmaTile);
   const int grid = (int)(blocks < kNumSMs * 2 ? blocks : kNumSMs * 2);
-  tile_bounds_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2);
+  tile_bounds_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2);
   CM_LAUNCH_CHECK("tile_bounds_kernel");
   return CM_OK;
 }
 template <typename T>
-int launch_tile_bounds_any(const T* X, int64_t ld, int d, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
+int launch_tile_bounds_any(const T* X, int64_t ld, int d, const double* mu, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
                            const float* piv_norm, int nc, const unsigned int* rad2_bits, float* lb2, cudaStream_t st) {
-  if (d <= 16) return launch_tile_bounds<T, 16>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
-  if (d <= 32) return launch_tile_bounds<T, 32>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
-  if (d <= 48) return launch_tile_bounds<T, 48>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
-  return launch_tile_bounds<T, kAssignMaxD>(X, ld, d, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 16) return launch_tile_bounds<T, 16>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 32) return launch_tile_bounds<T, 32>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 48) return launch_tile_bounds<T, 48>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  return launch_tile_bounds<T, kAssignMaxD>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
 }
 
 // without cells: queries in their own order, reference rows scrambled by a golden-ratio stride so that
@@ -1699,6 +1717,7 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
 
 struct MmaBuffers {
   ScaleInfo* info;
+  double* mu;  // [64] origin of the tensor-core arithmetic
   double* q_norms;
   double* r_norms;
   unsigned char* q_img;
@@ -1725,6 +1744,7 @@ struct MmaBuffers {
 MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
   MmaBuffers b;
   b.info = ws.take<ScaleInfo>(1);
+  b.mu = ws.take<double>(64);
   b.q_norms = ws.take<double>(n_q);
   b.r_norms = ws.take<double>(n_r);
   b.q_img = ws.take<unsigned char>((size_t)pl.n_q_pad * pl.kp_q * 2);
@@ -1756,9 +1776,11 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
   const int wpb = 8;
   int gq = (int)(ceil_div(n_q, wpb) < kNumSMs * 8 ? ceil_div(n_q, wpb) : kNumSMs * 8);
   int gr = (int)(ceil_div(n_r, wpb) < kNumSMs * 8 ? ceil_div(n_r, wpb) : kNumSMs * 8);
-  rowstats_kernel<T><<<gq, wpb * 32, 0, st>>>(Q, ldq, n_q, d, b.q_norms, b.info, 0);
+  centre_kernel<T><<<1, 64, 0, st>>>(R, ldr, n_r, d, b.mu);
+  CM_LAUNCH_CHECK("centre_kernel");
+  rowstats_kernel<T><<<gq, wpb * 32, 0, st>>>(Q, ldq, n_q, d, b.mu, b.q_norms, b.info, 0);
   CM_LAUNCH_CHECK("rowstats_kernel(Q)");
-  rowstats_kernel<T><<<gr, wpb * 32, 0, st>>>(R, ldr, n_r, d, b.r_norms, b.info, 1);
+  rowstats_kernel<T><<<gr, wpb * 32, 0, st>>>(R, ldr, n_r, d, b.mu, b.r_norms, b.info, 1);
   CM_LAUNCH_CHECK("rowstats_kernel(R)");
   // scan order
   if (pl.n_cells > 0) {
@@ -1767,11 +1789,11 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     CM_CUDA_CHECK(cudaMemsetAsync(b.cell_rad2, 0, kMaxCells * sizeof(unsigned int), st));
     CM_CUDA_CHECK(cudaMemsetAsync(b.perm_q, 0xFF, (size_t)pl.n_q_pad * sizeof(int32_t), st));
     CM_CUDA_CHECK(cudaMemsetAsync(b.perm_r, 0xFF, (size_t)pl.n_r_pad * sizeof(int32_t), st));
-    gather_pivots_kernel<T><<<ceil_div(nc, 128), 128, 0, st>>>(R, ldr, n_r / nc, d, nc, b.piv_t, b.piv_norm);
+    gather_pivots_kernel<T><<<ceil_div(nc, 128), 128, 0, st>>>(R, ldr, n_r / nc, d, nc, b.mu, b.piv_t, b.piv_norm);
     CM_LAUNCH_CHECK("gather_pivots_kernel");
-    int rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, b.cell_rad2, st);
+    int rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.mu, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, b.cell_rad2, st);
     if (rc_a) return rc_a;
-    rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, nullptr, st);
+    rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.mu, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, nullptr, st);
     if (rc_a) return rc_a;
     cell_scan_kernel<<<1, 32, 0, st>>>(b.cell_counts, nc, b.cell_starts, b.cell_cursor);
     CM_LAUNCH_CHECK("cell_scan_kernel");
@@ -1783,7 +1805,7 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     CM_LAUNCH_CHECK("cell_scatter_kernel(Q)");
     home_cell_kernel<<<(unsigned)ceil_div(pl.n_q_tiles, 128), 128, 0, st>>>(b.perm_q, b.q_cell, (int)pl.n_q_tiles, b.home_cell);
     CM_LAUNCH_CHECK("home_cell_kernel");
-    rc_a = launch_tile_bounds_any<T>(Q, ldq, d, b.perm_q, pl.n_q_tiles, b.piv_t, b.piv_norm, nc, b.cell_rad2, b.cell_lb2, st);
+    rc_a = launch_tile_bounds_any<T>(Q, ldq, d, b.mu, b.perm_q, pl.n_q_tiles, b.piv_t, b.piv_norm, nc, b.cell_rad2, b.cell_lb2, st);
     if (rc_a) return rc_a;
   } else {
     fill_perm_kernel<<<(unsigned)(ceil_div(pl.n_q_pad, 256) < kNumSMs * 8 ? ceil_div(pl.n_q_pad, 256) : kNumSMs * 8), 256, 0, st>>>(
@@ -1796,10 +1818,10 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
   int64_t tq = pl.n_q_pad * (pl.kp_q / 8), tr = pl.n_r_pad * (pl.kp_r / 8);
   int bq = (int)(ceil_div(tq, 256) < kNumSMs * 16 ? ceil_div(tq, 256) : kNumSMs * 16);
   int br = (int)(ceil_div(tr, 256) < kNumSMs * 16 ? ceil_div(tr, 256) : kNumSMs * 16);
-  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q, pl.dc, b.q_norms, b.info, 1, b.perm_q,
+  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q, pl.dc, b.mu, b.q_norms, b.info, 1, b.perm_q,
                                      reinterpret_cast<uint4*>(b.q_img));
   CM_LAUNCH_CHECK("prep_kernel(Q)");
-  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r, pl.dc, b.r_norms, b.info, 0, b.perm_r,
+  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r, pl.dc, b.mu, b.r_norms, b.info, 0, b.perm_r,
                                      reinterpret_cast<uint4*>(b.r_img));
   CM_LAUNCH_CHECK("prep_kernel(R)");
   return CM_OK;

@@ -57,9 +57,13 @@ def test_tensor_core_products_match_float64(torch_cuda, d, n_q, n_r):
     out, scale = device.debug_mma_tile(dev(torch, q), dev(torch, r))
     out = out.cpu().numpy().astype(np.float64)[:n_q, :n_r]
     s = float(scale.item())
-    amax = max(np.abs(q).max(), np.abs(r).max())
-    assert 32 <= amax * s < 64 and np.log2(s) == np.round(np.log2(s))
-    q64, r64 = q.astype(np.float64) * s, r.astype(np.float64) * s
+    # the kernel works relative to mu = mean of <= 256 reference rows at a fixed stride (centre_kernel)
+    n_s = min(n_r, 256)
+    mu = r[:: n_r // n_s][:n_s].astype(np.float64).mean(0)
+    qc, rc = q.astype(np.float64) - mu, r.astype(np.float64) - mu
+    amax = max(np.abs(qc).max(), np.abs(rc).max())
+    assert 32 <= amax * s < 64 * (1 + 1e-6) and np.log2(s) == np.round(np.log2(s))
+    q64, r64 = qc * s, rc * s
     want = (r64 * r64).sum(1)[None, :] - 2.0 * q64 @ r64.T
     bound = 2.0**-18 * ((q64 * q64).sum(1)[:, None] + (r64 * r64).sum(1)[None, :])
     err = np.abs(out - want)
@@ -146,6 +150,70 @@ def test_search_duplicates_and_ties(torch_cuda):
     for row in range(20):
         assert len(set(ii[row].tolist())) == 30
         np.testing.assert_allclose(np.sqrt(((xr[ii[row]].astype(np.float64) - xq[row]) ** 2).sum(1)), dd[row], rtol=1e-12)
+
+
+# --------------------------------------------------------------------------------------------
+# P1 search with coarse cells (>= 16384 references): the pruned scan must stay exact
+# --------------------------------------------------------------------------------------------
+def _pruning_case(name, rng):
+    """(query, reference) float arrays that stress the cell bounds in different ways."""
+    if name == "mixture":  # well separated clusters: almost everything is pruned
+        c = rng.standard_normal((12, 40)) * 6
+        lab_r, lab_q = rng.integers(0, 12, 40_000), rng.integers(0, 12, 20_000)  # > 148 query tiles: no split scans
+        return (c[lab_q] + rng.standard_normal((20_000, 40))).astype(np.float32), (c[lab_r] + rng.standard_normal((40_000, 40))).astype(np.float32)
+    if name == "uniform":  # no structure: nothing can be pruned
+        return rng.random((2_000, 24), dtype=np.float32), rng.random((30_000, 24), dtype=np.float32)
+    if name == "offset":  # far from the origin: the float32 expansion of the bounds loses digits
+        c = rng.standard_normal((6, 32)) * 3
+        lab_r, lab_q = rng.integers(0, 6, 25_000), rng.integers(0, 6, 1_500)
+        return (1000.0 + c[lab_q] + rng.standard_normal((1_500, 32))).astype(np.float32), (1000.0 + c[lab_r] + rng.standard_normal((25_000, 32))).astype(np.float32)
+    if name == "outliers":  # queries far away from every reference cell, tiny and huge clusters side by side
+        c = rng.standard_normal((5, 16)) * 10
+        sizes = [20_000, 3_000, 500, 40, 7]
+        r = np.concatenate([c[i] + rng.standard_normal((n, 16)) * (0.2 + i) for i, n in enumerate(sizes)]).astype(np.float32)
+        q = np.concatenate([c[rng.integers(0, 5, 1_000)] + rng.standard_normal((1_000, 16)), rng.standard_normal((300, 16)) * 40]).astype(np.float32)
+        return q, r
+    if name == "duplicates":  # every reference point 25 times: ties everywhere, cells full of equal rows
+        base = rng.standard_normal((800, 20)).astype(np.float32) * 4
+        return (base[:600] + 0.01).astype(np.float32), np.repeat(base, 25, axis=0)
+    if name == "float64":
+        c = rng.standard_normal((9, 50)) * 4
+        return c[rng.integers(0, 9, 2_000)] + rng.standard_normal((2_000, 50)), c[rng.integers(0, 9, 20_000)] + rng.standard_normal((20_000, 50))
+    if name == "few_queries":  # fewer query tiles than SMs: the scan of a tile is split over several CTAs
+        c = rng.standard_normal((10, 30)) * 5
+        return (c[rng.integers(0, 10, 300)] + rng.standard_normal((300, 30))).astype(np.float32), (c[rng.integers(0, 10, 60_000)] + rng.standard_normal((60_000, 30))).astype(np.float32)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["mixture", "uniform", "offset", "outliers", "duplicates", "float64", "few_queries"])
+def test_pruned_search_is_exact(torch_cuda, name):
+    """Tensor-core search with cell pruning == exhaustive scan of the same kernel == float64 SIMT brute force."""
+    torch = torch_cuda
+    from cellmapper_b200 import _lib, device
+
+    q, r = _pruning_case(name, np.random.default_rng(11))
+    k = 30
+    qd, rd = dev(torch, q), dev(torch, r)
+    lib = _lib.load()
+    dd, ii, st = device.knn_search(qd, rd, k, return_stats=True)
+    try:
+        lib.cm_debug_probe_flags(32)  # exhaustive scan, no pruning
+        de, ie, se = device.knn_search(qd, rd, k, return_stats=True)
+    finally:
+        lib.cm_debug_probe_flags(0)
+    dx, ix = device.knn_search(qd, rd, k, algo=_lib.KNN_EXACT_F64)
+    dd, ii, de, ie, dx, ix = (t.cpu().numpy() for t in (dd, ii, de, ie, dx, ix))
+    n_pairs = -(-q.shape[0] // 128) * -(-r.shape[0] // 128)
+    assert int(se[3]) >= n_pairs and int(st[3]) <= int(se[3])
+    np.testing.assert_array_equal(dd, de)  # pruning must not change a single bit
+    np.testing.assert_allclose(dd, dx, rtol=1e-13)  # (the SIMT kernel sums the dimensions in another order)
+    assert neighbours_match(ii, dd, ix, dx) == 0
+    assert neighbours_match(ie, de, ix, dx) == 0
+    if name != "duplicates":
+        np.testing.assert_array_equal(ii, ix)
+    if name == "mixture":
+        assert int(st[3]) < 0.5 * n_pairs, "well separated clusters must be pruned"
+    assert int(st[0]) <= 0.01 * q.shape[0] + 1, f"{int(st[0])} rows needed the exact fallback"
 
 
 def test_search_errors(torch_cuda):
