@@ -345,6 +345,7 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxCells = 256;
 constexpr int kAssignThreads = 256;
+constexpr int kAssignRows = 2 * kAssignThreads;  // rows per block and pass: two per thread
 constexpr int kAssignMaxD = 56;  // >= the largest d of the tensor-core path (53)
 constexpr int kMinRefsForCells = 16384;  // below this the scan is short anyway: scrambled order, no cells
 // float32 expansion ||x||^2 + ||p||^2 - 2 x.p with d <= 56: |error| <= ~4e-6 (||x||^2 + ||p||^2); the bounds
@@ -378,30 +379,31 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
   extern __shared__ __align__(16) float asm_smem[];
   float* sp = asm_smem;                          // [DP][n_cells]
   float* sn = sp + (size_t)DP * n_cells;         // [n_cells]
-  float* sx = sn + n_cells;                      // [DP][kAssignThreads]
   __shared__ int hist[kMaxCells];
   __shared__ unsigned int rad[kMaxCells];  // float bits of the largest squared distance to the cell's pivot
   for (int i = threadIdx.x; i < DP * n_cells; i += blockDim.x) sp[i] = i < d * n_cells ? piv_t[i] : 0.f;
   for (int i = threadIdx.x; i < n_cells; i += blockDim.x) sn[i] = piv_norm[i];
   for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x) { hist[i] = 0; rad[i] = 0u; }
-  for (int i = threadIdx.x; i < DP * kAssignThreads; i += blockDim.x) sx[i] = 0.f;
   __syncthreads();
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
-    // coalesced stage of this block's rows, transposed: sx[c][thread]
-    const int rows_here = (int)min((int64_t)blockDim.x, n - base);
-    for (int i = threadIdx.x; i < rows_here * d; i += blockDim.x) {
-      const int r = i / d, c = i - r * d;
-      sx[c * kAssignThreads + r] = (float)((double)X[(base + r) * ld + c] - mu[c]);
-    }
-    __syncthreads();
+  for (int64_t base = (int64_t)blockIdx.x * kAssignRows; base < n; base += (int64_t)gridDim.x * kAssignRows) {
+    const int rows_here = (int)min((int64_t)kAssignRows, n - base);
     if (threadIdx.x < rows_here) {
-      float x[DP];
+      // two rows per thread (tid and tid + 256), read straight from global memory into registers (a row is one
+      // contiguous 4*d-byte run, so every fetched sector is used by the thread that fetched it); every
+      // broadcast 16-byte pivot read then feeds 8 FMAs
+      const bool two = threadIdx.x + kAssignThreads < rows_here;
+      const T* rx = X + (base + threadIdx.x) * ld;
+      const T* ry = X + (base + (two ? kAssignThreads + threadIdx.x : threadIdx.x)) * ld;
+      float x[DP], y[DP];
 #pragma unroll
-      for (int c = 0; c < DP; ++c) x[c] = sx[c * kAssignThreads + threadIdx.x];
-      float best = CUDART_INF_F;
-      int best_j = 0;
+      for (int c = 0; c < DP; ++c) {
+        x[c] = c < d ? (float)((double)rx[c] - mu[c]) : 0.f;
+        y[c] = c < d ? (float)((double)ry[c] - mu[c]) : 0.f;
+      }
+      float best = CUDART_INF_F, bestb = CUDART_INF_F;
+      int best_j = 0, bestb_j = 0;
       for (int j0 = 0; j0 < n_cells; j0 += 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
         for (int c = 0; c < DP; ++c) {
           const float4 pv = *reinterpret_cast<const float4*>(sp + (size_t)c * n_cells + j0);
@@ -409,27 +411,48 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
           a1 = fmaf(x[c], pv.y, a1);
           a2 = fmaf(x[c], pv.z, a2);
           a3 = fmaf(x[c], pv.w, a3);
+          b0 = fmaf(y[c], pv.x, b0);
+          b1 = fmaf(y[c], pv.y, b1);
+          b2 = fmaf(y[c], pv.z, b2);
+          b3 = fmaf(y[c], pv.w, b3);
         }
-        const float s0 = sn[j0] - 2.f * a0, s1 = sn[j0 + 1] - 2.f * a1, s2 = sn[j0 + 2] - 2.f * a2, s3 = sn[j0 + 3] - 2.f * a3;
+        const float n0 = sn[j0], n1 = sn[j0 + 1], n2 = sn[j0 + 2], n3 = sn[j0 + 3];
+        const float s0 = n0 - 2.f * a0, s1 = n1 - 2.f * a1, s2 = n2 - 2.f * a2, s3 = n3 - 2.f * a3;
         if (s0 < best) { best = s0; best_j = j0; }
         if (s1 < best) { best = s1; best_j = j0 + 1; }
         if (s2 < best) { best = s2; best_j = j0 + 2; }
         if (s3 < best) { best = s3; best_j = j0 + 3; }
+        const float u0 = n0 - 2.f * b0, u1 = n1 - 2.f * b1, u2 = n2 - 2.f * b2, u3 = n3 - 2.f * b3;
+        if (u0 < bestb) { bestb = u0; bestb_j = j0; }
+        if (u1 < bestb) { bestb = u1; bestb_j = j0 + 1; }
+        if (u2 < bestb) { bestb = u2; bestb_j = j0 + 2; }
+        if (u3 < bestb) { bestb = u3; bestb_j = j0 + 3; }
       }
       cell[base + threadIdx.x] = (uint8_t)best_j;
       atomicAdd(&hist[best_j], 1);
+      if (two) {
+        cell[base + kAssignThreads + threadIdx.x] = (uint8_t)bestb_j;
+        atomicAdd(&hist[bestb_j], 1);
+      }
       if (rad2_bits) {
         // upper bound of ||x - p||^2 from the expansion: the float32 rounding of the three terms is covered
         // by kBoundSlack * (||x||^2 + ||p||^2)   (see tile_bounds_kernel)
-        float xn = 0.f;
+        float xn = 0.f, yn = 0.f;
 #pragma unroll
-        for (int c = 0; c < DP; ++c) xn = fmaf(x[c], x[c], xn);
+        for (int c = 0; c < DP; ++c) {
+          xn = fmaf(x[c], x[c], xn);
+          yn = fmaf(y[c], y[c], yn);
+        }
         const float up = best + xn + kBoundSlack * (xn + sn[best_j]);
         atomicMax(&rad[best_j], __float_as_uint(fmaxf(up, 0.f)));
+        if (two) {
+          const float upb = bestb + yn + kBoundSlack * (yn + sn[bestb_j]);
+          atomicMax(&rad[bestb_j], __float_as_uint(fmaxf(upb, 0.f)));
+        }
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
   for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
     if (hist[i]) atomicAdd(&counts[i], hist[i]);
     if (rad2_bits && rad[i]) atomicMax(&rad2_bits[i], rad[i]);
@@ -439,9 +462,9 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
 template <typename T, int DP>
 int launch_assign(const T* X, int64_t ld, int64_t n, int d, const double* mu, const float* piv_t, const float* piv_norm, int nc, uint8_t* cell,
                   int32_t* counts, unsigned int* rad2_bits, cudaStream_t st) {
-  const size_t smem = ((size_t)DP * nc + nc + (size_t)DP * kAssignThreads) * sizeof(float);
+  const size_t smem = ((size_t)DP * nc + nc) * sizeof(float);
   CM_CUDA_CHECK(cudaFuncSetAttribute(assign_cells_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)(ceil_div(n, kAssignThreads) < kNumSMs * 2 ? ceil_div(n, kAssignThreads) : kNumSMs * 2);
+  const int grid = (int)(ceil_div(n, kAssignRows) < kNumSMs * 2 ? ceil_div(n, kAssignRows) : kNumSMs * 2);
   assign_cells_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits);
   CM_LAUNCH_CHECK("assign_cells_kernel");
   return CM_OK;
@@ -522,36 +545,33 @@ tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const double* __r
   extern __shared__ __align__(16) float asm_smem[];
   float* sp = asm_smem;                          // [DP][n_cells]
   float* sn = sp + (size_t)DP * n_cells;         // [n_cells]
-  float* sx = sn + n_cells;                      // [DP][kAssignThreads]
-  __shared__ uint32_t wmin[kAssignThreads / 32][kMaxCells];
-  __shared__ int32_t srow[kAssignThreads];
+  __shared__ uint32_t wmin[kAssignRows / 32][kMaxCells];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < DP * n_cells; i += blockDim.x) sp[i] = i < d * n_cells ? piv_t[i] : 0.f;
   for (int i = threadIdx.x; i < n_cells; i += blockDim.x) sn[i] = piv_norm[i];
-  for (int i = threadIdx.x; i < DP * kAssignThreads; i += blockDim.x) sx[i] = 0.f;
   __syncthreads();
-  constexpr int kTilesPerBlock = kAssignThreads / kMmaTile;
+  constexpr int kTilesPerBlock = kAssignRows / kMmaTile;
   for (int64_t t0 = (int64_t)blockIdx.x * kTilesPerBlock; t0 < n_q_tiles; t0 += (int64_t)gridDim.x * kTilesPerBlock) {
-    const int64_t pos = t0 * kMmaTile + threadIdx.x;
-    srow[threadIdx.x] = pos < n_q_tiles * kMmaTile ? perm_q[pos] : -1;
-    __syncthreads();
-    for (int i = threadIdx.x; i < kAssignThreads * d; i += blockDim.x) {
-      const int r = i / d, c = i - r * d;
-      const int32_t row = srow[r];
-      sx[c * kAssignThreads + r] = row >= 0 ? (float)((double)X[(int64_t)row * ld + c] - mu[c]) : 0.f;
-    }
-    __syncthreads();
     {
-      const bool valid = srow[threadIdx.x] >= 0;
-      float x[DP];
-      float xn = 0.f;
+      // two rows per thread (scan positions tid and tid + 256 of this block's four tiles), read straight from
+      // global memory into registers; every broadcast 16-byte pivot read feeds 8 FMAs
+      const int64_t pos_x = t0 * kMmaTile + threadIdx.x, pos_y = pos_x + kAssignThreads;
+      const int32_t row_x = pos_x < n_q_tiles * kMmaTile ? perm_q[pos_x] : -1;
+      const int32_t row_y = pos_y < n_q_tiles * kMmaTile ? perm_q[pos_y] : -1;
+      const bool valid_x = row_x >= 0, valid_y = row_y >= 0;
+      const T* rx = X + (int64_t)(valid_x ? row_x : 0) * ld;
+      const T* ry = X + (int64_t)(valid_y ? row_y : 0) * ld;
+      float x[DP], y[DP];
+      float xn = 0.f, yn = 0.f;
 #pragma unroll
       for (int c = 0; c < DP; ++c) {
-        x[c] = sx[c * kAssignThreads + threadIdx.x];
+        x[c] = c < d ? (float)((double)rx[c] - mu[c]) : 0.f;
+        y[c] = c < d ? (float)((double)ry[c] - mu[c]) : 0.f;
         xn = fmaf(x[c], x[c], xn);
+        yn = fmaf(y[c], y[c], yn);
       }
       for (int j0 = 0; j0 < n_cells; j0 += 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
         for (int c = 0; c < DP; ++c) {
           const float4 pv = *reinterpret_cast<const float4*>(sp + (size_t)c * n_cells + j0);
@@ -559,17 +579,33 @@ tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const double* __r
           a1 = fmaf(x[c], pv.y, a1);
           a2 = fmaf(x[c], pv.z, a2);
           a3 = fmaf(x[c], pv.w, a3);
+          b0 = fmaf(y[c], pv.x, b0);
+          b1 = fmaf(y[c], pv.y, b1);
+          b2 = fmaf(y[c], pv.z, b2);
+          b3 = fmaf(y[c], pv.w, b3);
         }
-        // lower bound of ||x - p_j||^2
-        const float v0 = valid ? (xn + sn[j0]) * (1.f - kBoundSlack) - 2.f * a0 : CUDART_INF_F;
-        const float v1 = valid ? (xn + sn[j0 + 1]) * (1.f - kBoundSlack) - 2.f * a1 : CUDART_INF_F;
-        const float v2 = valid ? (xn + sn[j0 + 2]) * (1.f - kBoundSlack) - 2.f * a2 : CUDART_INF_F;
-        const float v3 = valid ? (xn + sn[j0 + 3]) * (1.f - kBoundSlack) - 2.f * a3 : CUDART_INF_F;
+        // lower bounds of ||x - p_j||^2
+        const float n0 = sn[j0], n1 = sn[j0 + 1], n2 = sn[j0 + 2], n3 = sn[j0 + 3];
+        const float v0 = valid_x ? (xn + n0) * (1.f - kBoundSlack) - 2.f * a0 : CUDART_INF_F;
+        const float v1 = valid_x ? (xn + n1) * (1.f - kBoundSlack) - 2.f * a1 : CUDART_INF_F;
+        const float v2 = valid_x ? (xn + n2) * (1.f - kBoundSlack) - 2.f * a2 : CUDART_INF_F;
+        const float v3 = valid_x ? (xn + n3) * (1.f - kBoundSlack) - 2.f * a3 : CUDART_INF_F;
+        const float z0 = valid_y ? (yn + n0) * (1.f - kBoundSlack) - 2.f * b0 : CUDART_INF_F;
+        const float z1 = valid_y ? (yn + n1) * (1.f - kBoundSlack) - 2.f * b1 : CUDART_INF_F;
+        const float z2 = valid_y ? (yn + n2) * (1.f - kBoundSlack) - 2.f * b2 : CUDART_INF_F;
+        const float z3 = valid_y ? (yn + n3) * (1.f - kBoundSlack) - 2.f * b3 : CUDART_INF_F;
         const uint32_t m0 = __reduce_min_sync(0xffffffffu, float_to_ordered(v0));
         const uint32_t m1 = __reduce_min_sync(0xffffffffu, float_to_ordered(v1));
         const uint32_t m2 = __reduce_min_sync(0xffffffffu, float_to_ordered(v2));
         const uint32_t m3 = __reduce_min_sync(0xffffffffu, float_to_ordered(v3));
-        if (lane == 0) *reinterpret_cast<uint4*>(&wmin[warp][j0]) = make_uint4(m0, m1, m2, m3);
+        const uint32_t q0 = __reduce_min_sync(0xffffffffu, float_to_ordered(z0));
+        const uint32_t q1 = __reduce_min_sync(0xffffffffu, float_to_ordered(z1));
+        const uint32_t q2 = __reduce_min_sync(0xffffffffu, float_to_ordered(z2));
+        const uint32_t q3 = __reduce_min_sync(0xffffffffu, float_to_ordered(z3));
+        if (lane == 0) {
+          *reinterpret_cast<uint4*>(&wmin[warp][j0]) = make_uint4(m0, m1, m2, m3);          // rows [32 warp, +32)
+          *reinterpret_cast<uint4*>(&wmin[8 + warp][j0]) = make_uint4(q0, q1, q2, q3);      // rows 256 + [32 warp, +32)
+        }
       }
     }
     __syncthreads();
@@ -593,9 +629,9 @@ tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const double* __r
 template <typename T, int DP>
 int launch_tile_bounds(const T* X, int64_t ld, int d, const double* mu, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
                        const float* piv_norm, int nc, const unsigned int* rad2_bits, float* lb2, cudaStream_t st) {
-  const size_t smem = ((size_t)DP * nc + nc + (size_t)DP * kAssignThreads) * sizeof(float);
+  const size_t smem = ((size_t)DP * nc + nc) * sizeof(float);
   CM_CUDA_CHECK(cudaFuncSetAttribute(tile_bounds_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = ceil_div(n_q_tiles, kAssignThreads / kMmaTile);
+  const int64_t blocks = ceil_div(n_q_tiles, kAssignRows / kMmaTile);
   const int grid = (int)(blocks < kNumSMs * 2 ? blocks : kNumSMs * 2);
   tile_bounds_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2);
   CM_LAUNCH_CHECK("tile_bounds_kernel");
