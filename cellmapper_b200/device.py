@@ -17,6 +17,7 @@ from . import _lib
 __all__ = [
     "knn_search",
     "knn_merge_topk",
+    "finish_distances",
     "edge_stats",
     "edge_kernel_to_csr",
     "csr_row_normalize",
@@ -129,6 +130,18 @@ def knn_search(
             int(dist_mode), int(algo), _ptr(out_d), _ptr(out_i), _ptr(ws), ws_bytes, _ptr(stats), _stream(),
         )  # fmt: skip
     return (out_d, out_i, stats) if return_stats else (out_d, out_i)
+
+
+def finish_distances(d2: torch.Tensor, dist_mode: int) -> torch.Tensor:
+    """Squared float64 distances -> the returned distance of ``dist_mode`` (same roundings as the kernels:
+    ``sqrt`` in float64, or sklearn's float32 brute-force result ``(double)sqrtf((float)d2)``).  Used after
+    merging per-shard lists, which must be merged on the SQUARED distances: distinct d2 can round to the
+    same float32 distance, and the neighbour order is defined on d2."""
+    if dist_mode == _lib.DIST_SQUARED:
+        return d2
+    if dist_mode == _lib.DIST_SKLEARN_F32:
+        return d2.to(torch.float32).sqrt().to(torch.float64)
+    return d2.sqrt()
 
 
 def knn_merge_topk(cand_dist: torch.Tensor, cand_idx: torch.Tensor, k: int):

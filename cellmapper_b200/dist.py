@@ -26,6 +26,7 @@ __all__ = [
     "shard_bounds",
     "allreduce_sum",
     "reference_sharded_search",
+    "knn_reference_sharded",
     "gather_rows",
 ]
 
@@ -101,6 +102,19 @@ def reference_sharded_search(
     dist.all_gather_into_tensor(all_d, d)
     dist.all_gather_into_tensor(all_i, i)
     return merge(all_d.view(ws, n_q, k), all_i.view(ws, n_q, k), k)
+
+
+def knn_reference_sharded(q: torch.Tensor, r_local: torch.Tensor, r_offset: int, k: int, dist_mode: int):
+    """Exact k-NN of ``q`` over a row-sharded reference with the CUDA kernels: per-shard search returning SQUARED
+    float64 distances and global indices, NCCL all-gather, ``cm_knn_merge_topk`` on (d2, index), then the
+    rounding of ``dist_mode``.  Equals the single-GPU ``device.knn_search(q, r_all, k, dist_mode=...)`` bit for bit."""
+    from . import _lib, device
+
+    def search(qq, rr, kk, off):
+        return device.knn_search(qq, rr, kk, r_index_offset=off, dist_mode=_lib.DIST_SQUARED)
+
+    d2, idx = reference_sharded_search(q, r_local, r_offset, k, search, device.knn_merge_topk)
+    return device.finish_distances(d2, dist_mode), idx
 
 
 def gather_rows(t: torch.Tensor, counts: list[int] | None = None) -> torch.Tensor | None:

@@ -86,3 +86,17 @@ def test_neighbors_results_container():
     assert np.allclose(nr.knn_graph_distances.diagonal(), 0)
     with pytest.raises(ValueError):
         NeighborsResults(sd, si, n_targets=5).boolean_adjacency(set_diag=True)
+
+
+def test_finish_distances_matches_kernel_roundings():
+    """device.finish_distances (used after merging per-shard lists on squared distances) reproduces the
+    kernels' roundings: sqrt in float64, or sklearn's float32 brute-force result (double)sqrtf((float)d2)."""
+    import torch
+
+    from cellmapper_b200 import _lib, device
+
+    d2 = torch.tensor([0.0, 1e-12, 2.0, 33.333333333333336, 1e6 + 0.125], dtype=torch.float64)
+    np.testing.assert_array_equal(device.finish_distances(d2, _lib.DIST_SQUARED).numpy(), d2.numpy())
+    np.testing.assert_array_equal(device.finish_distances(d2, _lib.DIST_SQRT_F64).numpy(), np.sqrt(d2.numpy()))
+    want = np.sqrt(d2.numpy().astype(np.float32)).astype(np.float64)
+    np.testing.assert_array_equal(device.finish_distances(d2, _lib.DIST_SKLEARN_F32).numpy(), want)
