@@ -690,7 +690,7 @@ struct RowCand {
   uint32_t thr_key;  // every element seen so far with key < thr_key is in the buffer
   float thr;         // the same threshold as a float; +inf at start
   int n_compact;                  // compactions so far (warp-uniform)
-  CM_PROBE(int n_trig, n_leaf; long long c_slow, c_compact;)  // development counters
+  CM_PROBE(int n_trig, n_leaf; long long c_slow, c_compact, c_drain;)  // development counters
 };
 
 __device__ long long* g_compact_dbg = nullptr;  // development: per-lane compaction statistics
@@ -852,7 +852,7 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
   }
   for (; e < cnt; ++e) put(lds_u32(keys + e * kCandStride), lds_u32(idx + e * kCandStride));
   const int w = (int)((wa - keys) / kCandStride);
-#ifdef CM_DEV_PROBES
+#ifdef CM_DEV_PROBES_COMPACT
   if (dbg) {
     const long long tc3 = clock64();
     atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)n_iter);
@@ -949,6 +949,7 @@ __device__ __forceinline__ void append_leaf(const uint32_t* v, uint32_t c0, RowC
 // Drain the per-lane leaf queues into the candidate buffers: iteration j handles entry j of every lane
 // that has one, so the trip count is the longest queue of the warp.
 __device__ __forceinline__ void drain_queue(RowCand& rc, int k) {
+  CM_PROBE(const long long t_d0 = clock64();)
   const int n_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)rc.qn);
   const uint32_t idx_off = rc.idx - rc.keys;
   int since_check = 0;
@@ -981,6 +982,7 @@ __device__ __forceinline__ void drain_queue(RowCand& rc, int k) {
     }
   }
   rc.qn = 0;
+  CM_PROBE(rc.c_drain += clock64() - t_d0;)
 }
 
 // One 64-column half tile of one query row (thread = row).  Fast path: a tree of minima over 16 leaves of
@@ -1298,7 +1300,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     rc.thr_key = 0xFFFFFFFFu;
     rc.thr = CUDART_INF_F;
     rc.n_compact = 0;
-    CM_PROBE(rc.n_trig = rc.n_leaf = 0; rc.c_slow = rc.c_compact = 0;)
+    CM_PROBE(rc.n_trig = rc.n_leaf = 0; rc.c_slow = rc.c_compact = rc.c_drain = 0;)
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
     const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t t_lane = t_lane_a + kTmemACols;
@@ -1384,7 +1386,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
 #ifdef CM_DEV_PROBES
     if (p.prof_out && lane == 0) {
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 5], (unsigned long long)rc.n_trig);
-      atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 6], (unsigned long long)rc.n_leaf);
+      atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 6], (unsigned long long)rc.c_drain);
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 7], (unsigned long long)rc.n_compact);
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 0], (unsigned long long)rc.c_slow);
       atomicAdd((unsigned long long*)&p.prof_out[(size_t)blockIdx.x * 8 + 1], (unsigned long long)rc.c_compact);

@@ -31,7 +31,7 @@ def run(n_q, n_r, d, flags, k=30, reps=3):
         if cd[4] > 0: print('compaction per lane-call: iters %.2f  cycles minmax %.0f  search %.0f  rewrite %.0f  cnt %.1f  calls %d' % (cd[0]/cd[4], cd[1]/cd[4], cd[2]/cd[4], cd[3]/cd[4], cd[5]/cd[4], cd[4]))
         print(json.dumps(dict(n_q=n_q, n_r=n_r, d=d, flags=f, mma_ms=float(ph[1]), rerank_ms=float(ph[2]),
                               cyc_per_tile=dict(epi_slow_path_per_warp=per[0] / 8, of_which_compaction=per[1] / 8, issue=per[2], total=per[3]),
-                              per_warp_tile=dict(triggered_halves=ev[0], leaves=ev[1], compactions=ev[2]))), flush=True)
+                              per_warp_tile=dict(triggered_halves=ev[0], drain_cycles=ev[1], compactions=ev[2]))), flush=True)
     lib.cm_debug_probe_flags(0)
     lib.cm_debug_probe_prof(None)
 
