@@ -67,7 +67,10 @@ int cm_device_check(int device);
  * r_index_offset is added to every emitted index (reference-sharded search).
  * stats_out (device, 4 x int64, may be NULL): [0] rows re-done by the exact fallback,
  *   [1] rows whose certificate failed even there (duplicate-distance ties; result still valid
- *   under the tie rule), [2] candidates examined by the re-rank, [3] reserved.
+ *   under the tie rule), [2] candidates examined by the re-rank, [3] (query tile, reference tile) pairs of
+ *   128 x 128 the tensor-core kernel evaluated: the scan is exact but skips reference cells that a
+ *   triangle-inequality bound rules out, so [3] * 16384 <= padded n_q * n_r.
+ * For a reference-sharded search use dist_mode = CM_DIST_SQUARED per shard and merge on d2.
  * ------------------------------------------------------------------------------------------- */
 size_t cm_knn_workspace_bytes(int64_t n_q, int64_t n_r, int d, int k, int algo);
 int cm_knn_search(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d, int dtype,
