@@ -1046,15 +1046,18 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
       }
     }
     // push the flagged leaves (the queue has room for all of them)
-    uint32_t cur = rc.dump + 16u * (uint32_t)rc.qn;
-    uint32_t ccur = rc.dump + 16u * kQueueCap + 4u * (uint32_t)rc.qn;
+    // Every leaf gets its own address registers (slot = number of flagged leaves before it): a running
+    // cursor would be overwritten while the previous store still has to read it, and the warp then waits
+    // on the memory pipe's scoreboard after every store (ncu r1c: 80 % short-scoreboard stalls on the
+    // cursor increments, a quarter of the epilogue's time).
+    const uint32_t cur0 = rc.dump + 16u * (uint32_t)rc.qn;
+    const uint32_t ccur0 = rc.dump + 16u * kQueueCap + 4u * (uint32_t)rc.qn;
 #pragma unroll
     for (int T = 0; T < 16; ++T)
       if (mine & (1u << T)) {
-        sts_v4(cur, v[4 * T], v[4 * T + 1], v[4 * T + 2], v[4 * T + 3]);
-        sts_u32(ccur, c0 + (uint32_t)(4 * T));
-        cur += 16;
-        ccur += 4;
+        const uint32_t slot = (uint32_t)__popc(mine & ((1u << T) - 1u));
+        sts_v4(cur0 + 16u * slot, v[4 * T], v[4 * T + 1], v[4 * T + 2], v[4 * T + 3]);
+        sts_u32(ccur0 + 4u * slot, c0 + (uint32_t)(4 * T));
       }
     rc.qn += n_mine;
     CM_PROBE(rc.c_slow += clock64() - t_slow0;)
