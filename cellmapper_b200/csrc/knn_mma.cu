@@ -1491,19 +1491,25 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
       if (lane < kStageRows && base + lane < filled) {
         double d2 = CUDART_INF;
         if (my_ok) {
+          // same summation order as rerank64_kernel (four interleaved groups of element pairs, combined as
+          // (s0 + s1) + (s2 + s3)), so that both re-rank kernels return bit-identical distances
           const T* sp = stage + lane * ds;
-          double acc0 = 0.0, acc1 = 0.0;
-          int c = 0;
-          for (; c + 2 <= d; c += 2) {
-            const double df0 = (double)sp[c] - qrow[c], df1 = (double)sp[c + 1] - qrow[c + 1];
-            acc0 = fma(df0, df0, acc0);
-            acc1 = fma(df1, df1, acc1);
+          double part[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int c = 2 * g; c + 2 <= d; c += 8) {
+              const double df0 = (double)sp[c] - qrow[c], df1 = (double)sp[c + 1] - qrow[c + 1];
+              acc0 = fma(df0, df0, acc0);
+              acc1 = fma(df1, df1, acc1);
+            }
+            if ((d & 1) && g == (((d - 1) >> 1) & 3)) {
+              const double df = (double)sp[d - 1] - qrow[d - 1];
+              acc0 = fma(df, df, acc0);
+            }
+            part[g] = acc0 + acc1;
           }
-          if (c < d) {
-            const double df = (double)sp[c] - qrow[c];
-            acc0 = fma(df, df, acc0);
-          }
-          d2 = acc0 + acc1;
+          d2 = (part[0] + part[1]) + (part[2] + part[3]);
         }
         keys[base + lane] = d2;
       }
@@ -1595,40 +1601,73 @@ rerank64_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, i
     for (int c = lane; c < dp; c += 32) qrow[c] = c < d ? (double)Q[q * ldq + c] : 0.0;
     __syncwarp();
     const bool ok0 = id0 >= 0 && id0 < n_r, ok1 = id1 >= 0 && id1 < n_r;
-    const T* r0 = R + (int64_t)(ok0 ? id0 : 0) * ldr;
-    const T* r1 = R + (int64_t)(ok1 ? id1 : 0) * ldr;
-    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    int c = 0;
-    if (((reinterpret_cast<uintptr_t>(R) | (uintptr_t)(ldr * sizeof(T))) & (2 * sizeof(T) - 1)) == 0) {
-      // rows are aligned to two elements: paired loads
-      using T2 = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
-      for (; c + 2 <= d; c += 2) {
-        const T2 x0 = *reinterpret_cast<const T2*>(r0 + c), x1 = *reinterpret_cast<const T2*>(r1 + c);
-        const double2 qq = *reinterpret_cast<const double2*>(qrow + c);
-        const double e0 = (double)x0.x - qq.x, e1 = (double)x0.y - qq.y, f0 = (double)x1.x - qq.x, f1 = (double)x1.y - qq.y;
-        a0 = fma(e0, e0, a0);
-        a1 = fma(e1, e1, a1);
-        b0 = fma(f0, f0, b0);
-        b1 = fma(f1, f1, b1);
+    // Distances: four lanes per candidate row, eight candidates per round.  Lane i of a quad reads the
+    // element pairs i, i+4, i+8, ... of its row, so one warp-wide load touches 8 rows x one 32-byte sector
+    // (with a lane per row every load touched 32 rows and each sector was fetched four times: ncu r1c showed
+    // the L1/TEX pipe at 85 %).  All loads of a round are issued before the first use.  The partial sums are
+    // combined inside the quad, and candidate c = 8 * round + quad lands on lane c % 32 (first or second
+    // element), the layout the sorting network expects.
+    const int quad = lane >> 2, qi = lane & 3;
+    double ka = CUDART_INF, kb = CUDART_INF;
+    const bool aligned2 = ((reinterpret_cast<uintptr_t>(R) | (uintptr_t)(ldr * sizeof(T))) & (2 * sizeof(T) - 1)) == 0;
+    const int n_rounds = (total + 7) >> 3;
+    constexpr int kPairs = 7;  // pairs per lane: d <= 56 (the tensor-core path stops at 53)
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const int src = ((rd & 3) << 3) + quad;  // lane that holds candidate c = 8 rd + quad
+      const int idc = __shfl_sync(0xffffffffu, rd < 4 ? id0 : id1, src);
+      const bool okc = idc >= 0 && idc < n_r;
+      const T* rp = R + (int64_t)(okc ? idc : 0) * ldr;
+      T x0[kPairs], x1[kPairs];
+      if (aligned2) {
+        using T2 = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+#pragma unroll
+        for (int t = 0; t < kPairs; ++t) {
+          const int c = 2 * qi + 8 * t;
+          T2 x;
+          x.x = (T)0; x.y = (T)0;
+          if (c + 2 <= d) x = *reinterpret_cast<const T2*>(rp + c);
+          x0[t] = x.x;
+          x1[t] = x.y;
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < kPairs; ++t) {
+          const int c = 2 * qi + 8 * t;
+          x0[t] = c + 2 <= d ? rp[c] : (T)0;
+          x1[t] = c + 2 <= d ? rp[c + 1] : (T)0;
+        }
       }
-    } else {
-      for (; c + 2 <= d; c += 2) {
-        const double e0 = (double)r0[c] - qrow[c], e1 = (double)r0[c + 1] - qrow[c + 1];
-        const double f0 = (double)r1[c] - qrow[c], f1 = (double)r1[c + 1] - qrow[c + 1];
+      T xl = (T)0;
+      const bool has_last = (d & 1) && qi == (((d - 1) >> 1) & 3);  // odd d: the last element belongs to the lane whose turn it is
+      if (has_last) xl = rp[d - 1];
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < kPairs; ++t) {
+        const int c = 2 * qi + 8 * t;
+        if (c + 2 <= d) {
+          const double2 qq = *reinterpret_cast<const double2*>(qrow + c);
+          const double e0 = (double)x0[t] - qq.x, e1 = (double)x1[t] - qq.y;
+          a0 = fma(e0, e0, a0);
+          a1 = fma(e1, e1, a1);
+        }
+      }
+      if (has_last) {
+        const double e0 = (double)xl - qrow[d - 1];
         a0 = fma(e0, e0, a0);
-        a1 = fma(e1, e1, a1);
-        b0 = fma(f0, f0, b0);
-        b1 = fma(f1, f1, b1);
+      }
+      double sum = a0 + a1;
+      sum += shfl_xor_f64(sum, 1);
+      sum += shfl_xor_f64(sum, 2);
+      if (!okc) sum = CUDART_INF;
+      // hand candidate 8 rd + g to lane 8 (rd % 4) + g
+      const double got = shfl_f64_idx(sum, (lane & 7) << 2);
+      if ((lane >> 3) == (rd & 3)) {
+        if (rd < 4) ka = got; else kb = got;
       }
     }
-    if (c < d) {
-      const double e0 = (double)r0[c] - qrow[c], f0 = (double)r1[c] - qrow[c];
-      a0 = fma(e0, e0, a0);
-      b0 = fma(f0, f0, b0);
-    }
-    // same summation order as rerank_kernel: even and odd dimensions in two accumulators
-    double ka = ok0 ? a0 + a1 : CUDART_INF, kb = ok1 ? b0 + b1 : CUDART_INF;
     int va = ok0 ? id0 : INT32_MAX, vb = ok1 ? id1 : INT32_MAX;
+    if (!ok0) ka = CUDART_INF;
+    if (!ok1) kb = CUDART_INF;
     // bitonic sort of 64 pairs; element index i = lane (a) / lane + 32 (b)
 #pragma unroll
     for (int size = 2; size <= 64; size <<= 1) {
