@@ -689,6 +689,7 @@ struct RowCand {
   int cnt;
   uint32_t thr_key;  // every element seen so far with key < thr_key is in the buffer
   float thr;         // the same threshold as a float; +inf at start
+  uint32_t kmin;                  // float bits: estimate of the row's smallest key (+inf before the first compaction)
   int n_compact;                  // compactions so far (warp-uniform)
   CM_PROBE(int n_trig, n_leaf; long long c_slow, c_compact, c_drain;)  // development counters
 };
@@ -699,31 +700,24 @@ __device__ long long* g_compact_dbg = nullptr;  // development: per-lane compact
 // and the order-preserving uint domain (bisection needs integer midpoints)
 __device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds_u32(addr)); }
 
-__device__ __forceinline__ int count_below(uint32_t keys, int cnt, float piv) {
-  int c = 0;
-  int e = 0;
-  // 16 independent loads in flight: one warp per scheduler, so every pass runs at shared-memory latency / ILP
-  for (; e + 16 <= cnt; e += 16) {
-    float kk[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) kk[j] = lds_f32(keys + (e + j) * kCandStride);
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      c0 += kk[j] < piv;
-      c1 += kk[j + 1] < piv;
-      c2 += kk[j + 2] < piv;
-      c3 += kk[j + 3] < piv;
-    }
-    c += (c0 + c1) + (c2 + c3);
-  }
-  for (; e + 4 <= cnt; e += 4) {
-    const float k0 = lds_f32(keys + (e + 0) * kCandStride), k1 = lds_f32(keys + (e + 1) * kCandStride);
-    const float k2 = lds_f32(keys + (e + 2) * kCandStride), k3 = lds_f32(keys + (e + 3) * kCandStride);
-    c += (k0 < piv) + (k1 < piv) + (k2 < piv) + (k3 < piv);
-  }
-  for (; e < cnt; ++e) c += lds_f32(keys + e * kCandStride) < piv;
-  return c;
+// guarded shared load: `dflt` when the entry lies beyond the row's count (predicated, no branch)
+__device__ __forceinline__ uint32_t lds_u32_guard(uint32_t addr, bool ok, uint32_t dflt) {
+  uint32_t v;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %2, 0;\n\t"
+      "mov.u32 %0, %3;\n\t"
+      "@p ld.shared.u32 %0, [%1];\n\t}"
+      : "=r"(v)
+      : "r"(addr), "r"((uint32_t)ok), "r"(dflt));
+  return v;
+}
+constexpr uint32_t kInfBits = 0x7f800000u;
+// a < b as 1.0f / 0.0f: one FSET + one FADD per counted key (counts <= 128 are exact in fp32)
+__device__ __forceinline__ float lt_one(float a, float b) {
+  float m;
+  asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+  return m;
 }
 
 // Keep window: after a compaction a row holds between k + 6 and k + 22 candidates, never fewer than k,
@@ -740,96 +734,144 @@ __device__ __forceinline__ void keep_window(int k, int& keep_lo, int& keep_hi) {
   keep_lo = min(k + 6, keep_hi - 4);
 }
 
-// Shrink the buffer to between keep_lo and keep_hi entries and tighten the threshold.  Selection,
-// not sorting: a bracketed search for a pivot whose rank lands in the window -- the first probes
-// interpolate (neighbour distances grow smoothly with rank, so they usually hit at once), then plain
-// bisection on the ordered-uint image of the key.  Ties that straddle the window are cut arbitrarily
-// and the threshold is set to the tied value (the row then keeps fewer strictly-below entries and, if
-// it matters, fails its certificate).
+// Shrink the buffers of the warp's 32 rows to between keep_lo and keep_hi entries each and tighten the
+// thresholds.  Selection, not sorting: a bracketed search for a pivot whose rank lands in the window.
+// The 32 rows run in lockstep, so the whole routine is written WARP-UNIFORM: every loop runs to the
+// longest row of the warp with guarded (predicated) loads, there is no per-lane trip count and no
+// divergent tail loop (the first version ran per-lane loops over `cnt`; ncu r1d: 15 k cycles per call,
+// most of it branch resolution and reconvergence, and the three other epilogue warps of the CTA waited
+// for the compacting one).  Every counting pass probes FOUR pivots per row: the first four are placed by
+// a log-linear model of the neighbour count between the row's smallest key (a running estimate) and
+// its threshold, spread so that a factor-two model error still lands one of them in the window; later
+// passes interpolate inside the bracket, then fall back to 5-ary bisection on the ordered-uint image.
+// Ties that straddle the window are cut arbitrarily and the threshold is set to the tied value (the
+// row then keeps fewer strictly-below entries and, if it matters, fails its certificate).
+// Rows with cnt <= keep_hi take part in the votes but are left untouched.
 // Cold code, deliberately NOT inlined: the hot epilogue loop has to stay inside the instruction cache.
-// Returns (new count) | (new threshold key << 32).
-__device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint32_t idx, int cnt, uint32_t thr_key,
-                                                            int k, long long* dbg) {
+// Returns {new count, new threshold key, smallest key of the row (float bits), 0}.
+__device__ __noinline__ uint4 compact_rows_cold(uint32_t keys, uint32_t idx, int cnt, uint32_t thr_key, uint32_t kmin_bits,
+                                                int k, long long* dbg) {
   CM_PROBE(const long long tc0 = clock64();)
   int keep_lo, keep_hi;
   keep_window(k, keep_lo, keep_hi);
-  if (cnt <= keep_hi) return (unsigned long long)(uint32_t)cnt | ((unsigned long long)thr_key << 32);
+  const bool active = cnt > keep_hi;
+  const int n = active ? cnt : 0;
+  const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)n);
+  if (nmax == 0) return make_uint4((uint32_t)cnt, thr_key, kmin_bits, 0u);
   CM_PROBE(int n_iter = 0;)
-  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-  {
-    int e = 0;
-    for (; e + 16 <= cnt; e += 16) {  // 16 independent loads in flight, tree reduction
-      float kk[16];
+  float kmin = __uint_as_float(kmin_bits);
+  // bracket in the ordered domain: count(key < lo) = c_lo < keep_lo ; count(key < hi) = c_hi > keep_hi.
+  // Every key is <= the threshold (== only after a tie cut), so hi = threshold + 1 counts them all.
+  uint32_t lo = 0u, hi = thr_key + 1u;
+  int c_lo = 0, c_hi = n;
+  // the first compaction of a scan: no finite threshold / no estimate of the smallest key yet
+  const bool need_mm = active && (thr_key == 0xFFFFFFFFu || !(kmin < CUDART_INF_F));
+  if (__any_sync(0xffffffffu, need_mm)) {
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    for (int e = 0; e < nmax; e += 8) {
+      float kk[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) kk[j] = lds_f32(keys + (e + j) * kCandStride);
-      float a0 = fminf(fminf(kk[0], kk[1]), kk[2]), a1 = fminf(fminf(kk[3], kk[4]), kk[5]);
-      float a2 = fminf(fminf(kk[6], kk[7]), kk[8]), a3 = fminf(fminf(kk[9], kk[10]), kk[11]);
-      float a4 = fminf(fminf(kk[12], kk[13]), fminf(kk[14], kk[15]));
-      mn = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(a4, mn));
-      float b0 = fmaxf(fmaxf(kk[0], kk[1]), kk[2]), b1 = fmaxf(fmaxf(kk[3], kk[4]), kk[5]);
-      float b2 = fmaxf(fmaxf(kk[6], kk[7]), kk[8]), b3 = fmaxf(fmaxf(kk[9], kk[10]), kk[11]);
-      float b4 = fmaxf(fmaxf(kk[12], kk[13]), fmaxf(kk[14], kk[15]));
-      mx = fmaxf(fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)), fmaxf(b4, mx));
+      for (int j = 0; j < 8; ++j)
+        kk[j] = __uint_as_float(lds_u32_guard(keys + (uint32_t)(e + j) * kCandStride, e + j < n, kInfBits));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mn = fminf(mn, kk[j]);
+        mx = fmaxf(mx, e + j < n ? kk[j] : -CUDART_INF_F);
+      }
     }
-    for (; e < cnt; ++e) {
-      const float kx = lds_f32(keys + e * kCandStride);
-      mn = fminf(mn, kx);
-      mx = fmaxf(mx, kx);
-    }
+    if (active) kmin = fminf(kmin, mn);
+    if (need_mm) hi = float_to_ordered(mx) + 1u;  // keys are finite: no wrap
   }
   CM_PROBE(const long long tc1 = clock64();)
-  // bracket in the ordered domain: count(key < lo) = c_lo < keep_lo ; count(key < hi) = c_hi > keep_hi
-  uint32_t lo = float_to_ordered(mn), hi = float_to_ordered(mx) + 1u;  // keys are finite: no wrap
-  int c_lo = 0, c_hi = cnt;
   uint32_t tl = hi;
-  int c_tl = cnt;
-  bool tie = false, found = false;
-  const float target = 0.5f * (float)(keep_lo + keep_hi);
-  for (int iter = 0; hi - lo > 1u; ++iter) {
-    uint32_t piv;
-    if (iter < 4) {
+  int c_tl = n;
+  bool tie = false, done = !active;
+  const float w_lo = (float)keep_lo, w_span = (float)(keep_hi - keep_lo);
+  for (int iter = 0;; ++iter) {
+    uint32_t pv[4];
+    if (iter < 3) {
       // neighbour counts grow like a power of the distance, so the count is interpolated in log space
-      // (linear interpolation needs ~8 probes at 50 dimensions, this ~2)
-      const float f_lo = ordered_to_float(lo), f_hi = ordered_to_float(hi - 1u);
+      const float f_lo = c_lo > 0 ? ordered_to_float(lo) : kmin, f_hi = ordered_to_float(hi - 1u);
       const float l_lo = __log2f(fmaxf((float)c_lo, 0.5f));
-      const float frac = (__log2f(target) - l_lo) / (__log2f((float)c_hi) - l_lo);
-      piv = float_to_ordered(f_lo + (f_hi - f_lo) * frac);
-      piv = min(max(piv, lo + 1u), hi - 1u);
+      const float inv = 1.f / (__log2f((float)max(c_hi, 1)) - l_lo);
+      const float mid = w_lo + 0.5f * w_span;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // first pass: ranks mid * {0.62, 0.86, 1.16, 1.6}; later passes: four ranks inside the window
+        const float f0 = j == 0 ? 0.62f : j == 1 ? 0.86f : j == 2 ? 1.16f : 1.6f;
+        const float target = iter == 0 ? mid * f0 : w_lo + w_span * (0.125f + 0.25f * (float)j);
+        const float frac = (__log2f(target) - l_lo) * inv;
+        const uint32_t pj = float_to_ordered(f_lo + (f_hi - f_lo) * frac);
+        pv[j] = min(max(pj, lo + 1u), hi - 1u);
+      }
     } else {
-      piv = lo + ((hi - lo) >> 1);
+      const uint32_t span = hi - lo;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t step = (uint32_t)(((unsigned long long)span * (unsigned)(j + 1)) / 5ull);
+        pv[j] = min(lo + max(step, 1u), hi - 1u);
+      }
     }
-    const int c = count_below(keys, cnt, ordered_to_float(piv));
+    // keep the pivots ascending after clamping (NaN-free: all finite)
+    pv[1] = max(pv[1], pv[0]);
+    pv[2] = max(pv[2], pv[1]);
+    pv[3] = max(pv[3], pv[2]);
+    const float p0 = ordered_to_float(pv[0]), p1 = ordered_to_float(pv[1]), p2 = ordered_to_float(pv[2]),
+                p3 = ordered_to_float(pv[3]);
+    float cf0 = 0.f, cf1 = 0.f, cf2 = 0.f, cf3 = 0.f;
+    for (int e = 0; e < nmax; e += 8) {
+      float kk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        kk[j] = __uint_as_float(lds_u32_guard(keys + (uint32_t)(e + j) * kCandStride, e + j < n, kInfBits));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        cf0 += lt_one(kk[j], p0);
+        cf1 += lt_one(kk[j], p1);
+        cf2 += lt_one(kk[j], p2);
+        cf3 += lt_one(kk[j], p3);
+      }
+    }
+    const int c[4] = {(int)cf0, (int)cf1, (int)cf2, (int)cf3};
     CM_PROBE(++n_iter;)
-    if (c < keep_lo) {
-      lo = piv;
-      c_lo = c;
-    } else if (c > keep_hi) {
-      hi = piv;
-      c_hi = c;
-    } else {
-      tl = piv;
-      c_tl = c;
-      found = true;
-      break;
+    if (!done) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (done || pv[j] >= hi) continue;  // above a pivot that already overshot
+        if (c[j] < keep_lo) {
+          lo = pv[j];
+          c_lo = c[j];
+        } else if (c[j] > keep_hi) {
+          hi = pv[j];
+          c_hi = c[j];
+        } else {
+          tl = pv[j];
+          c_tl = c[j];
+          done = true;
+        }
+      }
+      if (!done && hi - lo <= 1u) {  // keys equal to `lo` straddle the window
+        tl = lo;
+        c_tl = c_lo;
+        tie = true;
+        done = true;
+      }
     }
-  }
-  if (!found) {  // keys equal to `lo` straddle the window
-    tl = lo;
-    c_tl = c_lo;
-    tie = true;
+    if (!__any_sync(0xffffffffu, !done)) break;
   }
   CM_PROBE(const long long tc2 = clock64();)
   const float tl_f = ordered_to_float(tl);
   int extra = tie ? keep_hi - c_tl : 0;
   const uint32_t idx_off = idx - keys;
   uint32_t wa = keys;  // shared address of the next kept slot
-  // branch-free: the 32 rows of the warp run this in lockstep, a divergent branch per entry costs more
-  // than the two predicated stores
+  float mn_new = CUDART_INF_F;
+  // branch-free: a divergent branch per entry costs more than the two predicated stores
   auto put = [&](uint32_t raw, uint32_t ix) {
-    const float kx = __uint_as_float(raw);
+    const float kx = __uint_as_float(raw);  // +inf beyond the row's count: never kept
     const bool tie_keep = tie & (kx == tl_f) & (extra > 0);
     const bool keep = (kx < tl_f) | tie_keep;
     extra -= tie_keep ? 1 : 0;
+    mn_new = fminf(mn_new, kx);
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.u32 p, %4, 0;\n\t"
@@ -839,21 +881,19 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
         : "memory");
     wa += keep ? kCandStride : 0u;
   };
-  int e = 0;
-  for (; e + 8 <= cnt; e += 8) {  // all loads of a group before its stores (kept slot <= e: a store never hits an unread slot)
+  for (int e = 0; e < nmax; e += 8) {  // all loads of a group before its stores (kept slot <= e: a store never hits an unread slot)
     uint32_t rr[8], ii[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      rr[j] = lds_u32(keys + (e + j) * kCandStride);
-      ii[j] = lds_u32(idx + (e + j) * kCandStride);
+      rr[j] = lds_u32_guard(keys + (uint32_t)(e + j) * kCandStride, e + j < n, kInfBits);
+      ii[j] = lds_u32_guard(idx + (uint32_t)(e + j) * kCandStride, e + j < n, 0u);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) put(rr[j], ii[j]);
   }
-  for (; e < cnt; ++e) put(lds_u32(keys + e * kCandStride), lds_u32(idx + e * kCandStride));
   const int w = (int)((wa - keys) / kCandStride);
 #ifdef CM_DEV_PROBES_COMPACT
-  if (dbg) {
+  if (dbg && active) {
     const long long tc3 = clock64();
     atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)n_iter);
     atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(tc1 - tc0));
@@ -863,15 +903,18 @@ __device__ __noinline__ unsigned long long compact_row_cold(uint32_t keys, uint3
     atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)cnt);
   }
 #endif
-  return (unsigned long long)(uint32_t)w | ((unsigned long long)tl << 32);
+  if (!active) return make_uint4((uint32_t)cnt, thr_key, kmin_bits, 0u);
+  return make_uint4((uint32_t)w, tl, __float_as_uint(mn_new), 0u);
 }
 
+// all 32 lanes of the warp call this together
 __device__ __forceinline__ void compact_row(RowCand& rc, int k) {
   CM_PROBE(const long long t0 = clock64();)
-  const unsigned long long r = compact_row_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, k, g_compact_dbg);
+  const uint4 r = compact_rows_cold(rc.keys, rc.idx, rc.cnt, rc.thr_key, rc.kmin, k, g_compact_dbg);
   CM_PROBE(rc.c_compact += clock64() - t0;)
-  rc.cnt = (int)(uint32_t)r;
-  rc.thr_key = (uint32_t)(r >> 32);
+  rc.cnt = (int)r.x;
+  rc.thr_key = r.y;
+  rc.kmin = r.z;
   rc.thr = rc.thr_key == 0xFFFFFFFFu ? CUDART_INF_F : ordered_to_float(rc.thr_key);
 }
 
@@ -1302,6 +1345,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     rc.qn = 0;
     rc.thr_key = 0xFFFFFFFFu;
     rc.thr = CUDART_INF_F;
+    rc.kmin = kInfBits;
     rc.n_compact = 0;
     CM_PROBE(rc.n_trig = rc.n_leaf = 0; rc.c_slow = rc.c_compact = rc.c_drain = 0;)
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
