@@ -1095,13 +1095,20 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     // cursor increments, a quarter of the epilogue's time).
     const uint32_t cur0 = rc.dump + 16u * (uint32_t)rc.qn;
     const uint32_t ccur0 = rc.dump + 16u * kQueueCap + 4u * (uint32_t)rc.qn;
+    // Predicated, not branched: the flagged leaves differ from lane to lane, so a branch per leaf diverges
+    // on nearly every one of them (ncu r1e: instruction-fetch and branch-resolution stalls on the 16 tests).
 #pragma unroll
-    for (int T = 0; T < 16; ++T)
-      if (mine & (1u << T)) {
-        const uint32_t slot = (uint32_t)__popc(mine & ((1u << T) - 1u));
-        sts_v4(cur0 + 16u * slot, v[4 * T], v[4 * T + 1], v[4 * T + 2], v[4 * T + 3]);
-        sts_u32(ccur0 + 4u * slot, c0 + (uint32_t)(4 * T));
-      }
+    for (int T = 0; T < 16; ++T) {
+      const uint32_t slot = (uint32_t)__popc(mine & ((1u << T) - 1u));
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.u32 p, %7, 0;\n\t"
+          "@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t"
+          "@p st.shared.u32 [%5], %6;\n\t}"
+          ::"r"(cur0 + 16u * slot), "r"(v[4 * T]), "r"(v[4 * T + 1]), "r"(v[4 * T + 2]), "r"(v[4 * T + 3]),
+            "r"(ccur0 + 4u * slot), "r"(c0 + (uint32_t)(4 * T)), "r"(mine & (1u << T))
+          : "memory");
+    }
     rc.qn += n_mine;
     CM_PROBE(rc.c_slow += clock64() - t_slow0;)
   }
