@@ -82,11 +82,15 @@ class _DeviceCSR:
 class CellMapper:
     """Mapping of labels, embeddings, and expression values between reference and query datasets."""
 
-    def __init__(self, query: AnnData, reference: AnnData | None = None, *, allreduce=None) -> None:
+    def __init__(self, query: AnnData, reference: AnnData | None = None, *, allreduce=None, upload_replicated=None) -> None:
         """``allreduce`` (keyword-only, not in the reference): in-place SUM over ranks for the kernel
         bandwidth statistics when the query cells are sharded over several GPUs
-        (``cellmapper_b200.dist.allreduce_sum``); ``None`` for a single process."""
+        (``cellmapper_b200.dist.allreduce_sum``); ``None`` for a single process.
+        ``upload_replicated`` (keyword-only): callable(host array) -> device tensor used for the
+        reference-side arrays every rank holds in full (``cellmapper_b200.dist.upload_replicated``:
+        each rank uploads 1/world of the rows, NCCL all-gather); ``None``: plain uploads."""
         self._allreduce = allreduce
+        self._upload_ref = upload_replicated if (upload_replicated is not None and reference is not None) else None
         self.query = query
         self.reference = reference if reference is not None else query  # cellmapper.py:37-38
         self._is_self_mapping = reference is None
@@ -186,7 +190,7 @@ class CellMapper:
         yrep = np.ascontiguousarray(np.asarray(yrep)[:, :n_comps])
         # cellmapper.py:250 always passes both arrays; in self-mapping they are the same object here so
         # the embedding is uploaded once
-        self.knn = Neighbors(xrep, xrep if self._is_self_mapping else yrep)
+        self.knn = Neighbors(xrep, xrep if self._is_self_mapping else yrep, upload_reference=self._upload_ref)
         self.knn.compute_neighbors(n_neighbors=n_neighbors, method=method, metric=metric, only_yx=only_yx)
         self._mapping = None
 
@@ -253,10 +257,10 @@ class CellMapper:
             col = self.reference.obs[key]
             if isinstance(col.dtype, pd.CategoricalDtype) or pd.api.types.is_object_dtype(col) or pd.api.types.is_string_dtype(col):
                 cats, codes = sorted_category_codes(col)
-                self._prefetched[("obs", key)] = (cats, _to_device(codes))
+                self._prefetched[("obs", key)] = (cats, (self._upload_ref or _to_device)(codes))
         for key in ([obsm_keys] if isinstance(obsm_keys, str) else (obsm_keys or [])):
             if key in self.reference.obsm:
-                self._prefetched[("obsm", key)] = _to_device(np.asarray(self.reference.obsm[key]))
+                self._prefetched[("obsm", key)] = (self._upload_ref or _to_device)(np.asarray(self.reference.obsm[key]))
 
     def _require_mapping(self) -> _DeviceCSR:
         if self._mapping is None:

@@ -377,45 +377,44 @@ __global__ void gather_pivots_kernel(const T* __restrict__ R, int64_t ldr, int64
 // around in.  One CTA, pivot j in the registers of thread j; 255 steps of one distance + one block argmin.
 __global__ void __launch_bounds__(kMaxCells) order_pivots_kernel(int d, int n_cells, float* __restrict__ piv_t, float* __restrict__ piv_norm) {
   __shared__ float cur[kAssignMaxD];
-  __shared__ unsigned long long wmin[kMaxCells / 32];
-  __shared__ int s_next;
+  __shared__ unsigned long long wmin[2][kMaxCells / 32];
   const int j = threadIdx.x;
   const bool have = j < n_cells;
   float pv[kAssignMaxD];
 #pragma unroll
   for (int c = 0; c < kAssignMaxD; ++c) pv[c] = (have && c < d) ? piv_t[(size_t)c * n_cells + j] : 0.f;
   const float nn = have ? piv_norm[j] : 0.f;
-  bool visited = !have;
+  bool visited = !have || j == 0;
   int pos = 0;  // new number of this thread's pivot
   int at = 0;
-  if (j == 0) visited = true;
   for (int step = 1; step < n_cells; ++step) {
     if (j == at) {
 #pragma unroll
       for (int c = 0; c < kAssignMaxD; ++c) cur[c] = pv[c];
     }
     __syncthreads();
-    float dist = 0.f;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // four chains: the loop is latency-bound
 #pragma unroll
-    for (int c = 0; c < kAssignMaxD; ++c) {
-      const float t = pv[c] - cur[c];
-      dist = fmaf(t, t, dist);
+    for (int c = 0; c < kAssignMaxD; c += 4) {
+      const float t0 = pv[c] - cur[c], t1 = pv[c + 1] - cur[c + 1], t2 = pv[c + 2] - cur[c + 2], t3 = pv[c + 3] - cur[c + 3];
+      d0 = fmaf(t0, t0, d0);
+      d1 = fmaf(t1, t1, d1);
+      d2 = fmaf(t2, t2, d2);
+      d3 = fmaf(t3, t3, d3);
     }
+    const float dist = (d0 + d1) + (d2 + d3);
     unsigned long long key = visited ? ~0ull : (((unsigned long long)__float_as_uint(dist)) << 32) | (unsigned)j;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
       key = other < key ? other : key;
     }
-    if ((j & 31) == 0) wmin[j >> 5] = key;
+    if ((j & 31) == 0) wmin[step & 1][j >> 5] = key;
     __syncthreads();
-    if (j == 0) {
-      unsigned long long m = wmin[0];
-      for (int w = 1; w < kMaxCells / 32; ++w) m = wmin[w] < m ? wmin[w] : m;
-      s_next = (int)(unsigned)(m & 0xffffffffull);
-    }
-    __syncthreads();
-    at = s_next;
+    unsigned long long m = wmin[step & 1][0];
+#pragma unroll
+    for (int w = 1; w < kMaxCells / 32; ++w) m = wmin[step & 1][w] < m ? wmin[step & 1][w] : m;
+    at = (int)(unsigned)(m & 0xffffffffull);
     if (j == at) {
       visited = true;
       pos = step;

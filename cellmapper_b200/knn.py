@@ -231,7 +231,10 @@ def extract_neighbors_from_distances(distances_matrix, include_self: bool | None
 class Neighbors:
     """Compute and store nearest neighbours (reference: knn.py:269-492) with the B200 back-end."""
 
-    def __init__(self, xrep, yrep=None):
+    def __init__(self, xrep, yrep=None, *, upload_reference=None):
+        # upload_reference: optional callable(host array) -> device tensor for the reference side
+        # (cellmapper_b200.dist.upload_replicated in multi-GPU runs); default: a plain upload
+        self._upload_reference = upload_reference
         self.xrep = xrep
         self.yrep = yrep if yrep is not None else xrep
         self.xx: NeighborsResults | None = None
@@ -273,7 +276,7 @@ class Neighbors:
         if metric != "euclidean":
             raise ValueError(f"method='b200' supports metric='euclidean' only (got {metric!r}).")
         logger.info("Using %s to compute %d neighbors.", method, n_neighbors)
-        x = _to_device(self.xrep)
+        x = self._upload_reference(self.xrep) if self._upload_reference is not None else _to_device(self.xrep)
         y = x if self.yrep is self.xrep else _to_device(self.yrep)
         np_dtype = np.result_type(
             np.float32 if x.dtype == torch.float32 else np.float64, np.float32 if y.dtype == torch.float32 else np.float64

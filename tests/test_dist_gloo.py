@@ -69,6 +69,12 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         return torch.from_numpy(key[rows, order]), torch.from_numpy(ci2[rows, order])
 
     md, mi = cmd.reference_sharded_search(torch.from_numpy(xq), torch.from_numpy(xr[rlo:rhi]), rlo, k, search, merge)
+    # ---- replicated reference arrays: every rank uploads its row block, all-gather (odd row count, 1-D and 2-D)
+    up2 = cmd.upload_replicated(xr, device=torch.device("cpu"), min_bytes=0)
+    up1 = cmd.upload_replicated(cr.astype(np.int32), device=torch.device("cpu"), min_bytes=0)
+    small = cmd.upload_replicated(xr[:3], device=torch.device("cpu"))  # below min_bytes: direct upload
+    assert up2.shape == xr.shape and torch.equal(up2, torch.from_numpy(xr))
+    assert torch.equal(up1, torch.from_numpy(cr.astype(np.int32))) and torch.equal(small, torch.from_numpy(xr[:3]))
     if rank == 0:
         np.savez(
             os.path.join(out_dir, "out.npz"), w=gathered_w.numpy(), i=gathered_i.numpy(), mean=mean, std=std,
