@@ -1158,17 +1158,34 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     const uint32_t ccur0 = rc.dump + 16u * kQueueCap + 4u * (uint32_t)rc.qn;
     // Predicated, not branched: the flagged leaves differ from lane to lane, so a branch per leaf diverges
     // on nearly every one of them (ncu r1e: instruction-fetch and branch-resolution stalls on the 16 tests).
+    // The two store addresses advance through a chain of fresh registers: a cursor updated in place would
+    // wait for the store still reading it, and the slot as popc(mine & below) cost 16 POPCs per half tile
+    // on a pipe that issues one warp instruction every 8 cycles.
+    uint32_t a16 = cur0, a4 = ccur0;
 #pragma unroll
     for (int T = 0; T < 16; ++T) {
-      const uint32_t slot = (uint32_t)__popc(mine & ((1u << T) - 1u));
+      // bit = 0 or 2^T; next address = address + 16 (4) * [bit set] as ONE multiply-add on the FMA pipe
+      // (mad.hi with 2^(36-T) for T >= 5: bit * 2^(36-T) >> 32 = 16; mad.lo with 16 >> T below), leaving the compare/logic pipe to the screening
+      const uint32_t bit = mine & (1u << T);
+      uint32_t n16, n4;
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
-          "setp.ne.u32 p, %7, 0;\n\t"
-          "@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t"
-          "@p st.shared.u32 [%5], %6;\n\t}"
-          ::"r"(cur0 + 16u * slot), "r"(v[4 * T]), "r"(v[4 * T + 1]), "r"(v[4 * T + 2]), "r"(v[4 * T + 3]),
-            "r"(ccur0 + 4u * slot), "r"(c0 + (uint32_t)(4 * T)), "r"(mine & (1u << T))
+          "setp.ne.u32 p, %2, 0;\n\t"
+          "@p st.shared.v4.u32 [%0], {%3, %4, %5, %6};\n\t"
+          "@p st.shared.u32 [%1], %7;\n\t}"
+          ::"r"(a16), "r"(a4), "r"(bit), "r"(v[4 * T]), "r"(v[4 * T + 1]), "r"(v[4 * T + 2]), "r"(v[4 * T + 3]),
+            "r"(c0 + (uint32_t)(4 * T))
           : "memory");
+      if (T >= 5)
+        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(1u << ((36 - T) & 31)), "r"(a16));
+      else
+        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(16u >> T), "r"(a16));
+      if (T >= 3)
+        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(1u << ((34 - T) & 31)), "r"(a4));
+      else
+        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(4u >> T), "r"(a4));
+      a16 = n16;
+      a4 = n4;
     }
     rc.qn += n_mine;
     CM_PROBE(rc.c_slow += clock64() - t_slow0;)
