@@ -1116,13 +1116,15 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
   if (__any_sync(0xffffffffu, m < rc.thr) && !(flags & 16)) {  // probe 16: fast path only
     const float thr0 = rc.thr;
     CM_PROBE(++rc.n_trig; const long long t_slow0 = clock64();)
-    // this lane's flagged leaves; two partial masks so the bit-insert chains are 8 deep
+    // this lane's flagged leaves, leaf T at bit 15 - T: the sign of t[T] - thr0 (an add on the FMA pipe) is
+    // shifted into the mask by ONE funnel shift per leaf (compare + select + or was three instructions of
+    // the compare/logic pipe, which bounds this loop); two partial masks so the chains are 8 deep
     uint32_t ma = 0, mb = 0;
 #pragma unroll
-    for (int T = 0; T < 8; ++T) ma |= (t[T] < thr0) ? (1u << T) : 0u;
+    for (int T = 0; T < 8; ++T) ma = __funnelshift_l(__float_as_uint(t[T] - thr0), ma, 1);
 #pragma unroll
-    for (int T = 8; T < 16; ++T) mb |= (t[T] < thr0) ? (1u << T) : 0u;
-    const uint32_t mine = ma | mb;
+    for (int T = 8; T < 16; ++T) mb = __funnelshift_l(__float_as_uint(t[T] - thr0), mb, 1);
+    const uint32_t mine = (ma << 8) | mb;
     const int n_mine = __popc(mine);
     if (__any_sync(0xffffffffu, rc.qn + n_mine > kQueueCap)) {
       drain_queue(rc, k);
@@ -1164,9 +1166,10 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     uint32_t a16 = cur0, a4 = ccur0;
 #pragma unroll
     for (int T = 0; T < 16; ++T) {
-      // bit = 0 or 2^T; next address = address + 16 (4) * [bit set] as ONE multiply-add on the FMA pipe
-      // (mad.hi with 2^(36-T) for T >= 5: bit * 2^(36-T) >> 32 = 16; mad.lo with 16 >> T below), leaving the compare/logic pipe to the screening
-      const uint32_t bit = mine & (1u << T);
+      // bit = 0 or 2^B; next address = address + 16 (4) * [bit set] as ONE multiply-add on the FMA pipe
+      // (mad.hi with 2^(36-B) for B >= 5: bit * 2^(36-B) >> 32 = 16; mad.lo with 16 >> B below), leaving the compare/logic pipe to the screening
+      const int B = 15 - T;  // bit position of leaf T
+      const uint32_t bit = mine & (1u << B);
       uint32_t n16, n4;
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
@@ -1176,14 +1179,14 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
           ::"r"(a16), "r"(a4), "r"(bit), "r"(v[4 * T]), "r"(v[4 * T + 1]), "r"(v[4 * T + 2]), "r"(v[4 * T + 3]),
             "r"(c0 + (uint32_t)(4 * T))
           : "memory");
-      if (T >= 5)
-        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(1u << ((36 - T) & 31)), "r"(a16));
+      if (B >= 5)
+        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(1u << ((36 - B) & 31)), "r"(a16));
       else
-        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(16u >> T), "r"(a16));
-      if (T >= 3)
-        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(1u << ((34 - T) & 31)), "r"(a4));
+        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(16u >> B), "r"(a16));
+      if (B >= 3)
+        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(1u << ((34 - B) & 31)), "r"(a4));
       else
-        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(4u >> T), "r"(a4));
+        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(4u >> B), "r"(a4));
       a16 = n16;
       a4 = n4;
     }
