@@ -12,7 +12,7 @@ namespace {
 constexpr int kExactThreads = 256;
 constexpr int kQT = 4;        // queries per block
 constexpr int kCap = 1024;    // candidate slots per query
-constexpr int kDimChunk = 32; // dims staged per pass
+constexpr int kDimChunk = 32; // dims staged per pass (a multiple of 8: see the partial sums)
 
 struct ExactSmem {
   unsigned long long keys[kQT][kCap];  // bit pattern of the (non-negative) float64 d2
@@ -101,9 +101,15 @@ knn_exact_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, 
           __syncthreads();
         }
       }
-      double acc[kQT];
+      // Eight partial sums per query, element c into sum c % 8, combined as ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7)):
+      // the summation order of the re-rank kernels of the tensor-core path (knn_mma.cu: four lanes per candidate
+      // row, element pairs interleaved, two shuffle steps).  A row that fails its certificate there and is
+      // recomputed here gets bit-identical distances, so the results do not depend on which rows fell back.
+      double acc8[kQT][8];
 #pragma unroll
-      for (int q = 0; q < kQT; ++q) acc[q] = 0.0;
+      for (int q = 0; q < kQT; ++q)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc8[q][u] = 0.0;
       const int64_t j = base + tid;
       for (int c0 = 0; c0 < d; c0 += kDimChunk) {
         const int cw = min(kDimChunk, d - c0);
@@ -115,15 +121,24 @@ knn_exact_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, 
           tile[rr * (kDimChunk + 1) + cc] = jj < n_r ? R[jj * ldr + c0 + cc] : (T)0;
         }
         __syncthreads();
-        for (int cc = 0; cc < cw; ++cc) {
-          const double rv = (double)tile[tid * (kDimChunk + 1) + cc];
+        for (int cc8 = 0; cc8 < cw; cc8 += 8) {  // c0 and cc8 are multiples of 8: (c0 + cc8 + u) % 8 == u
 #pragma unroll
-          for (int q = 0; q < kQT; ++q) {
-            const double df = rv - qs[q * d + c0 + cc];
-            acc[q] = fma(df, df, acc[q]);
+          for (int u = 0; u < 8; ++u) {
+            if (cc8 + u < cw) {
+              const double rv = (double)tile[tid * (kDimChunk + 1) + cc8 + u];
+#pragma unroll
+              for (int q = 0; q < kQT; ++q) {
+                const double df = rv - qs[q * d + c0 + cc8 + u];
+                acc8[q][u] = fma(df, df, acc8[q][u]);
+              }
+            }
           }
         }
       }
+      double acc[kQT];
+#pragma unroll
+      for (int q = 0; q < kQT; ++q)
+        acc[q] = ((acc8[q][0] + acc8[q][1]) + (acc8[q][2] + acc8[q][3])) + ((acc8[q][4] + acc8[q][5]) + (acc8[q][6] + acc8[q][7]));
       if (j < n_r) {
 #pragma unroll
         for (int q = 0; q < kQT; ++q) {
