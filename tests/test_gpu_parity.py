@@ -216,6 +216,35 @@ def test_pruned_search_is_exact(torch_cuda, name):
     assert int(st[0]) <= 0.01 * q.shape[0] + 1, f"{int(st[0])} rows needed the exact fallback"
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_search_randomised_shapes(torch_cuda, seed):
+    """Randomised d (2..53), k (1..40), sizes, dtypes and data kinds (mixtures, uniform, integer lattices full of exact
+    ties, duplicated rows, a 3-d manifold, offset + constant column; tools/stress_search.py): the tensor-core path
+    must return the float64 SIMT kernel's distances bit for bit and its neighbours outside exact ties."""
+    torch = torch_cuda
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import stress_search
+    from cellmapper_b200 import _lib, device
+
+    rng = np.random.default_rng(seed)
+    kinds = ["mixture", "uniform", "lattice", "duplicates", "manifold", "offset_const"]
+    for case in range(12):
+        kind = kinds[case % len(kinds)]
+        d, k = int(rng.integers(2, 54)), int(rng.integers(1, 41))
+        n_r = int(rng.integers(16_384, 80_000))
+        n_q = int(rng.integers(64, 3_000))
+        dt = np.float32 if rng.random() < 0.7 else np.float64
+        q, r = stress_search.make(kind, rng, n_q, n_r, d)
+        qd, rd = dev(torch, np.ascontiguousarray(q.astype(dt))), dev(torch, np.ascontiguousarray(r.astype(dt)))
+        dd, ii = device.knn_search(qd, rd, k)
+        dx, ix = device.knn_search(qd, rd, k, algo=_lib.KNN_EXACT_F64)
+        dd, ii, dx, ix = (t.cpu().numpy() for t in (dd, ii, dx, ix))
+        where = f"{kind} n_q={n_q} n_r={n_r} d={d} k={k} {np.dtype(dt).name}"
+        np.testing.assert_array_equal(dd, dx, err_msg=where)
+        assert neighbours_match(ii, dd, ix, dx, rel=0.0) == 0, where
+
+
 def test_search_errors(torch_cuda):
     torch = torch_cuda
     from cellmapper_b200 import device
