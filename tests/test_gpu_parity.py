@@ -464,6 +464,31 @@ def test_cellmapper_map_matches_reference(torch_cuda, name, kernel):
         np.testing.assert_allclose(ref.obs["presence_score"].to_numpy(), g["presence_score"], atol=1e-9)
 
 
+def test_cellmapper_upload_hook(torch_cuda):
+    """The reference-side upload hook of the multi-GPU mode (dist.upload_replicated; a plain upload in a single
+    process) sees the embedding, the label codes and the obsm payload, and changes no result."""
+    from cellmapper_b200 import CellMapper
+    from cellmapper_b200 import dist as cmd
+
+    g = load_golden(Q2R[0])
+    seen = []
+
+    def hook(a):
+        seen.append(tuple(np.asarray(a).shape))
+        return cmd.upload_replicated(a, min_bytes=0)
+
+    q1, r1 = make_adatas(g)
+    q2, r2 = make_adatas(g)
+    kw = dict(use_rep="X_joint", obs_keys="celltype", obsm_keys="X_umap", n_neighbors=int(g["k"]), only_yx=True)
+    CellMapper(q1, r1).map(**kw)
+    CellMapper(q2, r2, upload_replicated=hook).map(**kw)
+    n_r = r1.n_obs
+    assert (n_r,) in seen and sum(1 for sh in seen if len(sh) == 2 and sh[0] == n_r) >= 2, seen
+    np.testing.assert_array_equal(q1.obs["celltype_pred"].to_numpy().astype(str), q2.obs["celltype_pred"].to_numpy().astype(str))
+    np.testing.assert_array_equal(q1.obs["celltype_conf"].to_numpy(), q2.obs["celltype_conf"].to_numpy())
+    np.testing.assert_array_equal(q1.obsm["X_umap_pred"], q2.obsm["X_umap_pred"])
+
+
 def test_cellmapper_errors_mirror_reference(torch_cuda):
     from cellmapper_b200 import CellMapper
 
