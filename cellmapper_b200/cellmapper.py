@@ -290,10 +290,6 @@ class CellMapper:
             if not x.has_sorted_indices:
                 x = x.sorted_indices()
             n_genes = x.shape[1]
-            if n_genes > _lib.SPGEMM_MAX_COLS:
-                raise NotImplementedError(
-                    f"sparse layers with more than {_lib.SPGEMM_MAX_COLS} columns are not supported yet (got {n_genes})"
-                )
             if x.dtype != np.float32:
                 logger.warning("sparse layer of dtype %s is transferred in float32 by method='b200'.", x.dtype)
             oip, ocols, ovals = device.spgemm(

@@ -173,8 +173,12 @@ template <bool kFill>
 __global__ void __launch_bounds__(kSpgemmThreads)
 spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_cols, const float* __restrict__ m_vals,
               int64_t n_q, const int64_t* __restrict__ x_indptr, const int32_t* __restrict__ x_cols,
-              const float* __restrict__ x_vals, int32_t n_genes, int32_t* __restrict__ out_row_nnz,
-              const int64_t* __restrict__ out_indptr, int32_t* __restrict__ out_cols, float* __restrict__ out_vals) {
+              const float* __restrict__ x_vals, int32_t g_lo, int32_t n_genes, int32_t* __restrict__ out_row_nnz,
+              int accumulate_count, const int64_t* __restrict__ out_indptr, int64_t* __restrict__ row_off,
+              int32_t* __restrict__ out_cols, float* __restrict__ out_vals) {
+  // One pass covers the gene window [g_lo, g_lo + n_genes): entries outside it are skipped.  Matrices with more
+  // columns than the shared-memory accumulator holds are processed window by window (spgemm_launch); `row_off`
+  // then carries every row's write position from one window to the next.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_words = (n_genes + 31) >> 5;
   uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw);
@@ -217,7 +221,7 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
 #pragma unroll
           for (int u = 0; u < kPer; ++u) {
             const int64_t p = xs + threadIdx.x + (int64_t)u * kSpgemmThreads;
-            gc[j][u] = p < xe ? x_cols[p] : -1;
+            gc[j][u] = p < xe ? x_cols[p] - g_lo : -1;
             gv[j][u] = (kFill && p < xe) ? x_vals[p] : 0.f;
           }
         }
@@ -228,15 +232,17 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
 #pragma unroll
             for (int u = 0; u < kPer; ++u) {
               const int32_t g = gc[j][u];
-              if (g >= 0) {
+              if ((uint32_t)g < (uint32_t)n_genes) {
                 atomicOr(&bitmap[g >> 5], 1u << (g & 31));
                 if (kFill) acc[g] = __fadd_rn(acc[g], __fmul_rn(w, gv[j][u]));  // columns are unique inside one X row
               }
             }
             for (int64_t p = s_xs[g0 + j] + threadIdx.x + (int64_t)kPer * kSpgemmThreads; p < s_xe[g0 + j]; p += kSpgemmThreads) {
-              const int32_t g = x_cols[p];
-              atomicOr(&bitmap[g >> 5], 1u << (g & 31));
-              if (kFill) acc[g] = __fadd_rn(acc[g], __fmul_rn(w, x_vals[p]));
+              const int32_t g = x_cols[p] - g_lo;
+              if ((uint32_t)g < (uint32_t)n_genes) {
+                atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+                if (kFill) acc[g] = __fadd_rn(acc[g], __fmul_rn(w, x_vals[p]));
+              }
             }
             if (kFill) __syncthreads();  // the next neighbour may touch the same genes from other threads
           }
@@ -255,13 +261,13 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
       const int ex = block_exclusive_scan(pc, warp_sums, &total_sh);
       total = total_sh;
       if (kFill && bits) {
-        int64_t o = out_indptr[row] + base_rank + ex;
+        int64_t o = (row_off ? row_off[row] : out_indptr[row]) + base_rank + ex;
         uint32_t b = bits;
         while (b) {
           const int bit = __ffs(b) - 1;
           b &= b - 1;
           const int g = (w << 5) + bit;
-          out_cols[o] = g;
+          out_cols[o] = g + g_lo;
           out_vals[o] = acc[g];
           acc[g] = 0.f;
           ++o;
@@ -271,8 +277,9 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
       base_rank += total;
       __syncthreads();
     }
-    if (!kFill && threadIdx.x == 0) out_row_nnz[row] = base_rank;
-    __syncthreads();
+    if (!kFill && threadIdx.x == 0) out_row_nnz[row] = base_rank + (accumulate_count ? out_row_nnz[row] : 0);
+    __syncthreads();  // (also: every thread has read row_off[row] before it moves)
+    if (kFill && row_off && threadIdx.x == 0) row_off[row] += base_rank;
   }
 }
 
@@ -324,30 +331,49 @@ extern "C" int cm_spmm_csr_dense(const int32_t* indptr, const int32_t* cols, con
   return CM_OK;
 }
 
+__global__ void copy_i64_kernel(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
                          const int64_t* x_indptr, const int32_t* x_cols, const float* x_vals, int32_t n_genes,
                          int32_t* out_row_nnz, const int64_t* out_indptr, int32_t* out_cols, float* out_vals,
                          cudaStream_t st) {
-  CM_REQUIRE(n_q >= 0 && n_genes >= 1 && n_genes <= CM_SPGEMM_MAX_COLS, "n_genes = %d outside 1..%d", n_genes,
-             CM_SPGEMM_MAX_COLS);
+  CM_REQUIRE(n_q >= 0 && n_genes >= 1, "n_genes = %d must be positive", n_genes);
   if (n_q == 0) return CM_OK;
-  const int n_words = (n_genes + 31) >> 5;
-  size_t smem = (size_t)n_words * 4 + (fill ? (size_t)n_genes * 4 : 0);
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
-  int64_t want = (int64_t)kNumSMs * per_sm;
-  int grid = (int)(n_q < want ? n_q : want);
-  if (fill) {
-    CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spgemm_kernel<true><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals,
-                                                           n_genes, out_row_nnz, out_indptr, out_cols, out_vals);
-  } else {
-    CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spgemm_kernel<false><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals,
-                                                            n_genes, out_row_nnz, out_indptr, out_cols, out_vals);
+  // gene windows of at most CM_SPGEMM_MAX_COLS columns (the dense accumulator of a CTA); one window in the usual case
+  const int n_win = (n_genes + CM_SPGEMM_MAX_COLS - 1) / CM_SPGEMM_MAX_COLS;
+  int win = (n_genes + n_win - 1) / n_win;
+  win = (win + 31) & ~31;
+  int64_t* row_off = nullptr;
+  if (fill && n_win > 1) {  // running write position of every row, carried from window to window
+    CM_CUDA_CHECK(cudaMallocAsync((void**)&row_off, (size_t)n_q * sizeof(int64_t), st));
+    copy_i64_kernel<<<(unsigned)(n_q < 65536 * 256 ? (n_q + 255) / 256 : 65536), 256, 0, st>>>(out_indptr, row_off, n_q);
+    CM_LAUNCH_CHECK("copy_i64_kernel");
   }
-  CM_LAUNCH_CHECK("spgemm_kernel");
+  for (int w = 0; w < n_win; ++w) {
+    const int32_t g_lo = w * win;
+    const int32_t g_n = n_genes - g_lo < win ? n_genes - g_lo : win;
+    if (g_n <= 0) break;
+    const int n_words = (g_n + 31) >> 5;
+    size_t smem = (size_t)n_words * 4 + (fill ? (size_t)g_n * 4 : 0);
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int64_t want = (int64_t)kNumSMs * per_sm;
+    int grid = (int)(n_q < want ? n_q : want);
+    if (fill) {
+      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spgemm_kernel<true><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n,
+                                                             out_row_nnz, 0, out_indptr, row_off, out_cols, out_vals);
+    } else {
+      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spgemm_kernel<false><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n,
+                                                              out_row_nnz, w > 0, out_indptr, row_off, out_cols, out_vals);
+    }
+    CM_LAUNCH_CHECK("spgemm_kernel");
+  }
+  if (row_off) CM_CUDA_CHECK(cudaFreeAsync(row_off, st));
   return CM_OK;
 }
 

@@ -464,6 +464,37 @@ def test_cellmapper_map_matches_reference(torch_cuda, name, kernel):
         np.testing.assert_allclose(ref.obs["presence_score"].to_numpy(), g["presence_score"], atol=1e-9)
 
 
+def test_spgemm_wide_layer(torch_cuda):
+    """Sparse layers with more columns than one CTA's accumulator (CM_SPGEMM_MAX_COLS = 49 152; e.g. ATAC peaks)
+    are processed in gene windows: same result as scipy's M @ X, bit for bit, rows sorted."""
+    torch = torch_cuda
+    import scipy.sparse as sp
+    from cellmapper_b200 import device
+
+    rng = np.random.default_rng(3)
+    n_q, n_r, k = 300, 700, 12
+    for n_genes in (49_152, 49_153, 120_001):
+        cols = np.stack([rng.choice(n_r, k, replace=False) for _ in range(n_q)])
+        cols.sort(axis=1)
+        w = rng.random((n_q, k)).astype(np.float32)
+        w /= w.sum(1, keepdims=True)
+        m = sp.csr_matrix((w.ravel(), cols.ravel().astype(np.int32), np.arange(0, n_q * k + 1, k, dtype=np.int32)), shape=(n_q, n_r))
+        x = sp.random(n_r, n_genes, density=400 / n_genes, format="csr", dtype=np.float32, random_state=int(n_genes))
+        x = x.tolil()
+        x[0, n_genes - 1] = 2.5  # the last column of the last window is present
+        x = x.tocsr()
+        x.sort_indices()
+        ref = (m @ x).tocsr()
+        ref.sort_indices()
+        oip, ocols, ovals = device.spgemm(
+            dev(torch, m.indptr, torch.int32), dev(torch, m.indices, torch.int32), dev(torch, m.data, torch.float32),
+            dev(torch, x.indptr), dev(torch, x.indices), dev(torch, x.data), n_genes,
+        )
+        np.testing.assert_array_equal(oip.cpu().numpy(), ref.indptr)
+        np.testing.assert_array_equal(ocols.cpu().numpy(), ref.indices)
+        np.testing.assert_array_equal(ovals.cpu().numpy(), ref.data)
+
+
 def test_cellmapper_upload_hook(torch_cuda):
     """The reference-side upload hook of the multi-GPU mode (dist.upload_replicated; a plain upload in a single
     process) sees the embedding, the label codes and the obsm payload, and changes no result."""
