@@ -6,7 +6,8 @@
   ONE statistic over all edges (knn.py:196,206): an all-reduce of 3 float64 per pass.
 * reference-sharded (reference does not fit / presence score over a 10M-cell atlas): every rank
   searches its block of the reference for ALL queries, the per-rank top-k lists are all-gathered
-  and merged (``cm_knn_merge_topk``).
+  and merged (``cm_knn_merge_topk``).  Expression is transferred as partial products against each
+  rank's block of X, all-gathered and summed per query block (``spgemm_reference_sharded``).
 
 The compute callables are injected so that the collective plumbing can be exercised on CPU with
 world_size 2 over gloo.
@@ -29,6 +30,8 @@ __all__ = [
     "knn_reference_sharded",
     "gather_rows",
     "upload_replicated",
+    "csr_column_block",
+    "spgemm_reference_sharded",
 ]
 
 
@@ -162,3 +165,85 @@ def upload_replicated(a, device: torch.device | None = None, min_bytes: int = 8 
     full = torch.empty((ws * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
     dist.all_gather_into_tensor(full, block)
     return full[:n]
+
+
+def csr_column_block(indptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, lo: int, hi: int):
+    """Columns [lo, hi) of a CSR matrix, renumbered from 0 (row order and the order inside rows are kept).
+    Returns (indptr int32, cols int32, vals)."""
+    n = indptr.numel() - 1
+    keep = (cols >= lo) & (cols < hi)
+    csum = torch.zeros(cols.numel() + 1, dtype=torch.int64, device=cols.device)
+    torch.cumsum(keep.to(torch.int64), 0, out=csum[1:])
+    new_indptr = csum[indptr.to(torch.int64)].to(torch.int32)
+    assert new_indptr.numel() == n + 1
+    return new_indptr, (cols[keep] - lo).to(torch.int32), vals[keep]
+
+
+def spgemm_reference_sharded(
+    m_indptr: torch.Tensor,
+    m_cols: torch.Tensor,
+    m_vals: torch.Tensor,
+    x_indptr: torch.Tensor,
+    x_cols: torch.Tensor,
+    x_vals: torch.Tensor,
+    r_lo: int,
+    r_hi: int,
+    n_genes: int,
+    spgemm: Callable,
+    q_block: tuple[int, int] | None = None,
+):
+    """``M @ X`` (cellmapper.py:372-373) when the rows of the expression matrix X are sharded over the ranks
+    like the reference: this rank holds X[r_lo:r_hi] as CSR (``x_*``) and the whole row-normalised
+    mapping matrix M (n_q x n_r, CSR).
+
+    1. partial product of M's columns [r_lo, r_hi) with the local rows of X (``spgemm``: the CSR x CSR
+       kernel, ``cellmapper_b200.device.spgemm``);
+    2. all-gather of the partial CSR matrices (one padded buffer per array);
+    3. every rank sums the partials of ITS block of query rows (``q_block``, default: the balanced block of
+       this rank) with the same kernel: the stacked partials times a matrix of ones, so the terms are
+       added in rank order, deterministically.
+
+    Returns the CSR rows [q_lo, q_hi) of the result (indptr int64, cols int32, vals float32) and (q_lo, q_hi).
+    The value of an entry is sum over ranks of (sum over the rank's reference rows, ascending): equal to
+    scipy's single pass up to float32 re-association (1e-6 relative)."""
+    rank, ws = world()
+    n_q = m_indptr.numel() - 1
+    q_lo, q_hi = q_block if q_block is not None else shard_bounds(n_q, ws, rank)
+    lip, lcols, lvals = csr_column_block(m_indptr, m_cols, m_vals, r_lo, r_hi)
+    pip, pcols, pvals = spgemm(lip, lcols, lvals, x_indptr, x_cols, x_vals, n_genes)
+    pip = pip.to(torch.int64).contiguous()
+    if ws == 1:
+        lo_e, hi_e = int(pip[q_lo]), int(pip[q_hi])
+        return (pip[q_lo : q_hi + 1] - pip[q_lo]), pcols[lo_e:hi_e], pvals[lo_e:hi_e], (q_lo, q_hi)
+    dev = pip.device
+    nnz = torch.tensor([pcols.numel()], dtype=torch.int64, device=dev)
+    all_nnz = torch.empty(ws, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_nnz, nnz)
+    all_nnz = [int(v) for v in all_nnz.tolist()]
+    m = max(max(all_nnz), 1)
+
+    def gather(t: torch.Tensor, length: int) -> torch.Tensor:
+        buf = torch.zeros(length, dtype=t.dtype, device=dev)
+        buf[: t.numel()] = t
+        out = torch.empty(ws * length, dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, buf)
+        return out.view(ws, length)
+
+    g_ip, g_cols, g_vals = gather(pip, n_q + 1), gather(pcols.to(torch.int32), m), gather(pvals.to(torch.float32), m)
+    # the stacked partials restricted to this rank's query block: rows (rank-major) q_lo..q_hi of every partial
+    nb = q_hi - q_lo
+    seg_lo = [int(g_ip[r, q_lo]) for r in range(ws)]
+    seg_hi = [int(g_ip[r, q_hi]) for r in range(ws)]
+    s_cols = torch.cat([g_cols[r, seg_lo[r] : seg_hi[r]] for r in range(ws)])
+    s_vals = torch.cat([g_vals[r, seg_lo[r] : seg_hi[r]] for r in range(ws)])
+    offs, parts = 0, []
+    for r in range(ws):
+        parts.append(g_ip[r, q_lo:q_hi] - seg_lo[r] + offs)
+        offs += seg_hi[r] - seg_lo[r]
+    s_ip = torch.cat(parts + [torch.tensor([offs], dtype=torch.int64, device=dev)])
+    # ones matrix: row i sums the stacked rows i, nb + i, 2 nb + i, ... (ascending = rank order)
+    o_ip = torch.arange(0, nb * ws + 1, ws, dtype=torch.int32, device=dev)
+    o_cols = (torch.arange(nb, dtype=torch.int32, device=dev)[:, None] + nb * torch.arange(ws, dtype=torch.int32, device=dev)[None, :]).reshape(-1)
+    o_vals = torch.ones(nb * ws, dtype=torch.float32, device=dev)
+    oip, ocols, ovals = spgemm(o_ip, o_cols.contiguous(), o_vals, s_ip, s_cols, s_vals, n_genes)
+    return oip, ocols, ovals, (q_lo, q_hi)

@@ -69,6 +69,42 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         return torch.from_numpy(key[rows, order]), torch.from_numpy(ci2[rows, order])
 
     md, mi = cmd.reference_sharded_search(torch.from_numpy(xq), torch.from_numpy(xr[rlo:rhi]), rlo, k, search, merge)
+    # ---- reference-sharded expression transfer: partial CSR x CSR products, all-gather, per-block sum
+    import scipy.sparse as sp
+
+    def spgemm_cpu(ip, cc, vv, xip, xcc, xvv, n_genes):
+        a = sp.csr_matrix((vv.numpy(), cc.numpy(), ip.numpy()), shape=(ip.numel() - 1, xip.numel() - 1))
+        b = sp.csr_matrix((xvv.numpy(), xcc.numpy(), xip.numpy()), shape=(xip.numel() - 1, n_genes))
+        c = (a @ b).tocsr()
+        c.sort_indices()
+        return torch.from_numpy(c.indptr.astype(np.int64)), torch.from_numpy(c.indices.astype(np.int32)), torch.from_numpy(c.data.astype(np.float32))
+
+    rng = np.random.default_rng(7)
+    n_genes = 97
+    xmat = sp.random(xr.shape[0], n_genes, density=0.08, format="csr", dtype=np.float32, random_state=5)
+    xmat.sort_indices()
+    d_all, i_all = orc.search_sklearn(xr, xq, k)
+    wts = np.exp(-(d_all**2) / (2 * d_all.mean() ** 2))
+    wts = (wts / wts.sum(1, keepdims=True)).astype(np.float32)
+    order = np.argsort(i_all, axis=1)
+    mm = sp.csr_matrix(
+        (np.take_along_axis(wts, order, 1).ravel(), np.take_along_axis(i_all, order, 1).ravel().astype(np.int32),
+         np.arange(0, xq.shape[0] * k + 1, k, dtype=np.int32)), shape=(xq.shape[0], xr.shape[0]))
+    xs = xmat[rlo:rhi]
+    oip, ocols, ovals, (qlo_b, qhi_b) = cmd.spgemm_reference_sharded(
+        torch.from_numpy(mm.indptr), torch.from_numpy(mm.indices), torch.from_numpy(mm.data),
+        torch.from_numpy(xs.indptr.astype(np.int64)), torch.from_numpy(xs.indices), torch.from_numpy(xs.data),
+        rlo, rhi, n_genes, spgemm_cpu)
+    full = (mm @ xmat).tocsr()
+    full.sort_indices()
+    blk = full[qlo_b:qhi_b]
+    assert (qlo_b, qhi_b) == cmd.shard_bounds(xq.shape[0], w, r)
+    assert np.array_equal(oip.numpy(), blk.indptr) and np.array_equal(ocols.numpy(), blk.indices)
+    np.testing.assert_allclose(ovals.numpy(), blk.data, rtol=2e-6)
+    sub_ip, sub_c, sub_v = cmd.csr_column_block(torch.from_numpy(mm.indptr), torch.from_numpy(mm.indices), torch.from_numpy(mm.data), rlo, rhi)
+    ref_sub = mm[:, rlo:rhi].tocsr()
+    assert np.array_equal(sub_ip.numpy(), ref_sub.indptr) and np.array_equal(sub_c.numpy(), ref_sub.indices) and np.array_equal(sub_v.numpy(), ref_sub.data)
+
     # ---- replicated reference arrays: every rank uploads its row block, all-gather (odd row count, 1-D and 2-D)
     up2 = cmd.upload_replicated(xr, device=torch.device("cpu"), min_bytes=0)
     up1 = cmd.upload_replicated(cr.astype(np.int32), device=torch.device("cpu"), min_bytes=0)

@@ -70,6 +70,32 @@ def sharded():
 sharded()
 (md, mi, score), ms = sync_time(sharded)
 out["reference_sharded_search_presence_ms"] = ms
+# ---------------- 3. reference-sharded expression transfer (config 4 scaled): partial CSR x CSR + all-gather + block sum ----
+n_q4, n_r4, n_genes = 6_000, 40_000, 30_000
+xr4, cr4 = synth.mixture_embedding(n_r4, centres, seed=5)
+xq4, _ = synth.mixture_embedding(n_q4, centres, seed=6)
+import scipy.sparse as sp
+expr = sp.random(n_r4, n_genes, density=600 / n_genes, format="csr", dtype=np.float32, random_state=7)
+expr.sort_indices()
+q4 = torch.from_numpy(xq4).to(dev); r4 = torch.from_numpy(xr4).to(dev)
+d4, i4 = device.knn_search(q4, r4, k, dist_mode=_lib.DIST_SKLEARN_F32)
+m_ip, m_cols, m_vals = NeighborsResults(d4, i4, n_targets=n_r4).connectivities_device("scarches", normalize=True)
+rlo4, rhi4 = cmd.shard_bounds(n_r4, world, rank)
+xs = expr[rlo4:rhi4]
+xs_ip, xs_c, xs_v = (torch.from_numpy(a).to(dev) for a in (xs.indptr.astype(np.int64), xs.indices.astype(np.int32), xs.data.astype(np.float32)))
+def sharded_expr():
+    return cmd.spgemm_reference_sharded(m_ip, m_cols, m_vals.float(), xs_ip, xs_c, xs_v, rlo4, rhi4, n_genes, device.spgemm)
+sharded_expr()
+(oip4, oc4, ov4, (qlo4, qhi4)), ms = sync_time(sharded_expr)
+out["reference_sharded_expression_ms"] = ms
+x_ip, x_c, x_v = (torch.from_numpy(a).to(dev) for a in (expr.indptr.astype(np.int64), expr.indices.astype(np.int32), expr.data.astype(np.float32)))
+fip, fc, fv = device.spgemm(m_ip, m_cols, m_vals.float(), x_ip, x_c, x_v, n_genes)
+lo_e, hi_e = int(fip[qlo4]), int(fip[qhi4])
+ok4 = bool(torch.equal(oip4, fip[qlo4:qhi4 + 1] - fip[qlo4]) and torch.equal(oc4, fc[lo_e:hi_e]) and torch.allclose(ov4, fv[lo_e:hi_e], rtol=2e-6, atol=0))
+flag = torch.tensor([1 if ok4 else 0], device=dev)
+if world > 1: tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
+out["reference_sharded_expression_equal_1e-6"] = bool(flag.item())
+
 if rank == 0:
     r_all = torch.from_numpy(xr5).to(dev)
     gd, gi = device.knn_search(q_d, r_all, k, dist_mode=_lib.DIST_SKLEARN_F32)
