@@ -259,7 +259,9 @@ def b200_arm(args):
                 marks.append(e)
 
         mark()
-        dd, ii, st_search = device.knn_search(xq_d, xr_d, K, dist_mode=mode, return_stats=True)
+        # N > 1: the reference side of the coarse cells is computed block by block on the ranks and all-gathered (NCCL)
+        ref_cells = cmd.assign_reference_sharded(xr_d, K) if world > 1 else None
+        dd, ii, st_search = device.knn_search(xq_d, xr_d, K, dist_mode=mode, return_stats=True, ref_cells=ref_cells)
         search_stats.append(st_search)
         mark()
         st = device.edge_stats(dd, ii, allreduce=allreduce, need_std=False)
@@ -326,7 +328,8 @@ def b200_arm(args):
 
     def e2e_step():
         qry_ad = AnnData(X=csr_matrix((n_q, 1), dtype=np.float32), obs=pd.DataFrame(index=qry_index), obsm={"X_joint": xq_p})
-        cm = CellMapper(qry_ad, ref_ad, allreduce=allreduce, upload_replicated=cmd.upload_replicated if world > 1 else None)
+        cm = CellMapper(qry_ad, ref_ad, allreduce=allreduce, upload_replicated=cmd.upload_replicated if world > 1 else None,
+                        reference_cells=cmd.assign_reference_sharded if world > 1 else None)
         cm.map(use_rep="X_joint", obs_keys="celltype", obsm_keys="X_umap", n_neighbors=K, only_yx=True, mapping_method="gaussian")
         return qry_ad
 

@@ -33,6 +33,14 @@ SIGNATURES = {
         c_int,
         [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P, _P],
     ),
+    "cm_knn_assign_reference": (
+        c_int,
+        [_P, c_int64, c_int64, c_int, c_int, c_int, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P],
+    ),
+    "cm_knn_search_cells": (
+        c_int,
+        [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P, _P, _P, _P],
+    ),
     "cm_knn_merge_topk": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
     "cm_edge_stats": (c_int, [_P, _P, c_int64, _P, _P, _P, c_size_t, _P]),
     "cm_edge_kernel_to_csr": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P]),

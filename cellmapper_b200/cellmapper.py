@@ -82,15 +82,18 @@ class _DeviceCSR:
 class CellMapper:
     """Mapping of labels, embeddings, and expression values between reference and query datasets."""
 
-    def __init__(self, query: AnnData, reference: AnnData | None = None, *, allreduce=None, upload_replicated=None) -> None:
+    def __init__(self, query: AnnData, reference: AnnData | None = None, *, allreduce=None, upload_replicated=None, reference_cells=None) -> None:
         """``allreduce`` (keyword-only, not in the reference): in-place SUM over ranks for the kernel
         bandwidth statistics when the query cells are sharded over several GPUs
         (``cellmapper_b200.dist.allreduce_sum``); ``None`` for a single process.
         ``upload_replicated`` (keyword-only): callable(host array) -> device tensor used for the
         reference-side arrays every rank holds in full (``cellmapper_b200.dist.upload_replicated``:
-        each rank uploads 1/world of the rows, NCCL all-gather); ``None``: plain uploads."""
+        each rank uploads 1/world of the rows, NCCL all-gather); ``None``: plain uploads.
+        ``reference_cells`` (keyword-only): callable(reference tensor, k) -> the reference side of the search's
+        coarse cells (``cellmapper_b200.dist.assign_reference_sharded``: computed block by block on the ranks)."""
         self._allreduce = allreduce
         self._upload_ref = upload_replicated if (upload_replicated is not None and reference is not None) else None
+        self._reference_cells = reference_cells if reference is not None else None
         self.query = query
         self.reference = reference if reference is not None else query  # cellmapper.py:37-38
         self._is_self_mapping = reference is None
@@ -190,7 +193,8 @@ class CellMapper:
         yrep = np.ascontiguousarray(np.asarray(yrep)[:, :n_comps])
         # cellmapper.py:250 always passes both arrays; in self-mapping they are the same object here so
         # the embedding is uploaded once
-        self.knn = Neighbors(xrep, xrep if self._is_self_mapping else yrep, upload_reference=self._upload_ref)
+        self.knn = Neighbors(xrep, xrep if self._is_self_mapping else yrep, upload_reference=self._upload_ref,
+                             reference_cells=self._reference_cells)
         self.knn.compute_neighbors(n_neighbors=n_neighbors, method=method, metric=metric, only_yx=only_yx)
         self._mapping = None
 

@@ -35,7 +35,10 @@ void set_error(const char* fmt, ...) {
 
 int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d, int dtype,
                    int k, int64_t r_off, int dist_mode, double* out_dist, int64_t* out_idx, void* workspace,
-                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st);
+                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st, const uint8_t* ref_cell, const uint32_t* ref_rad2);
+int knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dtype, int64_t row_lo, int64_t row_hi,
+                         uint8_t* out_cell, uint32_t* out_rad2, int* n_cells_out, void* workspace, size_t ws_bytes,
+                         cudaStream_t st);
 size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d);
 void set_probe_flags(int f);
 void set_probe_prof(long long* p);
@@ -87,10 +90,31 @@ extern "C" size_t cm_knn_workspace_bytes(int64_t n_q, int64_t n_r, int d, int k,
   return 256;
 }
 
+extern "C" int cm_knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dtype, int k, int64_t row_lo,
+                                       int64_t row_hi, uint8_t* out_cell, uint32_t* out_rad2_bits, int* n_cells_out,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  CM_REQUIRE(R && out_cell && out_rad2_bits && n_cells_out && workspace, "null pointer argument");
+  CM_REQUIRE(n_r >= 1 && d >= 1 && ldr >= d, "bad shapes n_r=%lld d=%d", (long long)n_r, d);
+  CM_REQUIRE(dtype == CM_F32 || dtype == CM_F64, "bad dtype code %d", dtype);
+  CM_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= n_r, "bad row block [%lld, %lld)", (long long)row_lo, (long long)row_hi);
+  *n_cells_out = 0;
+  if (!(mma_supported(d, k) && n_r >= k)) return CM_OK;  // the float64 kernel has no cells
+  return knn_assign_reference(R, n_r, ldr, d, dtype, row_lo, row_hi, out_cell, out_rad2_bits, n_cells_out, workspace,
+                              workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int cm_knn_search(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d,
                              int dtype, int k, int64_t r_index_offset, int dist_mode, int algo, double* out_dist,
                              int64_t* out_idx, void* workspace, size_t workspace_bytes, int64_t* stats_out,
                              void* stream) {
+  return cm_knn_search_cells(Q, n_q, ldq, R, n_r, ldr, d, dtype, k, r_index_offset, dist_mode, algo, out_dist, out_idx,
+                             workspace, workspace_bytes, stats_out, nullptr, nullptr, stream);
+}
+
+extern "C" int cm_knn_search_cells(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d,
+                                   int dtype, int k, int64_t r_index_offset, int dist_mode, int algo, double* out_dist,
+                                   int64_t* out_idx, void* workspace, size_t workspace_bytes, int64_t* stats_out,
+                                   const uint8_t* ref_cell, const uint32_t* ref_rad2_bits, void* stream) {
   CM_REQUIRE(Q && R && out_dist && out_idx, "null pointer argument");
   CM_REQUIRE(n_q >= 0 && n_r >= 1 && d >= 1, "bad shapes n_q=%lld n_r=%lld d=%d", (long long)n_q, (long long)n_r, d);
   CM_REQUIRE(ldq >= d && ldr >= d, "leading dimensions smaller than d");
@@ -106,7 +130,7 @@ extern "C" int cm_knn_search(const void* Q, int64_t n_q, int64_t ldq, const void
   if (use_mma(n_r, d, k, algo)) {
     CM_REQUIRE(workspace, "workspace required (cm_knn_workspace_bytes)");
     return knn_search_mma(Q, n_q, ldq, R, n_r, ldr, d, dtype, k, r_index_offset, dist_mode, out_dist, out_idx,
-                          workspace, workspace_bytes, stats_out, st);
+                          workspace, workspace_bytes, stats_out, st, ref_cell, ref_rad2_bits);
   }
   if (stats_out) CM_CUDA_CHECK(cudaMemsetAsync(stats_out, 0, 4 * sizeof(int64_t), st));
   return launch_knn_exact(Q, n_q, ldq, R, n_r, ldr, d, dtype, k, nullptr, nullptr, n_q, r_index_offset, dist_mode,

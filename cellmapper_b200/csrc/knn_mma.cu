@@ -540,6 +540,17 @@ int launch_assign_any(const T* X, int64_t ld, int64_t n, int d, const double* mu
 }
 
 // exclusive scan of the two count arrays -> cell starts (+ a copy used as scatter cursor)
+// cell sizes from a cell assignment computed elsewhere (cm_knn_assign_reference on every rank's block of rows)
+__global__ void __launch_bounds__(kAssignThreads) cell_hist_kernel(const uint8_t* __restrict__ cell, int64_t n, int32_t* __restrict__ counts) {
+  __shared__ int hist[kMaxCells];
+  for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(&hist[cell[i]], 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[i], hist[i]);
+}
+
 __global__ void cell_scan_kernel(const int32_t* __restrict__ counts /*[2][kMaxCells]*/, int n_cells,
                                  int32_t* __restrict__ starts /*[2][kMaxCells+1]*/, int32_t* __restrict__ cursor /*[2][kMaxCells]*/) {
   if (threadIdx.x < 2) {
@@ -1997,7 +2008,7 @@ MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
 
 template <typename T>
 int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int64_t ldr, int d, const MmaPlan& pl,
-             const MmaBuffers& b, cudaStream_t st) {
+             const MmaBuffers& b, cudaStream_t st, const uint8_t* ref_cell = nullptr, const uint32_t* ref_rad2 = nullptr) {
   CM_CUDA_CHECK(cudaMemsetAsync(b.info, 0, sizeof(ScaleInfo), st));
   const int wpb = 8;
   int gq = (int)(ceil_div(n_q, wpb) < kNumSMs * 8 ? ceil_div(n_q, wpb) : kNumSMs * 8);
@@ -2019,7 +2030,18 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     CM_LAUNCH_CHECK("gather_pivots_kernel");
     order_pivots_kernel<<<1, kMaxCells, 0, st>>>(d, nc, b.piv_t, b.piv_norm);
     CM_LAUNCH_CHECK("order_pivots_kernel");
-    int rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.mu, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, b.cell_rad2, st);
+    int rc_a = 0;
+    if (ref_cell && ref_rad2) {
+      // the reference side was assigned by cm_knn_assign_reference (same pivots: they depend on R alone), block by
+      // block on the ranks of a multi-GPU run, and all-gathered: only the cell sizes are left to do
+      CM_CUDA_CHECK(cudaMemcpyAsync(b.r_cell, ref_cell, (size_t)n_r, cudaMemcpyDeviceToDevice, st));
+      CM_CUDA_CHECK(cudaMemcpyAsync(b.cell_rad2, ref_rad2, kMaxCells * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+      const int gh = (int)(ceil_div(n_r, kAssignThreads * 8) < kNumSMs * 4 ? ceil_div(n_r, kAssignThreads * 8) : kNumSMs * 4);
+      cell_hist_kernel<<<gh, kAssignThreads, 0, st>>>(b.r_cell, n_r, b.cell_counts);
+      CM_LAUNCH_CHECK("cell_hist_kernel");
+    } else {
+      rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.mu, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, b.cell_rad2, st);
+    }
     if (rc_a) return rc_a;
     rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.mu, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, nullptr, st);
     if (rc_a) return rc_a;
@@ -2133,9 +2155,50 @@ size_t mma_workspace_bytes(int64_t n_q, int64_t n_r, int d) {
 
 }  // namespace
 
+// Reference side of the coarse cells for rows [row_lo, row_hi): cell numbers and the cells' squared radii over
+// these rows (float bits; combine blocks with max).  The pivots depend on R alone, so every rank of a multi-GPU
+// run computes the same ones; 0 cells: the search of this reference does not use cells.
+int knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dtype, int64_t row_lo, int64_t row_hi,
+                         uint8_t* out_cell, uint32_t* out_rad2, int* n_cells_out, void* workspace, size_t ws_bytes,
+                         cudaStream_t st) {
+  const int nc = n_r >= kMinRefsForCells ? kMaxCells : 0;
+  *n_cells_out = nc;
+  if (nc == 0 || row_hi <= row_lo) return CM_OK;
+  Workspace ws(workspace, ws_bytes);
+  double* mu = ws.take<double>(64);
+  float* piv_t = ws.take<float>((size_t)kMaxCells * 64);
+  float* piv_norm = ws.take<float>(kMaxCells);
+  int32_t* counts = ws.take<int32_t>(kMaxCells);
+  if (!ws.ok()) {
+    set_error("workspace too small: need %zu bytes, got %zu", ws.off, ws_bytes);
+    return CM_ERR_WORKSPACE;
+  }
+  CM_CUDA_CHECK(cudaMemsetAsync(counts, 0, kMaxCells * sizeof(int32_t), st));
+  CM_CUDA_CHECK(cudaMemsetAsync(out_rad2, 0, kMaxCells * sizeof(uint32_t), st));
+  const int64_t n = row_hi - row_lo;
+  if (dtype == CM_F32) {
+    const float* r = (const float*)R;
+    centre_kernel<float><<<1, 64, 0, st>>>(r, ldr, n_r, d, mu);
+    CM_LAUNCH_CHECK("centre_kernel");
+    gather_pivots_kernel<float><<<ceil_div(nc, 128), 128, 0, st>>>(r, ldr, n_r / nc, d, nc, mu, piv_t, piv_norm);
+    CM_LAUNCH_CHECK("gather_pivots_kernel");
+    order_pivots_kernel<<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
+    CM_LAUNCH_CHECK("order_pivots_kernel");
+    return launch_assign_any<float>(r + row_lo * ldr, ldr, n, d, mu, piv_t, piv_norm, nc, out_cell, counts, out_rad2, st);
+  }
+  const double* r = (const double*)R;
+  centre_kernel<double><<<1, 64, 0, st>>>(r, ldr, n_r, d, mu);
+  CM_LAUNCH_CHECK("centre_kernel");
+  gather_pivots_kernel<double><<<ceil_div(nc, 128), 128, 0, st>>>(r, ldr, n_r / nc, d, nc, mu, piv_t, piv_norm);
+  CM_LAUNCH_CHECK("gather_pivots_kernel");
+  order_pivots_kernel<<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
+  CM_LAUNCH_CHECK("order_pivots_kernel");
+  return launch_assign_any<double>(r + row_lo * ldr, ldr, n, d, mu, piv_t, piv_norm, nc, out_cell, counts, out_rad2, st);
+}
+
 int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d, int dtype,
                    int k, int64_t r_off, int dist_mode, double* out_dist, int64_t* out_idx, void* workspace,
-                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st) {
+                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st, const uint8_t* ref_cell, const uint32_t* ref_rad2) {
   MmaPlan pl = make_plan(n_q, n_r, d);
   Workspace ws(workspace, ws_bytes);
   MmaBuffers b = carve(ws, pl, n_q, n_r);
@@ -2146,9 +2209,9 @@ int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64
   int rc;
   profile_mark(0, st);
   if (dtype == CM_F32) {
-    rc = run_prep<float>((const float*)Q, n_q, ldq, (const float*)R, n_r, ldr, d, pl, b, st);
+    rc = run_prep<float>((const float*)Q, n_q, ldq, (const float*)R, n_r, ldr, d, pl, b, st, ref_cell, ref_rad2);
   } else {
-    rc = run_prep<double>((const double*)Q, n_q, ldq, (const double*)R, n_r, ldr, d, pl, b, st);
+    rc = run_prep<double>((const double*)Q, n_q, ldq, (const double*)R, n_r, ldr, d, pl, b, st, ref_cell, ref_rad2);
   }
   if (rc) return rc;
   profile_mark(1, st);

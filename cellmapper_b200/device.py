@@ -100,9 +100,12 @@ def knn_search(
     dist_mode: int = _lib.DIST_SQRT_F64,
     algo: int = _lib.KNN_AUTO,
     return_stats: bool = False,
+    ref_cells: tuple[torch.Tensor, torch.Tensor] | None = None,
 ):
     """Exact Euclidean k-NN of every row of ``q`` in ``r`` (reference call site knn.py:428-440).
 
+    ``ref_cells``: optional (cell uint8 (n_r,), rad2 int32 (256,)) from ``knn_assign_reference`` over all rows of
+    ``r`` (assembled from the ranks' blocks in a multi-GPU run); the search then skips that part of its preparation.
     Returns (distances float64 (n_q,k), indices int64 (n_q,k)[, stats int64 (4,)]) on the device.
     """
     dev = _check_cuda(q, r)
@@ -124,12 +127,47 @@ def knn_search(
         stats = torch.zeros(4, dtype=torch.int64, device=dev)
         ws_bytes = int(lib.cm_knn_workspace_bytes(n_q, n_r, d, k, algo))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        cell = rad2 = None
+        if ref_cells is not None:
+            cell, rad2 = ref_cells
+            if cell.dtype != torch.uint8 or cell.numel() != n_r or rad2.numel() != 256 or rad2.element_size() != 4:
+                raise ValueError("ref_cells must be (uint8 (n_r,), 32-bit (256,)) tensors from knn_assign_reference")
+            _check_cuda(cell, rad2)
+            cell, rad2 = cell.contiguous(), rad2.contiguous()
         _call(
-            "cm_knn_search",
+            "cm_knn_search_cells",
             _ptr(q), n_q, q.stride(0), _ptr(r), n_r, r.stride(0), d, _dtype_code(q), k, int(r_index_offset),
-            int(dist_mode), int(algo), _ptr(out_d), _ptr(out_i), _ptr(ws), ws_bytes, _ptr(stats), _stream(),
+            int(dist_mode), int(algo), _ptr(out_d), _ptr(out_i), _ptr(ws), ws_bytes, _ptr(stats), _ptr(cell), _ptr(rad2),
+            _stream(),
         )  # fmt: skip
     return (out_d, out_i, stats) if return_stats else (out_d, out_i)
+
+
+def knn_assign_reference(r: torch.Tensor, k: int, row_lo: int = 0, row_hi: int | None = None):
+    """Reference side of the search's coarse cells for rows [row_lo, row_hi) of ``r``: (cell uint8 (rows,), rad2 int32
+    (256,) float bit patterns of the cells' squared radii over these rows), or None when a search of this reference
+    with ``k`` neighbours uses no cells.  Blocks of several ranks: concatenate the cells, integer max of rad2."""
+    dev = _check_cuda(r)
+    if r.dtype not in (torch.float32, torch.float64):
+        r = r.to(torch.float64)
+    if r.stride(-1) != 1:
+        r = r.contiguous()
+    n_r, d = r.shape
+    row_hi = n_r if row_hi is None else row_hi
+    import ctypes
+
+    n_cells = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        cell = torch.empty(max(row_hi - row_lo, 1), dtype=torch.uint8, device=dev)
+        rad2 = torch.zeros(256, dtype=torch.int32, device=dev)
+        ws = torch.empty(128 * 1024, dtype=torch.uint8, device=dev)
+        _call(
+            "cm_knn_assign_reference", _ptr(r), n_r, r.stride(0), d, _dtype_code(r), int(k), int(row_lo), int(row_hi),
+            _ptr(cell), _ptr(rad2), ctypes.addressof(n_cells), _ptr(ws), ws.numel(), _stream(),
+        )  # fmt: skip
+    if n_cells.value == 0:
+        return None
+    return cell[: row_hi - row_lo], rad2
 
 
 def finish_distances(d2: torch.Tensor, dist_mode: int) -> torch.Tensor:

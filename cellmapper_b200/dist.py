@@ -30,6 +30,7 @@ __all__ = [
     "knn_reference_sharded",
     "gather_rows",
     "upload_replicated",
+    "assign_reference_sharded",
     "csr_column_block",
     "spgemm_reference_sharded",
 ]
@@ -247,3 +248,32 @@ def spgemm_reference_sharded(
     o_vals = torch.ones(nb * ws, dtype=torch.float32, device=dev)
     oip, ocols, ovals = spgemm(o_ip, o_cols.contiguous(), o_vals, s_ip, s_cols, s_vals, n_genes)
     return oip, ocols, ovals, (q_lo, q_hi)
+
+
+def assign_reference_sharded(r: torch.Tensor, k: int, assign: Callable | None = None):
+    """Reference side of the search's coarse cells (nearest pivot of every reference row, cell radii) computed
+    block by block on the ranks and all-gathered: 1/world of the one part of the query-sharded search that does
+    not shrink with the number of GPUs (1.15 ms of a 9.4 ms step at 8 GPUs on BASELINE config 3).  ``r`` is the
+    replicated reference embedding on this rank's device.  Returns ``ref_cells`` for ``device.knn_search`` or None
+    (single process, or a search without cells).  ``assign(r, k, lo, hi)``: ``device.knn_assign_reference``."""
+    rank, ws = world()
+    if ws == 1:
+        return None
+    if assign is None:
+        from . import device
+
+        assign = device.knn_assign_reference
+    n = r.shape[0]
+    m = -(-n // ws)
+    lo, hi = min(n, rank * m), min(n, (rank + 1) * m)
+    got = assign(r, k, lo, hi)
+    if got is None:  # decided by (n_r, d, k) alone: the same on every rank, no collective needed
+        return None
+    cell, rad2 = got
+    block = torch.zeros(m, dtype=torch.uint8, device=r.device)
+    block[: hi - lo] = cell
+    full = torch.empty(ws * m, dtype=torch.uint8, device=r.device)
+    dist.all_gather_into_tensor(full, block)
+    rad2 = rad2.clone()
+    dist.all_reduce(rad2, op=dist.ReduceOp.MAX)  # non-negative floats order like their bit patterns
+    return full[:n], rad2

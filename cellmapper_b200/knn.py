@@ -231,7 +231,10 @@ def extract_neighbors_from_distances(distances_matrix, include_self: bool | None
 class Neighbors:
     """Compute and store nearest neighbours (reference: knn.py:269-492) with the B200 back-end."""
 
-    def __init__(self, xrep, yrep=None, *, upload_reference=None):
+    def __init__(self, xrep, yrep=None, *, upload_reference=None, reference_cells=None):
+        # reference_cells: optional callable(reference tensor, k) -> ref_cells for device.knn_search
+        # (cellmapper_b200.dist.assign_reference_sharded in multi-GPU runs)
+        self._reference_cells = reference_cells
         # upload_reference: optional callable(host array) -> device tensor for the reference side
         # (cellmapper_b200.dist.upload_replicated in multi-GPU runs); default: a plain upload
         self._upload_reference = upload_reference
@@ -284,7 +287,8 @@ class Neighbors:
 
         def search(q, r):
             mode = sklearn_like_dist_mode(np_dtype, r.shape[1], n_neighbors, r.shape[0])
-            d, i, st = device.knn_search(q, r, n_neighbors, dist_mode=mode, algo=algo, return_stats=True)
+            cells = self._reference_cells(r, n_neighbors) if (self._reference_cells is not None and r is x and q.dtype == r.dtype) else None
+            d, i, st = device.knn_search(q, r, n_neighbors, dist_mode=mode, algo=algo, return_stats=True, ref_cells=cells)
             return d, i, st
 
         d, i, st = search(y, x)

@@ -77,6 +77,22 @@ int cm_knn_search(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_
                   int k, int64_t r_index_offset, int dist_mode, int algo, double* out_dist, int64_t* out_idx,
                   void* workspace, size_t workspace_bytes, int64_t* stats_out, void* stream);
 
+/* Multi-GPU, query-sharded: the reference side of the search's coarse cells (the nearest of 256 pivots of every
+ * reference row and the cells' radii; the pivots depend on R alone) is the one part of cm_knn_search that does not
+ * shrink with the number of ranks.  cm_knn_assign_reference computes it for the rows [row_lo, row_hi) of R --
+ * out_cell (row_hi - row_lo bytes), out_rad2_bits (256 float bit patterns of squared radii over these rows; combine
+ * the blocks of all ranks with an integer max) --, the host side all-gathers the blocks (cellmapper_b200/dist.py),
+ * and cm_knn_search_cells takes the assembled arrays (ref_cell: n_r bytes; both NULL: same as cm_knn_search).
+ * n_cells_out (host) = 0: this reference is searched without cells, pass NULL.  workspace: >= 128 KB.
+ * Replaces nothing in the reference (it has no sharded search). */
+int cm_knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dtype, int k, int64_t row_lo, int64_t row_hi,
+                            uint8_t* out_cell, uint32_t* out_rad2_bits, int* n_cells_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int cm_knn_search_cells(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d, int dtype,
+                        int k, int64_t r_index_offset, int dist_mode, int algo, double* out_dist, int64_t* out_idx,
+                        void* workspace, size_t workspace_bytes, int64_t* stats_out, const uint8_t* ref_cell,
+                        const uint32_t* ref_rad2_bits, void* stream);
+
 /* merge n_lists per-shard candidate lists (each (n_q, k), ascending) into the global top-k.
  * Replaces nothing in the reference (it has no sharded search); used after the NCCL all-gather. */
 int cm_knn_merge_topk(const double* cand_dist, const int64_t* cand_idx, int n_lists, int64_t n_q, int k,

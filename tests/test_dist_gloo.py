@@ -105,6 +105,23 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
     ref_sub = mm[:, rlo:rhi].tocsr()
     assert np.array_equal(sub_ip.numpy(), ref_sub.indptr) and np.array_equal(sub_c.numpy(), ref_sub.indices) and np.array_equal(sub_v.numpy(), ref_sub.data)
 
+    # ---- reference side of the coarse cells: block per rank, all-gather of the cell numbers, max of the radii
+    def fake_assign(rt, kk, lo, hi):
+        cell = (torch.arange(lo, hi) % 251).to(torch.uint8)
+        rad = torch.zeros(256, dtype=torch.int32)
+        rad[r] = 1000 + r  # every rank contributes its own maximum somewhere
+        rad[200] = 7 * (r + 1)
+        return cell, rad
+
+    got_cells = cmd.assign_reference_sharded(torch.from_numpy(xr), k, assign=fake_assign)
+    if w == 1:
+        assert got_cells is None
+    else:
+        cell_all, rad_all = got_cells
+        assert torch.equal(cell_all, (torch.arange(xr.shape[0]) % 251).to(torch.uint8))
+        assert int(rad_all[200]) == 7 * w and all(int(rad_all[j]) == 1000 + j for j in range(w))
+        assert cmd.assign_reference_sharded(torch.from_numpy(xr), k, assign=lambda *a: None) is None
+
     # ---- replicated reference arrays: every rank uploads its row block, all-gather (odd row count, 1-D and 2-D)
     up2 = cmd.upload_replicated(xr, device=torch.device("cpu"), min_bytes=0)
     up1 = cmd.upload_replicated(cr.astype(np.int32), device=torch.device("cpu"), min_bytes=0)

@@ -245,6 +245,27 @@ def test_search_randomised_shapes(torch_cuda, seed):
         assert neighbours_match(ii, dd, ix, dx, rel=0.0) == 0, where
 
 
+def test_search_with_precomputed_reference_cells(torch_cuda):
+    """cm_knn_assign_reference block by block + cm_knn_search_cells == cm_knn_search bit for bit (the multi-GPU
+    query-sharded mode computes the reference side of the coarse cells 1/world per rank)."""
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    q, r = _pruning_case("mixture", np.random.default_rng(5))
+    qd, rd = dev(torch, q), dev(torch, r)
+    n_r = r.shape[0]
+    cuts = [0, 9_001, 17_000, n_r]
+    parts = [device.knn_assign_reference(rd, 30, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    cell = torch.cat([p[0] for p in parts])
+    rad2 = torch.stack([p[1] for p in parts]).max(0).values
+    whole = device.knn_assign_reference(rd, 30)
+    assert torch.equal(cell, whole[0]) and torch.equal(rad2, whole[1])
+    d0, i0, s0 = device.knn_search(qd, rd, 30, return_stats=True)
+    d1, i1, s1 = device.knn_search(qd, rd, 30, return_stats=True, ref_cells=(cell, rad2))
+    assert torch.equal(d0, d1) and torch.equal(i0, i1) and int(s0[3]) == int(s1[3])
+    assert device.knn_assign_reference(rd[:2000], 30) is None  # small references are searched without cells
+
+
 def test_search_errors(torch_cuda):
     torch = torch_cuda
     from cellmapper_b200 import device

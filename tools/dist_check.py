@@ -40,7 +40,7 @@ ref = AnnData(X=csr_matrix((n_r, 1), dtype=np.float32), obs=pd.DataFrame({"cellt
 def run_map(x, allreduce):
     q = AnnData(X=csr_matrix((x.shape[0], 1), dtype=np.float32), obs=pd.DataFrame(index=pd.RangeIndex(x.shape[0]).astype(str)), obsm={"X_joint": x})
     up = (lambda a: cmd.upload_replicated(a, min_bytes=0)) if allreduce is not None else None  # sharded upload + NCCL all-gather
-    cm = CellMapper(q, ref, allreduce=allreduce, upload_replicated=up).map(use_rep="X_joint", obs_keys="celltype", obsm_keys="X_umap", only_yx=True)
+    cm = CellMapper(q, ref, allreduce=allreduce, upload_replicated=up, reference_cells=cmd.assign_reference_sharded if allreduce is not None else None).map(use_rep="X_joint", obs_keys="celltype", obsm_keys="X_umap", only_yx=True)
     return q, cm
 lo, hi = cmd.shard_bounds(n_q, world, rank)
 run_map(xq[lo:hi], cmd.allreduce_sum if world > 1 else None)  # warm-up
