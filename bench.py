@@ -72,7 +72,7 @@ def make_inputs(name: str, rank: int = 0, world: int = 1):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -85,6 +85,13 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            # the first query of each kind initialises driver state for several milliseconds while holding a lock the
+            # kernel launches need (it showed up as one slow step in every short-step run): pay that before timing
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
             self.ok = True
         except Exception:  # pragma: no cover
             self.ok = False
@@ -278,10 +285,13 @@ def b200_arm(args):
         device_step()
     torch.cuda.synchronize()
     lib.cm_profile_enable(1)
-    sampler = ClockSampler(physical_gpu_index(local_rank))
+    # NVML queries take a driver lock that can hold up kernel launches for milliseconds: only the rank that
+    # reports the clocks samples them
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
     barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
     launches0 = lib.cm_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     phase_ms = np.zeros(4)
@@ -302,7 +312,7 @@ def b200_arm(args):
     torch.cuda.synchronize()
     barrier()
     launches = lib.cm_launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     lib.cm_profile_enable(0)
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
     step_ms = [a.elapsed_time(b) for a, b in ev]
