@@ -47,17 +47,22 @@ def sorted_category_codes(values: pd.Series):
     Returns (categories ndarray, codes int32 ndarray)."""
     if isinstance(values.dtype, pd.CategoricalDtype):
         cat = values.cat
-        present = np.unique(cat.codes.to_numpy())
-        present = present[present >= 0]
+        raw = cat.codes.to_numpy()
+        n_cat = len(cat.categories)
+        # which categories occur: one counting pass over the small-integer codes (np.unique hashes every element;
+        # at 1.5 M labels this function was 16 ms of host time in front of the vote, now ~3)
+        counts = np.bincount(raw.astype(np.intp) + 1, minlength=n_cat + 1)
+        if counts[0]:
+            raise ValueError("missing values in a categorical obs column are not supported by method='b200'")
+        present = np.flatnonzero(counts[1:])
         names = np.asarray(cat.categories.to_numpy(), dtype=object)[present]
         order = np.argsort(names, kind="stable")  # few categories: host sort of the names only
         cats = names[order]
-        lut = np.full(len(cat.categories) + 1, -1, dtype=np.int32)
+        if len(present) == n_cat and np.array_equal(order, np.arange(n_cat)):
+            return cats, raw.astype(np.int32)  # already in OneHotEncoder order: the codes are the class numbers
+        lut = np.full(n_cat, -1, dtype=np.int32)
         lut[present[order]] = np.arange(len(order), dtype=np.int32)
-        codes = lut[cat.codes.to_numpy()]
-        if (codes < 0).any():
-            raise ValueError("missing values in a categorical obs column are not supported by method='b200'")
-        return cats, codes
+        return cats, lut[raw]
     cats, codes = np.unique(np.asarray(values.to_numpy(), dtype=object), return_inverse=True)
     return cats, codes.astype(np.int32)
 
