@@ -13,11 +13,17 @@
 //                Q'.R'^T = c(n1+n2+n3) - 2(hi.hi + hi.lo + lo.hi) = ||r'||^2 - 2 q'.r'  (rank-equivalent
 //                to the squared distance) with ~2^-22 relative accuracy from three fp16 products,
 //                while the streamed reference tile carries only 2 of the 3 segments.
-//   mma_topk   : one CTA per (128-query tile, reference split).  Warp 0 streams reference tiles with
-//                bulk-async copies into a shared-memory ring, warp 1 issues tcgen05.mma (128x128xK')
-//                into three TMEM accumulator buffers, warps 2-5 first store the query tile into TMEM,
-//                then drain the accumulators (tcgen05.ld, one query row per thread) and keep a per-row
-//                threshold + candidate buffer in shared memory.
+//   cells      : <= 256 pivots (reference rows), numbered along a nearest-neighbour chain; both sides are
+//                bucketed by nearest pivot, the reference image is laid out cell by cell, the queries are
+//                sorted by cell, and per (query tile, cell) a triangle-inequality lower bound of the squared
+//                distance is tabulated (tile_bounds).  cm_knn_assign_reference / cm_knn_search_cells let the
+//                ranks of a multi-GPU run share the reference side of this step.
+//   mma_topk   : one CTA per (128-query tile, reference split).  Warp 0 schedules the reference cells the
+//                bounds cannot rule out and streams their tiles with bulk-async copies into a shared-memory
+//                ring, warps 1 and 6 issue tcgen05.mma (128x128xK') into three TMEM accumulator buffers,
+//                warps 2-5 first store the query tile into TMEM, then drain the accumulators (tcgen05.ld,
+//                one query row per thread) and keep a per-row threshold + candidate buffer in shared memory
+//                (leaf queues, warp-uniform selection with four pivots per counting pass).
 //                The n_q x n_r distance matrix never exists.
 //   rerank     : per query, exact float64 direct-difference distances of the <= 60*splits candidates,
 //                sort by (d2, index), emit k, and CERTIFY: d2_k + 2E <= smallest rejected value.
