@@ -18,9 +18,11 @@ LIBPATH = os.environ.get("CM_LIBPATH") or os.path.join(HERE, "lib", "libcellmapp
 F32, F64 = 0, 1
 KERNELS = {"gaussian": 0, "scarches": 1, "inverse_distance": 2, "equal": 3}
 DIST_SQRT_F64, DIST_SKLEARN_F32, DIST_SQUARED = 0, 1, 2
-KNN_AUTO, KNN_EXACT_F64 = 0, 1
+KNN_AUTO, KNN_EXACT_F64, KNN_TENSOR_EXHAUSTIVE = 0, 1, 2
 EDGE_STATS_WORKSPACE_BYTES = 32768
 SPGEMM_MAX_COLS = 49152
+SELECT_WORKSPACE_BYTES = 16384
+MOMENTS = 8
 
 _P = c_void_p
 #: name -> (restype, argtypes); must list every function include/cellmapper_b200.h declares
@@ -49,7 +51,16 @@ SIGNATURES = {
     "cm_vote_argmax": (c_int, [_P, _P, _P, c_int64, _P, c_int, _P, _P, _P, _P]),
     "cm_spmm_csr_dense": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, c_int, _P, c_int64, _P]),
     "cm_spgemm_count": (c_int, [_P, _P, c_int64, _P, _P, c_int32, _P, _P]),
-    "cm_spgemm_fill": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P, _P, _P]),
+    "cm_spgemm_fill": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int, c_int32, _P, _P, _P, _P]),
+    "cm_presence_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
+    "cm_presence_scores": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, c_int64, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "cm_select_ranks": (c_int, [_P, c_int, c_int64, c_int64, _P, c_int, _P, _P, c_size_t, _P]),
+    "cm_log1p_inplace": (c_int, [_P, c_int, c_int64, c_int64, _P]),
+    "cm_clip_minmax_inplace": (c_int, [_P, c_int, c_int64, c_int64, c_double, c_double, c_double, c_double, c_int, _P]),
+    "cm_expr_gene_sums": (
+        c_int,
+        [c_int, _P, _P, _P, c_int, c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P, _P, _P],
+    ),
     "cm_reverse_lists_workspace_bytes": (c_size_t, [c_int64]),
     "cm_reverse_lists": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P, c_size_t, _P]),
     "cm_jaccard_count": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P]),
@@ -57,9 +68,13 @@ SIGNATURES = {
     "cm_launch_count": (c_int64, []),
     "cm_profile_enable": (c_int, [c_int]),
     "cm_profile_last_knn_ms": (c_int, [_P]),
+    "cm_debug_mma_tile": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+}
+
+#: development-build-only entry points (nvcc -DCM_DEV_PROBES); bound when present, never required
+DEV_SIGNATURES = {
     "cm_debug_probe_flags": (c_int, [c_int]),
     "cm_debug_probe_prof": (c_int, [_P]),
-    "cm_debug_mma_tile": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
 }
 
 _lib = None
@@ -81,7 +96,7 @@ def load(build_if_missing: bool = False):
                 "(needs nvcc with sm_100a support). The 'b200' method has no CPU fallback."
             )
     lib = ctypes.CDLL(LIBPATH)
-    for name, (restype, argtypes) in SIGNATURES.items():
+    for name, (restype, argtypes) in {**SIGNATURES, **DEV_SIGNATURES}.items():
         if not hasattr(lib, name):
             continue  # reported by tests/test_cabi.py; calling it raises AttributeError
         fn = getattr(lib, name)

@@ -20,7 +20,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libcellmapper_b200.so")
 STAMP = os.path.join(LIBDIR, "build.stamp")
 
-SOURCES = ["cabi.cu", "knn_exact.cu", "knn_mma.cu", "graph_kernel.cu", "transfer.cu", "jaccard.cu"]
+SOURCES = ["cabi.cu", "scan.cu", "knn_exact.cu", "knn_mma.cu", "graph_kernel.cu", "transfer.cu", "jaccard.cu", "evaluate.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -59,35 +59,49 @@ def sources() -> list[str]:
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, dev_probes: bool = False) -> str:
+    """``dev_probes``: a separate library (lib/libcellmapper_b200_probes.so, -DCM_DEV_PROBES) that also exports
+    the development probes cm_debug_probe_flags / cm_debug_probe_prof; tools/ load it through CM_LIBPATH.  The
+    shipping library never contains them."""
+    from concurrent.futures import ThreadPoolExecutor
+
     os.makedirs(LIBDIR, exist_ok=True)
-    fp = _fingerprint()
-    if not force and os.path.exists(LIBPATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == fp:
-        return LIBPATH
+    tag = "_probes" if dev_probes else ""
+    libpath = LIBPATH.replace(".so", f"{tag}.so")
+    stamp = STAMP + tag
+    flags = NVCC_FLAGS + (["-DCM_DEV_PROBES"] if dev_probes else [])
+    fp = _fingerprint() + tag
+    if not force and os.path.exists(libpath) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+        return libpath
+
+    def compile_one(src):
+        obj = os.path.join(LIBDIR, os.path.basename(src).replace(".cu", f"{tag}.o"))
+        cmd = [_nvcc(), *flags, "-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, cmd, res
+
     objs = []
     logs = []
-    for src in sources():
-        obj = os.path.join(LIBDIR, os.path.basename(src).replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
-        if res.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
-        objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIBPATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        for obj, cmd, res in pool.map(compile_one, sources()):
+            logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {cmd[-3]}:\n{res.stdout}\n{res.stderr}")
+            objs.append(obj)
+    cmd = [_nvcc(), "-shared", "-o", libpath, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     logs.append(f"$ {' '.join(cmd)}\n{res.stdout}{res.stderr}")
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+    with open(os.path.join(LIBDIR, f"build{tag}.log"), "w") as f:
         f.write("\n".join(logs))
-    with open(STAMP, "w") as f:
+    with open(stamp, "w") as f:
         f.write(fp)
     if verbose:
         print("\n".join(logs))
-    return LIBPATH
+    return libpath
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, dev_probes="--dev-probes" in sys.argv)
     print(path)

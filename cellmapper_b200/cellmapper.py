@@ -22,10 +22,11 @@ from scipy.sparse import coo_matrix, csc_matrix, csr_matrix, issparse
 
 from . import _lib, device
 from ._anndata import AnnData
+from .evaluate import EvaluationMixin, process_presence_scores
 from .knn import Neighbors, NeighborsResults, _to_device
 from .logging import logger
 
-__all__ = ["CellMapper", "PackageConstants", "get_n_comps", "sorted_category_codes"]
+__all__ = ["CellMapper", "PackageConstants", "get_n_comps", "sorted_category_codes", "process_presence_scores"]
 
 KERNEL_METHODS = ("gaussian", "scarches", "inverse_distance", "random", "equal")
 
@@ -84,7 +85,7 @@ class _DeviceCSR:
         return self._host
 
 
-class CellMapper:
+class CellMapper(EvaluationMixin):
     """Mapping of labels, embeddings, and expression values between reference and query datasets."""
 
     def __init__(self, query: AnnData, reference: AnnData | None = None, *, allreduce=None, upload_replicated=None, reference_cells=None) -> None:
@@ -120,6 +121,7 @@ class CellMapper:
         #: last imputed layer as device CSR / dense tensor (kept for callers that stay on the GPU)
         self.imputed_device = None
         self._prefetched: dict = {}
+        self._layer_cache: dict = {}
 
     def __repr__(self):
         query_summary = f"AnnData(n_obs={self.query.n_obs:,}, n_vars={self.query.n_vars:,})"
@@ -155,7 +157,7 @@ class CellMapper:
             raise ValueError(f"Mapping matrix shape mismatch: expected ({expected[0]}, {expected[1]}), but got {m.shape}.")
         if not issparse(m):
             m = csr_matrix(np.asarray(m))
-        m = m.tocsr()
+        m = m.tocsr(copy=True)  # canonicalised below: never touch the caller's matrix (tocsr() returns self for CSR input)
         m.sum_duplicates()
         m.sort_indices()
         indptr = _to_device(m.indptr, torch.int32)
@@ -234,9 +236,13 @@ class CellMapper:
                 )
             if self.knn.xx is None or self.knn.yy is None or self.knn.xy is None or self.knn.yx is None:
                 raise ValueError("Neighbors must be computed before accessing adjacency matrices.")
-            from .jaccard import jaccard_mapping_device
-
-            indptr, cols, vals = jaccard_mapping_device(self.knn, hnoca=(method == "hnoca"))
+            # shared-neighbour counts J = yx @ xx.T + yy @ xy.T, J/(4k-J) or (J/(2k-J))^2, then the normalisation of
+            # cellmapper.py:99-137 -- all on the device
+            knn = self.knn
+            indptr, cols, vals64 = device.jaccard(
+                knn.yx.indices_device, knn.yy.indices_device, knn.xx.indices_device, knn.xy.indices_device, hnoca=(method == "hnoca")
+            )
+            vals, _zero = device.csr_row_normalize(indptr, vals64)
             self._mapping = _DeviceCSR(indptr, cols, vals, (self.query.n_obs, self.reference.n_obs))
         elif method in KERNEL_METHODS:
             yx: NeighborsResults = self.knn.yx
@@ -288,32 +294,53 @@ class CellMapper:
         self.query.obsm[output_key] = out.cpu().numpy()
         logger.info("Embeddings mapped and stored in query.obsm['%s'].", output_key)
 
-    def map_layers(self, key: str) -> None:
-        """reference: cellmapper.py:346-383.  Sparse layers go through the CSR x CSR kernel, dense
-        layers through the k-sparse x dense kernel."""
-        m = self._require_mapping()
-        logger.info("Mapping layer for key '%s'.", key)
-        layer = self.reference.X if key == "X" else self.reference.layers[key]
-        if issparse(layer):
+    def _layer_device(self, key: str):
+        """The reference layer ``key`` as device CSR (indptr int64, cols int32 ascending per row, vals) + gene count;
+        the last one stays cached (the same layer feeds map_layers and the streamed evaluation)."""
+        cache = self._layer_cache
+        if key not in cache:
+            cache.clear()  # one layer at a time: a reference expression matrix is GBs of device memory
+            layer = self.reference.X if key == "X" else self.reference.layers[key]
             x = layer.tocsr()
             if not x.has_sorted_indices:
                 x = x.sorted_indices()
-            n_genes = x.shape[1]
-            if x.dtype != np.float32:
-                logger.warning("sparse layer of dtype %s is transferred in float32 by method='b200'.", x.dtype)
-            oip, ocols, ovals = device.spgemm(
-                m.indptr, m.cols, m.vals, _to_device(x.indptr), _to_device(x.indices), _to_device(x.data), n_genes
-            )
-            self.imputed_device = (oip, ocols, ovals)
-            ip = oip.cpu().numpy()
-            if ip[-1] < np.iinfo(np.int32).max:
-                ip = ip.astype(np.int32)
-            out = csr_matrix((ovals.cpu().numpy(), ocols.cpu().numpy(), ip), shape=(self.query.n_obs, n_genes))
-            out.has_sorted_indices = True
-        else:
+            data = x.data if x.data.dtype in (np.float32, np.float64) else x.data.astype(np.float64)  # scipy: int -> float64 result
+            cache[key] = (_to_device(x.indptr, torch.int64), _to_device(x.indices, torch.int32), _to_device(data), int(x.shape[1]))
+        return cache[key]
+
+    def _spgemm_layer_chunks(self, key: str, max_chunk_nnz: int = 1 << 27, info: dict | None = None):
+        """Device chunks (``device.SpgemmChunk``) of ``mapping_matrix @ layer`` for a sparse reference layer."""
+        m = self._require_mapping()
+        x_ip, x_cols, x_vals, n_genes = self._layer_device(key)
+        yield from device.spgemm_chunks(m.indptr, m.cols, m.vals, x_ip, x_cols, x_vals, n_genes, max_chunk_nnz=max_chunk_nnz, info=info)
+
+    def map_layers(self, key: str, *, chunk_consumer=None, max_chunk_nnz: int = 1 << 27) -> None:
+        """reference: cellmapper.py:346-383.  Sparse layers go through the CSR x CSR kernel, dense layers through
+        the k-sparse x dense kernel; float32 layers give float32, float64 / integer layers float64 (scipy's rule).
+
+        The sparse result is produced in row chunks of at most ``max_chunk_nnz`` entries (keyword-only, not in the
+        reference): the device only ever holds two chunks, each is copied to pinned host memory on a copy stream
+        while the next one is computed.  At BASELINE config 4 (500 k cells x ~15 k imputed genes) the whole result is
+        40-80 GB -- it exists, if at all, only on the host:
+
+        * ``chunk_consumer=None``: the chunks land in ONE pinned host CSR, which becomes ``query_imputed.X``;
+        * ``chunk_consumer(row_lo, row_hi, csr_chunk)``: called per chunk with a scipy CSR view (rows
+          [row_lo, row_hi), valid only during the call) -- write it to disk, reduce it, ...; ``query_imputed`` is
+          left untouched and nothing of the size of the result is ever allocated."""
+        m = self._require_mapping()
+        logger.info("Mapping layer for key '%s'.", key)
+        layer = self.reference.X if key == "X" else self.reference.layers[key]
+        if not issparse(layer):
             dense = device.spmm(m.indptr, m.cols, m.vals, _to_device(np.asarray(layer)))
             self.imputed_device = dense
             out = dense.cpu().numpy()
+            if chunk_consumer is not None:
+                chunk_consumer(0, self.query.n_obs, out)
+                return
+        else:
+            out = self._map_sparse_layer_streamed(key, chunk_consumer, max_chunk_nnz)
+            if chunk_consumer is not None:
+                return
         self.query_imputed = out
         message = f"Expression for layer '{key}' mapped and stored in query_imputed.X."
         if not self._is_self_mapping:
@@ -322,6 +349,74 @@ class CellMapper:
                 f"not the query (n_vars={self.query.n_vars})."
             )
         logger.info(message)
+
+    def _map_sparse_layer_streamed(self, key: str, chunk_consumer, max_chunk_nnz: int):
+        n_q, n_genes = self.query.n_obs, self._layer_device(key)[3]
+        info: dict = {}
+        chunks = self._spgemm_layer_chunks(key, max_chunk_nnz, info)
+        copy_stream = torch.cuda.Stream()
+        compute = torch.cuda.current_stream()
+        host_cols = host_vals = None  # whole-result pinned arrays (no consumer)
+        stage: list = []              # two pinned staging chunks (consumer)
+        pending = None                # (chunk, event, host cols view, host vals view)
+
+        def deliver(p):
+            ch, ev, hc, hv = p
+            ev.synchronize()
+            if chunk_consumer is not None:
+                ip = info["indptr"][ch.row_lo : ch.row_hi + 1] - info["indptr"][ch.row_lo]
+                block = csr_matrix((hv.numpy(), hc.numpy(), ip), shape=(ch.row_hi - ch.row_lo, n_genes))
+                block.has_sorted_indices = True
+                chunk_consumer(ch.row_lo, ch.row_hi, block)
+
+        for ci, ch in enumerate(chunks):
+            if ci == 0:
+                np_val = torch.float32 if ch.vals.dtype == torch.float32 else torch.float64
+                if chunk_consumer is None:
+                    total = max(info["nnz"], 1)
+                    try:  # page-locked: the chunks are DMA-ed straight into the final arrays
+                        host_cols = torch.empty(total, dtype=torch.int32, pin_memory=True)
+                        host_vals = torch.empty(total, dtype=np_val, pin_memory=True)
+                    except RuntimeError:  # the host refuses to lock that much memory: pageable destination
+                        logger.warning("could not page-lock %.1f GB for the imputed matrix; using pageable memory", total * 8 / 1e9)
+                        host_cols = torch.empty(total, dtype=torch.int32)
+                        host_vals = torch.empty(total, dtype=np_val)
+                else:
+                    cap = max(int(np.diff(info["indptr"]).max()) if n_q else 1, max_chunk_nnz, 1)
+                    stage = [(torch.empty(cap, dtype=torch.int32, pin_memory=True), torch.empty(cap, dtype=np_val, pin_memory=True)) for _ in range(2)]
+            if chunk_consumer is None:
+                e_lo = int(info["indptr"][ch.row_lo])
+                hc, hv = host_cols[e_lo : e_lo + ch.nnz], host_vals[e_lo : e_lo + ch.nnz]
+            else:
+                # staging buffer ci % 2 held chunk ci - 2, which was delivered while chunk ci - 1 was being copied
+                hc, hv = stage[ci % 2][0][: ch.nnz], stage[ci % 2][1][: ch.nnz]
+            filled = torch.cuda.Event()
+            filled.record(compute)
+            copy_stream.wait_event(filled)
+            with torch.cuda.stream(copy_stream):
+                hc.copy_(ch.cols, non_blocking=True)
+                hv.copy_(ch.vals, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            ch.done = done  # the device buffer may be refilled only after its copy has left
+            if pending is not None:
+                deliver(pending)  # the previous chunk's copy overlapped this chunk's fill
+            pending = (ch, done, hc, hv)
+        if pending is not None:
+            deliver(pending)
+        self.imputed_device = None
+        if chunk_consumer is not None:
+            return None
+        ip = info["indptr"]
+        if ip[-1] < np.iinfo(np.int32).max:
+            ip = ip.astype(np.int32)
+        nnz = int(info["nnz"])
+        if host_cols is None:  # no query rows
+            host_cols = torch.empty(0, dtype=torch.int32)
+            host_vals = torch.empty(0, dtype=torch.float32 if self._layer_device(key)[2].dtype == torch.float32 else torch.float64)
+        out = csr_matrix((host_vals.numpy()[:nnz], host_cols.numpy()[:nnz], ip), shape=(n_q, n_genes))
+        out.has_sorted_indices = True
+        return out
 
     @property
     def query_imputed(self) -> AnnData | None:
@@ -462,61 +557,3 @@ class CellMapper:
                 "Please provide at least one of ``obs_keys``, ``obsm_keys`` or ``layer_key``."
             )
         return self
-
-    # ------------------------------------------------------------------------------------------
-    # presence score (evaluate.py:426-521) -- "next" row f1 of the scope table
-    # ------------------------------------------------------------------------------------------
-    def estimate_presence_score(
-        self,
-        groupby: str | None = None,
-        key_added: str = "presence_score",
-        log: bool = False,
-        percentile: tuple[float, float] = (1, 99),
-    ):
-        if self.knn is None or self.knn.yx is None:
-            raise ValueError("Neighbors must be computed before estimating presence scores.")
-        yx = self.knn.yx
-        indptr, cols, vals = yx.connectivities_device("gaussian", normalize=False)
-        n_ref = self.reference.n_obs
-        scores_all = device.csr_col_sums(indptr, cols, vals, n_ref).cpu().numpy()
-        df_all = pd.DataFrame({"all": scores_all}, index=self.reference.obs_names)
-        self.reference.obs[key_added] = process_presence_scores(df_all, log=log, percentile=percentile)["all"]
-        logger.info("Presence score across all query cells computed and stored in `reference.obs['%s']`", key_added)
-        if groupby is not None:
-            group_labels = self.query.obs[groupby]
-            groups = group_labels.unique()
-            score_matrix = np.zeros((n_ref, len(groups)), dtype=np.float32)
-            ip_host = indptr.cpu().numpy().astype(np.int64)
-            for gi, group in enumerate(groups):
-                rows = np.flatnonzero((group_labels == group).values)
-                # row-slice of the device CSR: gather the rows' edges into a compact CSR
-                lens = ip_host[rows + 1] - ip_host[rows]
-                sub_ip = np.zeros(len(rows) + 1, dtype=np.int32)
-                np.cumsum(lens, out=sub_ip[1:])
-                take = np.concatenate([np.arange(ip_host[r], ip_host[r + 1]) for r in rows]) if len(rows) else np.zeros(0, dtype=np.int64)
-                take_dev = _to_device(take, torch.int64)
-                sub = device.csr_col_sums(_to_device(sub_ip, torch.int32), cols[take_dev].contiguous(), vals[take_dev].contiguous(), n_ref)
-                score_matrix[:, gi] = sub.cpu().numpy()
-            df_groups = pd.DataFrame(score_matrix, index=self.reference.obs_names, columns=groups)
-            self.reference.obsm[key_added] = process_presence_scores(df_groups, log=log, percentile=percentile)
-            logger.info(
-                "Presence scores per group defined in `query.obs['%s']` computed and stored in `reference.obsm['%s']`",
-                groupby,
-                key_added,
-            )
-
-
-def process_presence_scores(scores: pd.DataFrame, log: bool = False, percentile: tuple[float, float] = (1, 99)) -> pd.DataFrame:
-    """log1p / percentile clip / min-max of presence scores (reference: evaluate.py:483-521).
-    Post-processing of one float per reference cell; host side like the reference."""
-    if log:
-        scores = np.log1p(scores)
-    if tuple(percentile) != (0, 100):
-        low, high = percentile
-        scores = scores.apply(lambda x: np.clip(x, np.percentile(x, low), np.percentile(x, high)), axis=0)
-
-    def minmax(x):
-        min_val, max_val = np.min(x), np.max(x)
-        return (x - min_val) / (max_val - min_val) if max_val > min_val else np.zeros_like(x)
-
-    return scores.apply(minmax, axis=0)

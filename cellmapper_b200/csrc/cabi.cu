@@ -35,13 +35,16 @@ void set_error(const char* fmt, ...) {
 
 int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d, int dtype,
                    int k, int64_t r_off, int dist_mode, double* out_dist, int64_t* out_idx, void* workspace,
-                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st, const uint8_t* ref_cell, const uint32_t* ref_rad2);
+                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st, const uint8_t* ref_cell, const uint32_t* ref_rad2,
+                   bool exhaustive);
 int knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dtype, int64_t row_lo, int64_t row_hi,
                          uint8_t* out_cell, uint32_t* out_rad2, int* n_cells_out, void* workspace, size_t ws_bytes,
                          cudaStream_t st);
-size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d);
+size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d, bool exhaustive);
+#ifdef CM_DEV_PROBES
 void set_probe_flags(int f);
 void set_probe_prof(long long* p);
+#endif
 int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st);
 
@@ -81,12 +84,12 @@ extern "C" int cm_device_check(int device) {
 }
 
 static bool use_mma(int64_t n_r, int d, int k, int algo) {
-  return algo == CM_KNN_AUTO && mma_supported(d, k) && n_r >= k;
+  return (algo == CM_KNN_AUTO || algo == CM_KNN_TENSOR_EXHAUSTIVE) && mma_supported(d, k) && n_r >= k;
 }
 
 extern "C" size_t cm_knn_workspace_bytes(int64_t n_q, int64_t n_r, int d, int k, int algo) {
   if (n_q <= 0 || n_r <= 0 || d <= 0) return 256;
-  if (use_mma(n_r, d, k, algo)) return knn_mma_workspace_bytes(n_q, n_r, d);
+  if (use_mma(n_r, d, k, algo)) return knn_mma_workspace_bytes(n_q, n_r, d, algo == CM_KNN_TENSOR_EXHAUSTIVE);
   return 256;
 }
 
@@ -120,7 +123,7 @@ extern "C" int cm_knn_search_cells(const void* Q, int64_t n_q, int64_t ldq, cons
   CM_REQUIRE(ldq >= d && ldr >= d, "leading dimensions smaller than d");
   CM_REQUIRE(dtype == CM_F32 || dtype == CM_F64, "bad dtype code %d", dtype);
   CM_REQUIRE(dist_mode >= 0 && dist_mode <= 2, "bad dist_mode %d", dist_mode);
-  CM_REQUIRE(algo == CM_KNN_AUTO || algo == CM_KNN_EXACT_F64, "bad algo %d", algo);
+  CM_REQUIRE(algo == CM_KNN_AUTO || algo == CM_KNN_EXACT_F64 || algo == CM_KNN_TENSOR_EXHAUSTIVE, "bad algo %d", algo);
   // sklearn: "Expected n_neighbors <= n_samples_fit" (sklearn/neighbors/_base.py:841-851)
   CM_REQUIRE(k >= 1 && k <= n_r, "Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %lld", k,
              (long long)n_r);
@@ -130,7 +133,8 @@ extern "C" int cm_knn_search_cells(const void* Q, int64_t n_q, int64_t ldq, cons
   if (use_mma(n_r, d, k, algo)) {
     CM_REQUIRE(workspace, "workspace required (cm_knn_workspace_bytes)");
     return knn_search_mma(Q, n_q, ldq, R, n_r, ldr, d, dtype, k, r_index_offset, dist_mode, out_dist, out_idx,
-                          workspace, workspace_bytes, stats_out, st, ref_cell, ref_rad2_bits);
+                          workspace, workspace_bytes, stats_out, st, ref_cell, ref_rad2_bits,
+                          algo == CM_KNN_TENSOR_EXHAUSTIVE);
   }
   if (stats_out) CM_CUDA_CHECK(cudaMemsetAsync(stats_out, 0, 4 * sizeof(int64_t), st));
   return launch_knn_exact(Q, n_q, ldq, R, n_r, ldr, d, dtype, k, nullptr, nullptr, n_q, r_index_offset, dist_mode,
@@ -144,6 +148,7 @@ extern "C" int cm_debug_mma_tile(const void* Q, int64_t n_q, const void* R, int6
   return debug_mma_tile(Q, n_q, R, n_r, d, dtype, out, scale_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+#ifdef CM_DEV_PROBES
 extern "C" int cm_debug_probe_flags(int flags) {
   set_probe_flags(flags);
   return CM_OK;
@@ -153,3 +158,4 @@ extern "C" int cm_debug_probe_prof(long long* device_buf) {
   set_probe_prof(device_buf);
   return CM_OK;
 }
+#endif

@@ -60,6 +60,10 @@ struct Workspace {
   bool ok() const { return off <= size; }
 };
 
+// In-place inclusive scan of a[0..n) (scan.cu).  `block_sums`: device scratch of inclusive_scan_scratch_elems(n) int32.
+int64_t inclusive_scan_scratch_elems(int64_t n);
+int inclusive_scan_i32(int32_t* a, int64_t n, int32_t* block_sums, cudaStream_t st);
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
 // order-preserving map float -> uint32 (so that integer compare == float compare)

@@ -152,45 +152,6 @@ __global__ void count_valid_kernel(const double* __restrict__ dist, const int64_
   }
 }
 
-// in-place inclusive scan of a[0..n) (int32), three kernels, block sums kept in `scratch`
-constexpr int kScanBlock = 1024;
-__global__ void scan_local_kernel(int32_t* a, int64_t n, int32_t* block_sums) {
-  __shared__ int32_t sh[kScanBlock];
-  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  sh[threadIdx.x] = i < n ? a[i] : 0;
-  __syncthreads();
-  for (int o = 1; o < kScanBlock; o <<= 1) {
-    int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += v;
-    __syncthreads();
-  }
-  if (i < n) a[i] = sh[threadIdx.x];
-  if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = sh[threadIdx.x];
-}
-__global__ void scan_sums_kernel(int32_t* block_sums, int64_t nb) {
-  __shared__ int32_t sh[kScanBlock];
-  int32_t carry = 0;
-  for (int64_t base = 0; base < nb; base += kScanBlock) {
-    const int64_t i = base + threadIdx.x;
-    sh[threadIdx.x] = i < nb ? block_sums[i] : 0;
-    __syncthreads();
-    for (int o = 1; o < kScanBlock; o <<= 1) {
-      int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (i < nb) block_sums[i] = sh[threadIdx.x] + carry;
-    carry += sh[kScanBlock - 1];
-    __syncthreads();
-  }
-}
-__global__ void scan_add_kernel(int32_t* a, int64_t n, const int32_t* block_sums) {
-  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  if (blockIdx.x > 0 && i < n) a[i] += block_sums[blockIdx.x - 1];
-}
-
 __global__ void __launch_bounds__(kRowWarps * 32)
 edge_to_csr_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n_q, int k, int np,
                    int kernel, const double* __restrict__ stats3, int normalize, const int32_t* __restrict__ indptr,
@@ -403,16 +364,9 @@ extern "C" int cm_edge_kernel_to_csr(const double* dist, const int64_t* idx, int
   }
   {
     // inclusive scan of indptr[1..n_q]; block sums live at the head of `cols` until it is filled
-    const int64_t nb = ceil_div(n_q, kScanBlock);
-    CM_REQUIRE(nb <= n_q * (int64_t)k, "scratch too small");
-    scan_local_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(indptr + 1, n_q, cols);
-    CM_LAUNCH_CHECK("scan_local_kernel");
-    if (nb > 1) {
-      scan_sums_kernel<<<1, kScanBlock, 0, st>>>(cols, nb);
-      CM_LAUNCH_CHECK("scan_sums_kernel");
-      scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(indptr + 1, n_q, cols);
-      CM_LAUNCH_CHECK("scan_add_kernel");
-    }
+    CM_REQUIRE(inclusive_scan_scratch_elems(n_q) <= n_q * (int64_t)k, "scratch too small");
+    const int rc = inclusive_scan_i32(indptr + 1, n_q, cols, st);
+    if (rc) return rc;
   }
   {
     size_t smem = (size_t)kRowWarps * np * (sizeof(double) + sizeof(int32_t));

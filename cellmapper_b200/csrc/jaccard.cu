@@ -14,59 +14,24 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // reverse neighbour lists: (n, k) int64 indices -> CSR-like (indptr, rows) by target, rows ascending
 // ------------------------------------------------------------------------------------------------
-__global__ void rev_count_kernel(const int64_t* __restrict__ idx, int64_t n_edges, int64_t n_targets,
+// Targets are the columns [target_lo, target_lo + n_targets) (a rank's block of the reference in the sharded presence
+// score; the whole range otherwise); everything else, including the -1 padding of ragged graphs (knn.py:68-77), is skipped.
+__global__ void rev_count_kernel(const int64_t* __restrict__ idx, int64_t n_edges, int64_t target_lo, int64_t n_targets,
                                  int32_t* __restrict__ counts /* indptr + 1 */) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = idx[e];
-    if (t >= 0 && t < n_targets) atomicAdd(&counts[t], 1);  // -1 = padding of ragged graphs (knn.py:68-77)
+    const int64_t t = idx[e] - target_lo;
+    if (t >= 0 && t < n_targets) atomicAdd(&counts[t], 1);
   }
-}
-
-constexpr int kScanBlock = 1024;
-__global__ void scan_local_kernel(int32_t* a, int64_t n, int32_t* block_sums) {
-  __shared__ int32_t sh[kScanBlock];
-  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  sh[threadIdx.x] = i < n ? a[i] : 0;
-  __syncthreads();
-  for (int o = 1; o < kScanBlock; o <<= 1) {
-    int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += v;
-    __syncthreads();
-  }
-  if (i < n) a[i] = sh[threadIdx.x];
-  if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = sh[threadIdx.x];
-}
-__global__ void scan_sums_kernel(int32_t* block_sums, int64_t nb) {
-  __shared__ int32_t sh[kScanBlock];
-  int32_t carry = 0;
-  for (int64_t base = 0; base < nb; base += kScanBlock) {
-    const int64_t i = base + threadIdx.x;
-    sh[threadIdx.x] = i < nb ? block_sums[i] : 0;
-    __syncthreads();
-    for (int o = 1; o < kScanBlock; o <<= 1) {
-      int32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += v;
-      __syncthreads();
-    }
-    if (i < nb) block_sums[i] = sh[threadIdx.x] + carry;
-    carry += sh[kScanBlock - 1];
-    __syncthreads();
-  }
-}
-__global__ void scan_add_kernel(int32_t* a, int64_t n, const int32_t* block_sums) {
-  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  if (blockIdx.x > 0 && i < n) a[i] += block_sums[blockIdx.x - 1];
 }
 
 // cursor[t] = indptr[t]: the fill reserves slots with atomics, the per-list sort below restores order
-__global__ void rev_fill_kernel(const int64_t* __restrict__ idx, int64_t n, int k, int64_t n_targets,
-                                int32_t* __restrict__ cursor, int32_t* __restrict__ rows) {
+// store_edges: the list holds the edge numbers e = row * k + position (ascending e == ascending row) instead of the rows
+__global__ void rev_fill_kernel(const int64_t* __restrict__ idx, int64_t n, int k, int64_t target_lo, int64_t n_targets,
+                                int store_edges, int32_t* __restrict__ cursor, int32_t* __restrict__ rows) {
   const int64_t n_edges = n * k;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = idx[e];
-    if (t >= 0 && t < n_targets) rows[atomicAdd(&cursor[t], 1)] = (int32_t)(e / k);
+    const int64_t t = idx[e] - target_lo;
+    if (t >= 0 && t < n_targets) rows[atomicAdd(&cursor[t], 1)] = (int32_t)(store_edges ? e : e / k);
   }
 }
 
@@ -221,47 +186,41 @@ int launch_jaccard(const int64_t* yx, const int64_t* yy, int64_t n_q, int k, int
 }
 
 }  // namespace
-}  // namespace cm
 
-using namespace cm;
-
-extern "C" size_t cm_reverse_lists_workspace_bytes(int64_t n_targets) {
-  return align_up((size_t)(n_targets + 1) * sizeof(int32_t), 256) + align_up((size_t)(ceil_div(n_targets, kScanBlock) + 1) * sizeof(int32_t), 256);
+size_t reverse_lists_workspace_bytes(int64_t n_targets) {
+  return align_up((size_t)(n_targets + 1) * sizeof(int32_t), 256) +
+         align_up((size_t)(inclusive_scan_scratch_elems(n_targets) + 1) * sizeof(int32_t), 256);
 }
 
-extern "C" int cm_reverse_lists(const int64_t* idx, int64_t n, int k, int64_t n_targets, int32_t* out_indptr,
-                                int32_t* out_rows, void* workspace, size_t workspace_bytes, void* stream) {
+// Reverse neighbour lists of the targets [target_lo, target_lo + n_targets): out_indptr (n_targets + 1), out_rows
+// (<= n * k entries) ascending inside every list; store_edges: edge numbers instead of rows.
+int reverse_lists_build(const int64_t* idx, int64_t n, int k, int64_t target_lo, int64_t n_targets, int store_edges,
+                        int32_t* out_indptr, int32_t* out_rows, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CM_REQUIRE(idx && out_indptr && out_rows && workspace, "null pointer argument");
   CM_REQUIRE(n >= 0 && k >= 1 && n_targets >= 1, "bad reverse-list shape");
   CM_REQUIRE(n * (int64_t)k < (int64_t)INT32_MAX && n_targets < (int64_t)INT32_MAX, "edge count must fit int32");
-  CM_REQUIRE(workspace_bytes >= cm_reverse_lists_workspace_bytes(n_targets), "reverse-list workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
+  CM_REQUIRE(workspace_bytes >= reverse_lists_workspace_bytes(n_targets), "reverse-list workspace too small");
   Workspace ws(workspace, workspace_bytes);
   int32_t* cursor = ws.take<int32_t>(n_targets + 1);
-  int32_t* block_sums = ws.take<int32_t>(ceil_div(n_targets, kScanBlock) + 1);
+  int32_t* block_sums = ws.take<int32_t>(inclusive_scan_scratch_elems(n_targets) + 1);
   CM_CUDA_CHECK(cudaMemsetAsync(out_indptr, 0, (size_t)(n_targets + 1) * sizeof(int32_t), st));
   const int64_t n_edges = n * k;
   if (n_edges > 0) {
     const int64_t blocks = ceil_div(n_edges, 256);
     const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
-    rev_count_kernel<<<grid, 256, 0, st>>>(idx, n_edges, n_targets, out_indptr + 1);
+    rev_count_kernel<<<grid, 256, 0, st>>>(idx, n_edges, target_lo, n_targets, out_indptr + 1);
     CM_LAUNCH_CHECK("rev_count_kernel");
   }
-  const int64_t nb = ceil_div(n_targets, kScanBlock);
-  scan_local_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(out_indptr + 1, n_targets, block_sums);
-  CM_LAUNCH_CHECK("scan_local_kernel");
-  if (nb > 1) {
-    scan_sums_kernel<<<1, kScanBlock, 0, st>>>(block_sums, nb);
-    CM_LAUNCH_CHECK("scan_sums_kernel");
-    scan_add_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(out_indptr + 1, n_targets, block_sums);
-    CM_LAUNCH_CHECK("scan_add_kernel");
+  {
+    const int rc = inclusive_scan_i32(out_indptr + 1, n_targets, block_sums, st);
+    if (rc) return rc;
   }
   if (n_edges == 0) return CM_OK;
   CM_CUDA_CHECK(cudaMemcpyAsync(cursor, out_indptr, (size_t)n_targets * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   {
     const int64_t blocks = ceil_div(n_edges, 256);
     const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
-    rev_fill_kernel<<<grid, 256, 0, st>>>(idx, n, k, n_targets, cursor, out_rows);
+    rev_fill_kernel<<<grid, 256, 0, st>>>(idx, n, k, target_lo, n_targets, store_edges, cursor, out_rows);
     CM_LAUNCH_CHECK("rev_fill_kernel");
   }
   {
@@ -274,6 +233,17 @@ extern "C" int cm_reverse_lists(const int64_t* idx, int64_t n, int k, int64_t n_
     CM_LAUNCH_CHECK("rev_sort_long_kernel");
   }
   return CM_OK;
+}
+
+}  // namespace cm
+
+using namespace cm;
+
+extern "C" size_t cm_reverse_lists_workspace_bytes(int64_t n_targets) { return reverse_lists_workspace_bytes(n_targets); }
+
+extern "C" int cm_reverse_lists(const int64_t* idx, int64_t n, int k, int64_t n_targets, int32_t* out_indptr,
+                                int32_t* out_rows, void* workspace, size_t workspace_bytes, void* stream) {
+  return reverse_lists_build(idx, n, k, 0, n_targets, 0, out_indptr, out_rows, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int cm_jaccard_count(const int64_t* yx, const int64_t* yy, int64_t n_q, int k, int64_t n_r,

@@ -773,7 +773,7 @@ struct RowCand {
   CM_PROBE(int n_trig, n_leaf; long long c_slow, c_compact, c_drain;)  // development counters
 };
 
-__device__ long long* g_compact_dbg = nullptr;  // development: per-lane compaction statistics
+__device__ long long* g_compact_dbg = nullptr;  // development builds: per-lane compaction statistics
 
 // keys are stored as raw fp32 bit patterns and compared as floats; only pivots move between the float
 // and the order-preserving uint domain (bisection needs integer midpoints)
@@ -1031,8 +1031,17 @@ constexpr int kMaxStages = 4;
 static_assert(kTmemCols == 512, "TMEM allocations are powers of two");
 constexpr int kLoadPieces = 4;    // bulk copies per reference tile (independent requests overlap their latency)
 
-int g_probe_flags = 0;  // set through cm_debug_probe_flags (development only)
+// Development probes (cm_debug_probe_flags / cm_debug_probe_prof) exist only in -DCM_DEV_PROBES builds; the shipping
+// library has no process-global switch that could invalidate results.
+#ifdef CM_DEV_PROBES
+int g_probe_flags = 0;
 long long* g_probe_prof = nullptr;
+#define CM_FLAGS(x) (x)
+#else
+constexpr int g_probe_flags = 0;
+constexpr long long* g_probe_prof = nullptr;
+#define CM_FLAGS(x) 0
+#endif
 
 struct MmaParams {
   const unsigned char* q_img;  // n_q_tiles tiles of 128 x kp_q fp16
@@ -1258,7 +1267,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
 #pragma unroll 1
   for (int it = a.first;; it += 2) {
     const long long t0 = a.prof ? clock64() : 0;
-    if (!(a.flags & 8)) mbar_wait(a.bar_acc_empty0 + 8 * buf, aph ^ 1u);  // probe 8: free-running MMA issue
+    if (!(CM_FLAGS(a.flags) & 8)) mbar_wait(a.bar_acc_empty0 + 8 * buf, aph ^ 1u);  // probe 8: free-running MMA issue
     const long long t1 = a.prof ? clock64() : 0;
     mbar_wait(a.bar_b_full0 + 8 * s, ph);
     const long long t2 = a.prof ? clock64() : 0;
@@ -1367,7 +1376,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   if (warp == 0) {
     // ===== producer: decides which reference tiles are scanned, bulk-async copies of whole operand tiles =====
     const bool cells = p.n_cells > 0;
-    const bool prune = cells && p.cell_lb2 != nullptr && !(p.flags & 32);  // probe 32: exhaustive scan
+    const bool prune = cells && p.cell_lb2 != nullptr;  // null bounds: exhaustive scan (CM_KNN_TENSOR_EXHAUSTIVE)
     if (cells) {
       for (int i = lane; i <= kMaxCells; i += 32) s_starts[i] = p.cell_starts[i];
       if (prune)
@@ -1381,7 +1390,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       auto schedule = [&](int tile) {  // tile < 0: end marker, no data
         mbar_wait(bar_b_empty(s), ph ^ 1u);
         sts_u32(ring_addr + 4u * (uint32_t)(it & (kTileRing - 1)), (uint32_t)tile);
-        if (tile < 0 || (p.flags & 2)) {
+        if (tile < 0 || (CM_FLAGS(p.flags) & 2)) {
           mbar_arrive(bar_b_full(s));
         } else {
           mbar_expect_tx(bar_b_full(s), b_bytes);
@@ -1514,7 +1523,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       const uint32_t t_buf = t_lane + (uint32_t)buf * kMmaTile;
       float* dbg = kDebug ? p.debug_out + q_row * ((int64_t)p.n_r_tiles * kMmaTile) + col_base : nullptr;
 
-      if (p.flags & 4) {  // probe: MMA pipeline alone, accumulators are never read
+      if (CM_FLAGS(p.flags) & 4) {  // probe: MMA pipeline alone, accumulators are never read
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty(buf));
         mbar_wait(bar_acc_full((it + 1) % kAccBufs), (uint32_t)((it + 1) / kAccBufs) & 1u);
@@ -1524,7 +1533,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       tmem_ld_wait();                          // columns 0..63 in va
       tmem_ld_32x32b_x64(t_buf + 64, vb);      // columns 64..127 in flight
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[j] = __uint_as_float(va[j]);
-      if (!(p.flags & 1)) process_half(va, col_base, rc, p.k, p.flags);
+      if (!(CM_FLAGS(p.flags) & 1)) process_half(va, col_base, rc, p.k, CM_FLAGS(p.flags));
 
       tmem_ld_wait();                          // columns 64..127 in vb
       // this warp has read the whole buffer: hand it back, then start on the next tile
@@ -1541,7 +1550,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
         }
       }
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[64 + j] = __uint_as_float(vb[j]);
-      if (!(p.flags & 1)) process_half(vb, col_base + 64, rc, p.k, p.flags);
+      if (!(CM_FLAGS(p.flags) & 1)) process_half(vb, col_base + 64, rc, p.k, CM_FLAGS(p.flags));
       publish();
       CM_PROBE(++n_epi_tiles;)
     }
@@ -1891,6 +1900,7 @@ struct MmaPlan {
   uint64_t perm_mul;  // no cells: image position p holds reference row (perm_mul * p) mod n_r_pad
   int n_cells;        // 0 = no coarse cells
   int kp_q, kp_r, dc, stages, splits;
+  bool exhaustive;    // scan every reference tile (no pruning bounds): CM_KNN_TENSOR_EXHAUSTIVE
   int64_t n_full, n_items;  // query tiles scanned by one CTA each; total CTAs
   int64_t n_q_tiles, n_r_tiles, n_q_pad, n_r_pad;
   size_t smem_bytes;
@@ -1922,7 +1932,7 @@ uint64_t scramble_multiplier(int64_t n_pad) {
   return (uint64_t)modinv64(h, n_pad);
 }
 
-MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
+MmaPlan make_plan(int64_t n_q, int64_t n_r, int d, bool exhaustive) {
   MmaPlan pl;
   pl.dc = mma_seg_chunks(d);
   pl.kp_q = mma_kp_q(d);
@@ -1944,7 +1954,8 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d) {
   pl.n_full = (pl.n_q_tiles / kNumSMs) * kNumSMs;
   const int64_t tail = pl.n_q_tiles - pl.n_full;
   int64_t s = 1;
-  if (tail > 0 && !(pl.n_cells > 0 && pl.n_full > 0 && !(g_probe_flags & 32))) {
+  pl.exhaustive = exhaustive;
+  if (tail > 0 && !(pl.n_cells > 0 && pl.n_full > 0 && !exhaustive)) {
     // (with coarse cells a pruned scan is short and needs its home cell inside its range: once there
     // are whole waves, the tail tiles stay whole too)
     s = pl.n_full > 0 ? kNumSMs / tail : ceil_div(2 * kNumSMs, tail);
@@ -2106,7 +2117,7 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.n_cells = pl.n_cells;
   p.home_cell = pl.n_cells > 0 ? b.home_cell : nullptr;
   p.cell_starts = pl.n_cells > 0 ? b.cell_starts : nullptr;
-  p.cell_lb2 = (pl.n_cells > 0 && !(g_probe_flags & 32)) ? b.cell_lb2 : nullptr;
+  p.cell_lb2 = (pl.n_cells > 0 && !pl.exhaustive) ? b.cell_lb2 : nullptr;
   p.q_norms = b.q_norms;
   p.perm_q = b.perm_q;
   p.info = b.info;
@@ -2152,8 +2163,8 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
   return CM_OK;
 }
 
-size_t mma_workspace_bytes(int64_t n_q, int64_t n_r, int d) {
-  MmaPlan pl = make_plan(n_q, n_r, d);
+size_t mma_workspace_bytes(int64_t n_q, int64_t n_r, int d, bool exhaustive) {
+  MmaPlan pl = make_plan(n_q, n_r, d, exhaustive);
   Workspace ws(nullptr, 0);
   carve(ws, pl, n_q, n_r);
   return ws.off + 256;
@@ -2204,8 +2215,9 @@ int knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dty
 
 int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_t n_r, int64_t ldr, int d, int dtype,
                    int k, int64_t r_off, int dist_mode, double* out_dist, int64_t* out_idx, void* workspace,
-                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st, const uint8_t* ref_cell, const uint32_t* ref_rad2) {
-  MmaPlan pl = make_plan(n_q, n_r, d);
+                   size_t ws_bytes, int64_t* stats_out, cudaStream_t st, const uint8_t* ref_cell, const uint32_t* ref_rad2,
+                   bool exhaustive) {
+  MmaPlan pl = make_plan(n_q, n_r, d, exhaustive);
   Workspace ws(workspace, ws_bytes);
   MmaBuffers b = carve(ws, pl, n_q, n_r);
   if (!ws.ok()) {
@@ -2245,7 +2257,10 @@ int knn_search_mma(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64
   return CM_OK;
 }
 
-size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d) { return mma_workspace_bytes(n_q, n_r, d); }
+size_t knn_mma_workspace_bytes(int64_t n_q, int64_t n_r, int d, bool exhaustive) {
+  return mma_workspace_bytes(n_q, n_r, d, exhaustive);
+}
+#ifdef CM_DEV_PROBES
 void set_probe_flags(int f) { g_probe_flags = f; }
 void set_probe_prof(long long* p) {
   g_probe_prof = p;
@@ -2253,6 +2268,7 @@ void set_probe_prof(long long* p) {
   cudaError_t e = cudaMemcpyToSymbol(g_compact_dbg, &d, sizeof(d));
   if (e != cudaSuccess) fprintf(stderr, "set_probe_prof: %s\n", cudaGetErrorString(e));
 }
+#endif
 
 int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st);
@@ -2263,7 +2279,7 @@ __global__ void write_scale_kernel(const ScaleInfo* info, float* scale_out) { *s
 
 int debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                    float* scale_out, void* workspace, size_t ws_bytes, cudaStream_t st) {
-  MmaPlan pl = make_plan(n_q, n_r, d);
+  MmaPlan pl = make_plan(n_q, n_r, d, false);
   pl.splits = 1;
   pl.n_full = 0;
   pl.n_items = pl.n_q_tiles;

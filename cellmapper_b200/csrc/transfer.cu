@@ -142,6 +142,7 @@ __global__ void spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* _
 // CSR x CSR row gather/accumulate: one CTA per query row, dense accumulator + touched-bitmap in smem
 // ------------------------------------------------------------------------------------------------
 constexpr int kSpgemmThreads = 512;
+__device__ __forceinline__ size_t align_up_dev(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
   // exclusive scan of one int per thread across the block
@@ -169,30 +170,36 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
   return warp_sums[warp] + inc - v;
 }
 
-template <bool kFill>
+// multiply and add rounded separately, in the value type (scipy's csr_matmat: sums[k] += v * Bx[kk], no FMA)
+__device__ __forceinline__ float mul_add_rn(float acc, float w, float x) { return __fadd_rn(acc, __fmul_rn(w, x)); }
+__device__ __forceinline__ double mul_add_rn(double acc, double w, double x) { return __dadd_rn(acc, __dmul_rn(w, x)); }
+
+// T = float: float32 layers (result float32).  T = double: float64 and integer layers -- scipy promotes the
+// float32 mapping matrix to float64 for those and returns float64 (cellmapper.py:372-373).
+template <bool kFill, typename T>
 __global__ void __launch_bounds__(kSpgemmThreads)
 spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_cols, const float* __restrict__ m_vals,
               int64_t n_q, const int64_t* __restrict__ x_indptr, const int32_t* __restrict__ x_cols,
-              const float* __restrict__ x_vals, int32_t g_lo, int32_t n_genes, int32_t* __restrict__ out_row_nnz,
+              const T* __restrict__ x_vals, int32_t g_lo, int32_t n_genes, int32_t* __restrict__ out_row_nnz,
               int accumulate_count, const int64_t* __restrict__ out_indptr, int64_t* __restrict__ row_off,
-              int32_t* __restrict__ out_cols, float* __restrict__ out_vals) {
+              int32_t* __restrict__ out_cols, T* __restrict__ out_vals) {
   // One pass covers the gene window [g_lo, g_lo + n_genes): entries outside it are skipped.  Matrices with more
   // columns than the shared-memory accumulator holds are processed window by window (spgemm_launch); `row_off`
   // then carries every row's write position from one window to the next.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_words = (n_genes + 31) >> 5;
   uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw);
-  float* acc = reinterpret_cast<float*>(smem_raw + (size_t)n_words * 4);
+  T* acc = reinterpret_cast<T*>(smem_raw + align_up_dev((size_t)n_words * 4, sizeof(T)));
   __shared__ int warp_sums[32];
   __shared__ int total_sh;
 
   for (int w = threadIdx.x; w < n_words; w += blockDim.x) bitmap[w] = 0u;
   if (kFill)
-    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) acc[g] = 0.f;
+    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) acc[g] = (T)0;
   __syncthreads();
 
   __shared__ int64_t s_xs[32], s_xe[32];
-  __shared__ float s_w[32];
+  __shared__ T s_w[32];
   constexpr int kNbGroup = 4;  // neighbours whose expression rows are fetched together
   constexpr int kPer = 4;      // elements per thread and neighbour held in registers (rows up to 2048 nnz; longer: tail loop)
 
@@ -206,14 +213,14 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
         const int64_t r = m_cols[e0 + threadIdx.x];
         s_xs[threadIdx.x] = x_indptr[r];
         s_xe[threadIdx.x] = x_indptr[r + 1];
-        s_w[threadIdx.x] = kFill ? m_vals[e0 + threadIdx.x] : 0.f;
+        s_w[threadIdx.x] = kFill ? (T)m_vals[e0 + threadIdx.x] : (T)0;
       }
       __syncthreads();
       for (int g0 = 0; g0 < n_nb; g0 += kNbGroup) {
         // all loads of a group of neighbours are in flight before the first accumulate: the per-neighbour
         // barrier below then costs a barrier, not a trip to memory
         int32_t gc[kNbGroup][kPer];
-        float gv[kNbGroup][kPer];
+        T gv[kNbGroup][kPer];
 #pragma unroll
         for (int j = 0; j < kNbGroup; ++j) {
           const bool on = g0 + j < n_nb;
@@ -222,26 +229,26 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
           for (int u = 0; u < kPer; ++u) {
             const int64_t p = xs + threadIdx.x + (int64_t)u * kSpgemmThreads;
             gc[j][u] = p < xe ? x_cols[p] - g_lo : -1;
-            gv[j][u] = (kFill && p < xe) ? x_vals[p] : 0.f;
+            gv[j][u] = (kFill && p < xe) ? x_vals[p] : (T)0;
           }
         }
 #pragma unroll
         for (int j = 0; j < kNbGroup; ++j) {  // ascending reference index == scipy's accumulation order
           if (g0 + j < n_nb) {
-            const float w = s_w[g0 + j];
+            const T w = s_w[g0 + j];
 #pragma unroll
             for (int u = 0; u < kPer; ++u) {
               const int32_t g = gc[j][u];
               if ((uint32_t)g < (uint32_t)n_genes) {
                 atomicOr(&bitmap[g >> 5], 1u << (g & 31));
-                if (kFill) acc[g] = __fadd_rn(acc[g], __fmul_rn(w, gv[j][u]));  // columns are unique inside one X row
+                if (kFill) acc[g] = mul_add_rn(acc[g], w, gv[j][u]);  // columns are unique inside one X row
               }
             }
             for (int64_t p = s_xs[g0 + j] + threadIdx.x + (int64_t)kPer * kSpgemmThreads; p < s_xe[g0 + j]; p += kSpgemmThreads) {
               const int32_t g = x_cols[p] - g_lo;
               if ((uint32_t)g < (uint32_t)n_genes) {
                 atomicOr(&bitmap[g >> 5], 1u << (g & 31));
-                if (kFill) acc[g] = __fadd_rn(acc[g], __fmul_rn(w, x_vals[p]));
+                if (kFill) acc[g] = mul_add_rn(acc[g], w, x_vals[p]);
               }
             }
             if (kFill) __syncthreads();  // the next neighbour may touch the same genes from other threads
@@ -269,7 +276,7 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
           const int g = (w << 5) + bit;
           out_cols[o] = g + g_lo;
           out_vals[o] = acc[g];
-          acc[g] = 0.f;
+          acc[g] = (T)0;
           ++o;
         }
       }
@@ -335,14 +342,17 @@ __global__ void copy_i64_kernel(const int64_t* __restrict__ src, int64_t* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+template <typename T>
 static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
-                         const int64_t* x_indptr, const int32_t* x_cols, const float* x_vals, int32_t n_genes,
-                         int32_t* out_row_nnz, const int64_t* out_indptr, int32_t* out_cols, float* out_vals,
+                         const int64_t* x_indptr, const int32_t* x_cols, const T* x_vals, int32_t n_genes,
+                         int32_t* out_row_nnz, const int64_t* out_indptr, int32_t* out_cols, T* out_vals,
                          cudaStream_t st) {
   CM_REQUIRE(n_q >= 0 && n_genes >= 1, "n_genes = %d must be positive", n_genes);
   if (n_q == 0) return CM_OK;
-  // gene windows of at most CM_SPGEMM_MAX_COLS columns (the dense accumulator of a CTA); one window in the usual case
-  const int n_win = (n_genes + CM_SPGEMM_MAX_COLS - 1) / CM_SPGEMM_MAX_COLS;
+  // gene windows of at most max_cols columns (the dense accumulator of a CTA: CM_SPGEMM_MAX_COLS float32 values,
+  // half as many float64); one window in the usual case
+  const int max_cols = (int)(CM_SPGEMM_MAX_COLS * sizeof(float) / sizeof(T));
+  const int n_win = (n_genes + max_cols - 1) / max_cols;
   int win = (n_genes + n_win - 1) / n_win;
   win = (win + 31) & ~31;
   int64_t* row_off = nullptr;
@@ -356,20 +366,20 @@ static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_co
     const int32_t g_n = n_genes - g_lo < win ? n_genes - g_lo : win;
     if (g_n <= 0) break;
     const int n_words = (g_n + 31) >> 5;
-    size_t smem = (size_t)n_words * 4 + (fill ? (size_t)g_n * 4 : 0);
+    size_t smem = align_up((size_t)n_words * 4, sizeof(T)) + (fill ? (size_t)g_n * sizeof(T) : 0);
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     int64_t want = (int64_t)kNumSMs * per_sm;
     int grid = (int)(n_q < want ? n_q : want);
     if (fill) {
-      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      spgemm_kernel<true><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n,
-                                                             out_row_nnz, 0, out_indptr, row_off, out_cols, out_vals);
+      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spgemm_kernel<true, T><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo,
+                                                                g_n, out_row_nnz, 0, out_indptr, row_off, out_cols, out_vals);
     } else {
-      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      spgemm_kernel<false><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n,
-                                                              out_row_nnz, w > 0, out_indptr, row_off, out_cols, out_vals);
+      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spgemm_kernel<false, T><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo,
+                                                                 g_n, out_row_nnz, w > 0, out_indptr, row_off, out_cols, out_vals);
     }
     CM_LAUNCH_CHECK("spgemm_kernel");
   }
@@ -379,13 +389,19 @@ static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_co
 
 extern "C" int cm_spgemm_count(const int32_t* m_indptr, const int32_t* m_cols, int64_t n_q, const int64_t* x_indptr,
                                const int32_t* x_cols, int32_t n_genes, int32_t* out_row_nnz, void* stream) {
-  return spgemm_launch(false, m_indptr, m_cols, nullptr, n_q, x_indptr, x_cols, nullptr, n_genes, out_row_nnz, nullptr,
-                       nullptr, nullptr, (cudaStream_t)stream);
+  // the structure does not depend on the value type; the float32 windows are the wider ones
+  return spgemm_launch<float>(false, m_indptr, m_cols, nullptr, n_q, x_indptr, x_cols, nullptr, n_genes, out_row_nnz,
+                              nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int cm_spgemm_fill(const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
-                              const int64_t* x_indptr, const int32_t* x_cols, const float* x_vals, int32_t n_genes,
-                              const int64_t* out_indptr, int32_t* out_cols, float* out_vals, void* stream) {
-  return spgemm_launch(true, m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, n_genes, nullptr, out_indptr,
-                       out_cols, out_vals, (cudaStream_t)stream);
+                              const int64_t* x_indptr, const int32_t* x_cols, const void* x_vals, int dtype,
+                              int32_t n_genes, const int64_t* out_indptr, int32_t* out_cols, void* out_vals,
+                              void* stream) {
+  CM_REQUIRE(dtype == CM_F32 || dtype == CM_F64, "bad dtype code %d", dtype);
+  if (dtype == CM_F32)
+    return spgemm_launch<float>(true, m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, (const float*)x_vals, n_genes,
+                                nullptr, out_indptr, out_cols, (float*)out_vals, (cudaStream_t)stream);
+  return spgemm_launch<double>(true, m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, (const double*)x_vals, n_genes,
+                               nullptr, out_indptr, out_cols, (double*)out_vals, (cudaStream_t)stream);
 }

@@ -25,32 +25,26 @@ __all__ = [
     "vote_argmax",
     "spmm",
     "spgemm",
+    "spgemm_chunks",
+    "SpgemmChunk",
+    "presence_scores",
+    "select_ranks",
+    "log1p_",
+    "clip_minmax_",
+    "expr_gene_sums",
     "reverse_lists",
     "jaccard",
     "debug_mma_tile",
     "counters",
 ]
 
-#: number of native kernels-launching C-ABI calls made (bench.py reports it as evidence)
-counters = {"calls": 0, "launches": 0}
+#: C-ABI calls made by this process (the kernels they launched are counted by the library itself: cm_launch_count)
+counters = {"calls": 0}
 
-# kernels launched per C-ABI call (upper bound used for the bench's `gpu_launches` claim)
-_LAUNCHES = {
-    "cm_knn_search": 17,
-    "cm_reverse_lists": 8,
-    "cm_jaccard_count": 1,
-    "cm_jaccard_fill": 1,
-    "cm_knn_merge_topk": 1,
-    "cm_edge_stats": 1,
-    "cm_edge_kernel_to_csr": 5,
-    "cm_csr_row_normalize": 1,
-    "cm_csr_col_sums": 1,
-    "cm_vote_argmax": 1,
-    "cm_spmm_csr_dense": 1,
-    "cm_spgemm_count": 1,
-    "cm_spgemm_fill": 1,
-    "cm_debug_mma_tile": 6,
-}
+
+def launches() -> int:
+    """Kernels libcellmapper_b200 has launched in this process so far (counted inside the library at every launch)."""
+    return int(_lib.load().cm_launch_count())
 
 
 def _ptr(t: torch.Tensor | None):
@@ -64,7 +58,6 @@ def _stream() -> int:
 def _call(name: str, *args) -> None:
     lib = _lib.load()
     counters["calls"] += 1
-    counters["launches"] += _LAUNCHES.get(name, 1)
     _lib.check(getattr(lib, name)(*args), name)
 
 
@@ -74,6 +67,19 @@ def _dtype_code(t: torch.Tensor) -> int:
     if t.dtype == torch.float64:
         return _lib.F64
     raise TypeError(f"expected float32 or float64 tensor, got {t.dtype}")
+
+
+def _expect(t: torch.Tensor | None, dtype: torch.dtype, name: str) -> None:
+    """The kernels read raw pointers: a tensor of another element type would be read as the wrong number of bytes."""
+    if t is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _csr_f32(indptr, cols, vals):
+    _expect(indptr, torch.int32, "indptr")
+    _expect(cols, torch.int32, "cols")
+    _expect(vals, torch.float32, "vals")
+    return indptr.contiguous(), cols.contiguous(), vals.contiguous()
 
 
 def _check_cuda(*tensors: torch.Tensor) -> torch.device:
@@ -209,8 +215,8 @@ def edge_stats(
     skips the second pass (only the scarches kernel uses the standard deviation); slot 1 is then NaN.
     """
     dev = _check_cuda(dist, idx)
-    dist = dist.contiguous()
-    idx = idx.contiguous()
+    dist = dist.to(torch.float64).contiguous()
+    idx = idx.to(torch.int64).contiguous()
     n = dist.numel()
     with torch.cuda.device(dev):
         ws = torch.empty(_lib.EDGE_STATS_WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
@@ -241,8 +247,8 @@ def edge_kernel_to_csr(
         raise ValueError(
             f"Unknown kernel: {kernel}. Supported kernels are: 'gaussian', 'scarches', 'random', 'inverse_distance', 'equal'."
         )
-    dist = dist.contiguous()
-    idx = idx.contiguous()
+    dist = dist.to(torch.float64).contiguous()
+    idx = idx.to(torch.int64).contiguous()
     n_q, k = dist.shape
     with torch.cuda.device(dev):
         if stats3 is None:
@@ -261,6 +267,8 @@ def edge_kernel_to_csr(
 def csr_row_normalize(indptr: torch.Tensor, vals: torch.Tensor):
     """float64 CSR values -> row-normalised float32 (cellmapper.py:126-135). Returns (vals_f32, n_zero_rows tensor)."""
     dev = _check_cuda(indptr, vals)
+    _expect(indptr, torch.int32, "indptr")
+    indptr = indptr.contiguous()
     n_rows = indptr.numel() - 1
     vals = vals.to(torch.float64).contiguous()
     with torch.cuda.device(dev):
@@ -273,6 +281,10 @@ def csr_row_normalize(indptr: torch.Tensor, vals: torch.Tensor):
 def csr_col_sums(indptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_cols: int, out: torch.Tensor | None = None):
     """Column sums of a float64 CSR (presence score, evaluate.py:457)."""
     dev = _check_cuda(indptr, cols, vals)
+    _expect(indptr, torch.int32, "indptr")
+    _expect(cols, torch.int32, "cols")
+    _expect(vals, torch.float64, "vals")
+    indptr, cols, vals = indptr.contiguous(), cols.contiguous(), vals.contiguous()
     n_rows = indptr.numel() - 1
     with torch.cuda.device(dev):
         if out is None:
@@ -287,6 +299,7 @@ def csr_col_sums(indptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n
 def vote_argmax(indptr, cols, vals, codes: torch.Tensor, n_classes: int, return_probs: bool = False):
     """Weighted label vote (cellmapper.py:591-605). Returns (code int32 (n_q,), conf float32 (n_q,)[, probs])."""
     dev = _check_cuda(indptr, cols, vals, codes)
+    indptr, cols, vals = _csr_f32(indptr, cols, vals)
     n_q = indptr.numel() - 1
     codes = codes.to(torch.int32).contiguous()
     with torch.cuda.device(dev):
@@ -304,6 +317,7 @@ def spmm(indptr, cols, vals, dense: torch.Tensor) -> torch.Tensor:
     """M @ dense (cellmapper.py:338,373,628). float32 stays float32, anything else is computed in float64
     (scipy's promotion of a float32 matrix with a float64 / integer operand)."""
     dev = _check_cuda(indptr, cols, vals, dense)
+    indptr, cols, vals = _csr_f32(indptr, cols, vals)
     n_q = indptr.numel() - 1
     squeeze = dense.dim() == 1
     if squeeze:
@@ -322,27 +336,200 @@ def spmm(indptr, cols, vals, dense: torch.Tensor) -> torch.Tensor:
     return out.reshape(-1) if squeeze else out
 
 
-def spgemm(indptr, cols, vals, x_indptr: torch.Tensor, x_cols: torch.Tensor, x_vals: torch.Tensor, n_genes: int):
-    """M @ X for CSR X (cellmapper.py:372-373). Two passes (count, fill); one host sync for the output size.
-    Returns (out_indptr int64 (n_q+1,), out_cols int32, out_vals float32), columns sorted per row."""
-    dev = _check_cuda(indptr, cols, vals, x_indptr, x_cols, x_vals)
+def _layer_values(x_vals: torch.Tensor) -> torch.Tensor:
+    """float32 layers stay float32; float64 and integer layers are computed and returned in float64 -- scipy's
+    promotion of the float32 mapping matrix with such an operand (cellmapper.py:372-373)."""
+    return x_vals.contiguous() if x_vals.dtype == torch.float32 else x_vals.to(torch.float64).contiguous()
+
+
+def spgemm_count(indptr, cols, x_indptr, x_cols, n_genes: int) -> torch.Tensor:
+    """Structural nnz of every row of M @ X (int32 (n_q,)): the first of the two passes of ``spgemm``."""
+    dev = _check_cuda(indptr, cols, x_indptr, x_cols)
+    _expect(indptr, torch.int32, "indptr")
+    _expect(cols, torch.int32, "cols")
+    _expect(x_indptr, torch.int64, "x_indptr")
+    _expect(x_cols, torch.int32, "x_cols")
     n_q = indptr.numel() - 1
-    x_indptr = x_indptr.to(torch.int64).contiguous()
-    x_cols = x_cols.to(torch.int32).contiguous()
-    x_vals = x_vals.to(torch.float32).contiguous()
     with torch.cuda.device(dev):
         row_nnz = torch.empty(n_q, dtype=torch.int32, device=dev)
         _call("cm_spgemm_count", _ptr(indptr), _ptr(cols), n_q, _ptr(x_indptr), _ptr(x_cols), int(n_genes), _ptr(row_nnz), _stream())
+    return row_nnz
+
+
+def spgemm(indptr, cols, vals, x_indptr: torch.Tensor, x_cols: torch.Tensor, x_vals: torch.Tensor, n_genes: int):
+    """M @ X for CSR X (cellmapper.py:372-373). Two passes (count, fill); one host sync for the output size.
+    Returns (out_indptr int64 (n_q+1,), out_cols int32, out_vals), columns sorted per row; out_vals is float32 for a
+    float32 layer and float64 otherwise (scipy's promotion).  The whole result is materialised on the device: for
+    results that do not fit use ``spgemm_chunks``."""
+    dev = _check_cuda(indptr, cols, vals, x_indptr, x_cols, x_vals)
+    indptr, cols, vals = _csr_f32(indptr, cols, vals)
+    n_q = indptr.numel() - 1
+    x_indptr = x_indptr.to(torch.int64).contiguous()
+    x_cols = x_cols.to(torch.int32).contiguous()
+    x_vals = _layer_values(x_vals)
+    with torch.cuda.device(dev):
+        row_nnz = spgemm_count(indptr, cols, x_indptr, x_cols, n_genes)
         out_indptr = torch.zeros(n_q + 1, dtype=torch.int64, device=dev)
         torch.cumsum(row_nnz, 0, out=out_indptr[1:])
         nnz = int(out_indptr[-1].item())
         out_cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-        out_vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        out_vals = torch.empty(max(nnz, 1), dtype=x_vals.dtype, device=dev)
         _call(
             "cm_spgemm_fill", _ptr(indptr), _ptr(cols), _ptr(vals), n_q, _ptr(x_indptr), _ptr(x_cols), _ptr(x_vals),
-            int(n_genes), _ptr(out_indptr), _ptr(out_cols), _ptr(out_vals), _stream(),
+            _dtype_code(x_vals), int(n_genes), _ptr(out_indptr), _ptr(out_cols), _ptr(out_vals), _stream(),
         )  # fmt: skip
     return out_indptr, out_cols[:nnz], out_vals[:nnz]
+
+
+class SpgemmChunk:
+    """Rows [row_lo, row_hi) of M @ X as a device CSR: ``indptr`` int64 (rows + 1,) starting at 0, ``cols`` int32,
+    ``vals`` (views into one of two alternating buffers).  A consumer that reads the chunk on ANOTHER stream sets
+    ``done`` to an event recorded after its last read; the buffer is not overwritten before that event."""
+
+    __slots__ = ("row_lo", "row_hi", "indptr", "cols", "vals", "done")
+
+    def __init__(self, row_lo, row_hi, indptr, cols, vals):
+        self.row_lo, self.row_hi, self.indptr, self.cols, self.vals = row_lo, row_hi, indptr, cols, vals
+        self.done: torch.cuda.Event | None = None
+
+    @property
+    def nnz(self) -> int:
+        return int(self.cols.numel())
+
+
+def spgemm_chunks(indptr, cols, vals, x_indptr, x_cols, x_vals, n_genes: int, max_chunk_nnz: int = 1 << 27, info: dict | None = None):
+    """M @ X for CSR X, produced in chunks of consecutive query rows so that the result never has to exist at
+    once (BASELINE config 4: 500 k rows x ~15 k nnz = 40-80 GB).  One count pass over all rows and ONE host sync
+    (the row pointer of the result, needed to cut the chunks), then per chunk one fill into one of two device
+    buffers of ``max_chunk_nnz`` entries (rows are never split; a single row larger than that gets a chunk of its
+    own).  Generator of ``SpgemmChunk``; a chunk stays valid until the next-but-one is requested.
+    ``info`` (optional dict) receives ``indptr`` (host int64 row pointer of the whole result) and ``nnz``."""
+    import numpy as np
+
+    dev = _check_cuda(indptr, cols, vals, x_indptr, x_cols, x_vals)
+    indptr, cols, vals = _csr_f32(indptr, cols, vals)
+    n_q = indptr.numel() - 1
+    x_indptr = x_indptr.to(torch.int64).contiguous()
+    x_cols = x_cols.to(torch.int32).contiguous()
+    x_vals = _layer_values(x_vals)
+    with torch.cuda.device(dev):
+        row_nnz = spgemm_count(indptr, cols, x_indptr, x_cols, n_genes)
+        out_indptr = torch.zeros(n_q + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(row_nnz, 0, out=out_indptr[1:])
+        ip_host = out_indptr.cpu().numpy()  # the one host sync
+        if info is not None:
+            info["indptr"], info["nnz"] = ip_host, int(ip_host[-1])
+        # chunk boundaries: as many whole rows as fit max_chunk_nnz
+        bounds = [0]
+        while bounds[-1] < n_q:
+            lo = bounds[-1]
+            hi = int(np.searchsorted(ip_host, ip_host[lo] + max_chunk_nnz, side="right")) - 1
+            bounds.append(min(n_q, max(hi, lo + 1)))
+        cap = max(int((ip_host[np.asarray(bounds[1:])] - ip_host[np.asarray(bounds[:-1])]).max()) if n_q else 1, 1)
+        n_buf = 2 if len(bounds) > 2 else 1
+        buf_cols = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(n_buf)]
+        buf_vals = [torch.empty(cap, dtype=x_vals.dtype, device=dev) for _ in range(n_buf)]
+        in_flight: list[SpgemmChunk | None] = [None] * n_buf
+        for ci, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+            b = ci % n_buf
+            prev = in_flight[b]
+            if prev is not None and prev.done is not None:
+                torch.cuda.current_stream().wait_event(prev.done)
+            nnz = int(ip_host[hi] - ip_host[lo])
+            rel = out_indptr[lo : hi + 1] - out_indptr[lo]
+            _call(
+                "cm_spgemm_fill", indptr[lo:].data_ptr(), _ptr(cols), _ptr(vals), hi - lo, _ptr(x_indptr), _ptr(x_cols),
+                _ptr(x_vals), _dtype_code(x_vals), int(n_genes), _ptr(rel), _ptr(buf_cols[b]), _ptr(buf_vals[b]), _stream(),
+            )  # fmt: skip
+            chunk = SpgemmChunk(lo, hi, rel, buf_cols[b][:nnz], buf_vals[b][:nnz])
+            in_flight[b] = chunk
+            yield chunk
+
+
+# ------------------------------------------------------------------------------------------------
+# consumers: presence score (evaluate.py:426-521), expression-transfer evaluation (evaluate.py:236-323)
+# ------------------------------------------------------------------------------------------------
+def presence_scores(dist, idx, stats3, n_targets: int, target_lo: int = 0, group_of_query: torch.Tensor | None = None, n_groups: int = 0):
+    """Column sums of the un-normalised gaussian graph over the reference cells [target_lo, target_lo + n_targets):
+    (all float64 (n_targets,), groups float32 (n_targets, n_groups) or None).  Deterministic (ascending query row)."""
+    dev = _check_cuda(dist, idx, stats3, group_of_query)
+    dist = dist.to(torch.float64).contiguous()
+    idx = idx.to(torch.int64).contiguous()
+    _expect(stats3, torch.float64, "stats3")
+    n_q, k = dist.shape
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        out_all = torch.empty(n_targets, dtype=torch.float64, device=dev)
+        out_groups = None
+        if group_of_query is not None:
+            group_of_query = group_of_query.to(torch.int32).contiguous()
+            if group_of_query.numel() != n_q:
+                raise ValueError("group_of_query must have one entry per query cell")
+            out_groups = torch.empty((n_targets, n_groups), dtype=torch.float32, device=dev)
+        ws_bytes = int(lib.cm_presence_workspace_bytes(n_q, k, n_targets))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _call(
+            "cm_presence_scores", _ptr(dist), _ptr(idx), n_q, k, _ptr(stats3), int(target_lo), int(n_targets),
+            _ptr(group_of_query), int(n_groups), _ptr(out_all), _ptr(out_groups), _ptr(ws), ws_bytes, _stream(),
+        )  # fmt: skip
+    return out_all, out_groups
+
+
+def select_ranks(column: torch.Tensor, ranks) -> torch.Tensor:
+    """The ``ranks``-th smallest entries (0-based, at most 8) of a 1-D float32 / float64 tensor (any stride): the
+    sorted-array entries np.percentile interpolates between, by radix selection.  Returns a device tensor."""
+    import ctypes
+
+    dev = _check_cuda(column)
+    if column.dim() != 1:
+        raise ValueError("select_ranks expects a 1-D tensor (a column view is fine)")
+    ranks = [int(r) for r in ranks]
+    arr = (ctypes.c_int64 * len(ranks))(*ranks)
+    with torch.cuda.device(dev):
+        out = torch.empty(len(ranks), dtype=column.dtype, device=dev)
+        ws = torch.empty(_lib.SELECT_WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+        _call(
+            "cm_select_ranks", _ptr(column), _dtype_code(column), column.numel(), column.stride(0) if column.numel() > 1 else 1,
+            ctypes.addressof(arr), len(ranks), _ptr(out), _ptr(ws), ws.numel(), _stream(),
+        )  # fmt: skip
+    return out
+
+
+def log1p_(column: torch.Tensor) -> None:
+    dev = _check_cuda(column)
+    with torch.cuda.device(dev):
+        _call("cm_log1p_inplace", _ptr(column), _dtype_code(column), column.numel(), column.stride(0) if column.numel() > 1 else 1, _stream())
+
+
+def clip_minmax_(column: torch.Tensor, lo: float, hi: float, mn: float, mx: float, clip: bool) -> None:
+    """column <- (clip(column, lo, hi) - mn) / (mx - mn), or 0 when mx <= mn, in place (evaluate.py:511-519)."""
+    dev = _check_cuda(column)
+    with torch.cuda.device(dev):
+        _call(
+            "cm_clip_minmax_inplace", _ptr(column), _dtype_code(column), column.numel(), column.stride(0) if column.numel() > 1 else 1,
+            float(lo), float(hi), float(mn), float(mx), int(bool(clip)), _stream(),
+        )  # fmt: skip
+
+
+def expr_gene_sums(js_pass: bool, imp_indptr, imp_cols, imp_vals, row0: int, orig_indptr, orig_cols, orig_vals, maps, group_of_query,
+                   n_shared: int, moments: torch.Tensor, js_out: torch.Tensor | None = None) -> None:
+    """Accumulate one chunk of the imputed CSR into the per-gene sums (see cm_expr_gene_sums in the header).
+    ``maps`` = (imp_to_shared, orig_to_shared, orig_to_imp, imp_to_orig) int32 device tensors."""
+    dev = _check_cuda(imp_indptr, imp_cols, imp_vals, orig_indptr, orig_cols, orig_vals, moments)
+    _expect(imp_indptr, torch.int64, "imp_indptr")
+    _expect(imp_cols, torch.int32, "imp_cols")
+    _expect(orig_indptr, torch.int64, "orig_indptr")
+    _expect(orig_cols, torch.int32, "orig_cols")
+    _expect(moments, torch.float64, "moments")
+    for m in maps:
+        _expect(m, torch.int32, "gene map")
+    n_rows = imp_indptr.numel() - 1
+    with torch.cuda.device(dev):
+        _call(
+            "cm_expr_gene_sums", int(bool(js_pass)), _ptr(imp_indptr), _ptr(imp_cols), _ptr(imp_vals), _dtype_code(imp_vals), n_rows,
+            int(row0), _ptr(orig_indptr), _ptr(orig_cols), _ptr(orig_vals), _dtype_code(orig_vals), _ptr(maps[0]), _ptr(maps[1]),
+            _ptr(maps[2]), _ptr(maps[3]), _ptr(group_of_query), int(n_shared), _ptr(moments), _ptr(js_out), _stream(),
+        )  # fmt: skip
 
 
 # ------------------------------------------------------------------------------------------------

@@ -51,14 +51,19 @@ class NeighborsResults:
             raise ValueError("Indices and distances must have the same shape.")  # knn.py:46-47
         self._dist_host = self._idx_host = None
         self._dist_dev = self._idx_dev = None
-        if isinstance(distances, torch.Tensor):
-            self._dist_dev = distances
+        # The kernels read the device arrays through raw pointers as float64 / int64: tensors of another type
+        # (float32 distances, int32 indices: what faiss-GPU or torch.topk return) are converted here, and CPU
+        # tensors are host data, not the device copy.
+        if isinstance(distances, torch.Tensor) and distances.is_cuda:
+            self._dist_dev = distances if distances.dtype == torch.float64 else distances.to(torch.float64)
         else:
-            self._dist_host = np.asarray(distances)
-        if isinstance(indices, torch.Tensor):
-            self._idx_dev = indices
+            self._dist_host = distances.numpy() if isinstance(distances, torch.Tensor) else np.asarray(distances)
+        if isinstance(indices, torch.Tensor) and indices.is_cuda:
+            if indices.dtype.is_floating_point or indices.dtype == torch.bool:
+                raise TypeError(f"indices must be an integer tensor, got {indices.dtype}")
+            self._idx_dev = indices if indices.dtype == torch.int64 else indices.to(torch.int64)
         else:
-            self._idx_host = np.asarray(indices)
+            self._idx_host = indices.numpy() if isinstance(indices, torch.Tensor) else np.asarray(indices)
         self._shape2 = tuple(int(s) for s in indices.shape)
         self.n_targets = int(n_targets) if n_targets is not None else self._shape2[0]  # knn.py:49-51
         self._cache: dict = {}

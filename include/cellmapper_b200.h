@@ -49,8 +49,12 @@ enum cm_dist_mode {
 
 /* search algorithm selector for cm_knn_search */
 enum cm_knn_algo {
-  CM_KNN_AUTO = 0,     /* tcgen05 split-fp16 GEMM + exact re-rank, exact f64 fallback per row    */
-  CM_KNN_EXACT_F64 = 1 /* SIMT float64 brute force only (ground truth / fallback kernel)         */
+  CM_KNN_AUTO = 0,             /* tcgen05 split-fp16 GEMM + exact re-rank, exact f64 fallback per row; reference
+                                  cells that a triangle-inequality bound rules out are skipped (still exact)  */
+  CM_KNN_EXACT_F64 = 1,        /* SIMT float64 brute force only (ground truth / fallback kernel)             */
+  CM_KNN_TENSOR_EXHAUSTIVE = 2 /* the tensor-core path with the pruning switched off: every (query tile,
+                                  reference tile) pair is multiplied.  Same results as CM_KNN_AUTO; it is the
+                                  worst case of AUTO (structureless data) on demand, for measurement          */
 };
 
 int cm_abi_version(void);
@@ -179,8 +183,58 @@ int cm_spmm_csr_dense(const int32_t* indptr, const int32_t* cols, const float* v
 int cm_spgemm_count(const int32_t* m_indptr, const int32_t* m_cols, int64_t n_q, const int64_t* x_indptr,
                     const int32_t* x_cols, int32_t n_genes, int32_t* out_row_nnz, void* stream);
 int cm_spgemm_fill(const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
-                   const int64_t* x_indptr, const int32_t* x_cols, const float* x_vals, int32_t n_genes,
-                   const int64_t* out_indptr, int32_t* out_cols, float* out_vals, void* stream);
+                   const int64_t* x_indptr, const int32_t* x_cols, const void* x_vals, int dtype, int32_t n_genes,
+                   const int64_t* out_indptr, int32_t* out_cols, void* out_vals, void* stream);
+/* dtype (cm_dtype) is the type of x_vals AND out_vals: CM_F32 for float32 layers; CM_F64 for float64 / integer layers
+ * (converted to float64 by the caller), for which scipy promotes the float32 mapping matrix and returns float64.
+ * Row chunks: both calls index m_cols / m_vals through the VALUES of m_indptr, so passing m_indptr + row_lo with
+ * n_q = rows of the chunk (and an out_indptr that starts at 0 for the chunk) processes the rows [row_lo, row_lo + n_q)
+ * into a bounded buffer -- the 40-80 GB result of BASELINE config 4 never has to exist at once
+ * (cellmapper_b200/device.py: spgemm_chunks). */
+
+/* ---------------------------------------------------------------------------------------------
+ * Consumers of the path ("next" rows of the scope table): presence score and expression-transfer evaluation.
+ * ------------------------------------------------------------------------------------------- */
+/* Presence score: column sums of the UN-normalised gaussian graph over the reference cells
+ * [target_lo, target_lo + n_targets) -- `conn.sum(axis=0)` and, per query group, `conn[mask, :].sum(axis=0)`
+ * (src/cellmapper/model/evaluate.py:453-474).  dist / idx: the (n_q, k) neighbour arrays (global reference indices),
+ * stats3: cm_edge_stats.  Terms are added in ascending query row (scipy's order) through reverse neighbour lists:
+ * deterministic, no floating-point atomics.  out_all (n_targets) float64; out_groups (n_targets, n_groups) float32
+ * row-major (float64 sums, rounded like the reference's float32 score matrix) or NULL; group_of_query (n_q) int32
+ * in [0, n_groups) or negative = in no group.  A rank of a reference-sharded run passes its own block as targets. */
+size_t cm_presence_workspace_bytes(int64_t n_q, int k, int64_t n_targets);
+int cm_presence_scores(const double* dist, const int64_t* idx, int64_t n_q, int k, const double* stats3, int64_t target_lo,
+                       int64_t n_targets, const int32_t* group_of_query, int n_groups, double* out_all, float* out_groups,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Order statistics of a strided column (element i at x[i * stride], dtype cm_dtype): out[j] = the ranks_host[j]-th
+ * smallest (0-based), n_ranks <= 8, by radix selection.  These are the entries np.percentile interpolates between
+ * (evaluate.py:512); the interpolation itself is two flops on the host.  workspace >= CM_SELECT_WORKSPACE_BYTES. */
+#define CM_SELECT_WORKSPACE_BYTES 16384
+int cm_select_ranks(const void* x, int dtype, int64_t n, int64_t stride, const int64_t* ranks_host, int n_ranks, void* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* x <- log1p(x) (evaluate.py:508-509) and x <- (clip(x, lo, hi) - mn) / (mx - mn), 0 when mx <= mn
+ * (evaluate.py:511-519; clip != 0 applies np.clip first), in place on a strided column in its own type. */
+int cm_log1p_inplace(void* x, int dtype, int64_t n, int64_t stride, void* stream);
+int cm_clip_minmax_inplace(void* x, int dtype, int64_t n, int64_t stride, double lo, double hi, double mn, double mx, int clip,
+                           void* stream);
+
+/* evaluate_expression_transfer (evaluate.py:236-323) without densifying either matrix: per shared gene, sums over
+ * the cells of a chunk of the imputed CSR (rows [0, n_rows) = query cells [row0, row0 + n_rows), ascending reference
+ * gene columns, cm_dtype imp_dtype) against the original query expression (CSR over ALL query cells, query gene
+ * columns, ascending).  Gene maps (int32): imp_to_shared / orig_to_shared = slot among the n_shared shared genes or -1;
+ * orig_to_imp / imp_to_orig = the same gene's column in the other matrix or -1.  group_of_query (n_query) or NULL.
+ * js_pass = 0: accumulate into moments [n_groups + 1][CM_MOMENTS][n_shared] float64 (group 0 = all cells; slots:
+ *   1 sum x, 2 sum x^2, 3 sum y, 4 sum y^2, 5 sum xy, 6 sum max(x,0), 7 sum max(y,0); x = original, y = imputed;
+ *   slot 0 is left to the caller (cell counts)) -- Pearson and the z-scored RMSE follow from these.
+ * js_pass = 1: given finished moments, accumulate the Jensen-Shannon sums into js_out [n_groups + 1][n_shared].
+ * The caller zero-initialises both arrays; chunks accumulate (float64 atomics). */
+#define CM_MOMENTS 8
+int cm_expr_gene_sums(int js_pass, const int64_t* imp_indptr, const int32_t* imp_cols, const void* imp_vals, int imp_dtype,
+                      int64_t n_rows, int64_t row0, const int64_t* orig_indptr, const int32_t* orig_cols,
+                      const void* orig_vals, int orig_dtype, const int32_t* imp_to_shared, const int32_t* orig_to_shared,
+                      const int32_t* orig_to_imp, const int32_t* imp_to_orig, const int32_t* group_of_query, int64_t n_shared,
+                      double* moments, double* js_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * measurement hooks (bench.py)
@@ -201,12 +255,15 @@ int cm_profile_last_knn_ms(float* out4_host);
 int cm_debug_mma_tile(const void* Q, int64_t n_q, const void* R, int64_t n_r, int d, int dtype, float* out,
                       float* scale_out, void* workspace, size_t workspace_bytes, void* stream);
 
-/* development probes of the tensor-core kernel (results become INVALID): bit 0 skips the epilogue
- * math, bit 1 skips the reference-tile copies.  0 restores normal operation. */
+#ifdef CM_DEV_PROBES
+/* Development builds only (nvcc -DCM_DEV_PROBES, tools/probe_*.py; NOT in the shipping library): probes of
+ * the tensor-core kernel that make results INVALID -- bit 0 skips the epilogue math, bit 1 skips the
+ * reference-tile copies; 0 restores normal operation. */
 int cm_debug_probe_flags(int flags);
 /* device buffer of 8 int64 per CTA of the tensor-core kernel receiving the MMA warp's cycle counters
  * [wait accumulator, wait reference tile, issue, total, tiles]; NULL switches it off. */
 int cm_debug_probe_prof(long long* device_buf);
+#endif
 
 #ifdef __cplusplus
 }

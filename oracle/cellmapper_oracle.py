@@ -62,6 +62,8 @@ __all__ = [
     "presence_scores",
     "process_presence_scores",
     "extract_neighbors_from_distances",
+    "presence_scores_grouped",
+    "expression_transfer_metrics",
     "run_path",
 ]
 
@@ -332,6 +334,63 @@ def presence_scores(distances, indices, n_targets: int, log: bool = False, perce
     conn = connectivities_csr(distances, indices, n_targets, "gaussian")
     raw = np.array(conn.sum(axis=0)).flatten()
     return process_presence_scores(raw, log=log, percentile=percentile)
+
+
+def presence_scores_grouped(distances, indices, n_targets: int, group_labels, log: bool = False, percentile=(1, 99)):
+    """reference: evaluate.py:453-474 with ``groupby``.  Returns (overall float64 (n_r,), per-group float32
+    (n_r, n_groups) in the order of first appearance, group names)."""
+    import pandas as pd
+
+    conn = connectivities_csr(distances, indices, n_targets, "gaussian")
+    overall = process_presence_scores(np.array(conn.sum(axis=0)).flatten(), log=log, percentile=percentile)
+    labels = pd.Series(np.asarray(group_labels, dtype=object))
+    groups = list(labels.unique())
+    mat = np.zeros((n_targets, len(groups)), dtype=np.float32)
+    for i, g in enumerate(groups):
+        mat[:, i] = np.array(conn[(labels == g).values, :].sum(axis=0)).flatten()
+    out = np.empty_like(mat)
+    for i in range(len(groups)):  # column by column in float32, like DataFrame.apply on a float32 frame
+        x = mat[:, i]
+        if log:
+            x = np.log1p(x)
+        if tuple(percentile) != (0, 100):
+            x = np.clip(x, np.percentile(x, percentile[0]), np.percentile(x, percentile[1]))
+        mn, mx = np.min(x), np.max(x)
+        out[:, i] = (x - mn) / (mx - mn) if mx > mn else np.zeros_like(x)
+    return overall, out, groups
+
+
+def expression_transfer_metrics(imputed, original, method: str = "pearson", mask=None) -> np.ndarray:
+    """Per-gene agreement between two aligned (cells x genes) matrices, the way the reference computes it
+    (evaluate.py:275-296 with the metric functions at :22-64): densify, then one scipy call per gene.
+    float32 result, NaN where the metric is undefined.  ``mask``: boolean cell selection (a ``groupby`` group)."""
+    import warnings
+
+    from scipy.spatial.distance import jensenshannon
+    from scipy.stats import pearsonr
+
+    a = original.toarray() if issparse(original) else np.asarray(original)
+    b = imputed.toarray() if issparse(imputed) else np.asarray(imputed)
+    if mask is not None:
+        a, b = a[mask], b[mask]
+
+    def js(p, q):
+        p, q = np.clip(p, 0, None), np.clip(q, 0, None)
+        if p.sum() == 0 or q.sum() == 0:
+            return np.nan
+        return jensenshannon(p, q, base=10)
+
+    def rmse(x, y):
+        def z(v):
+            sd = np.std(v, ddof=0)
+            return (v - np.mean(v)) / (sd if sd != 0 else 1)
+
+        return np.sqrt(np.mean((z(x) - z(y)) ** 2))
+
+    fn = {"pearson": lambda x, y: pearsonr(x, y)[0], "js": js, "rmse": rmse}[method]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.array([fn(a[:, i], b[:, i]) for i in range(a.shape[1])], dtype=np.float32)
 
 
 def extract_neighbors_from_distances(dm, include_self=None):

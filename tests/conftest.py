@@ -93,3 +93,14 @@ def neighbours_match(idx, dist, ref_idx, ref_dist, rel=1e-6):
         if not ok:
             bad += 1
     return bad
+
+
+def agreeing_rows(idx, ref_idx, max_differing=0.001):
+    """Rows whose neighbour lists equal the reference's entry for entry.  ASSERTS that at most ``max_differing``
+    (a fraction of the rows) differ -- rows that order a (near-)tie differently; ``neighbours_match`` is the check
+    that those differences are legitimate -- so that the value comparisons made on the returned rows cannot be
+    skipped silently."""
+    same = (np.asarray(idx) == np.asarray(ref_idx)).all(axis=1)
+    n_bad = int((~same).sum())
+    assert n_bad <= max_differing * same.shape[0], f"{n_bad} of {same.shape[0]} neighbour rows differ from the reference"
+    return np.flatnonzero(same)

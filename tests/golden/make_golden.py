@@ -214,10 +214,94 @@ def case_reference_unit_fixtures(name):
     print(name, "ok")
 
 
+def case_evaluate(name, n_q, n_r, d, k, n_comp, n_genes):
+    """Consumers of the path: evaluate_expression_transfer (evaluate.py:236-424: pearson / rmse / js, groupby,
+    test_var_key), estimate_presence_score with groupby / log / percentile (evaluate.py:426-521), and an
+    integer-valued layer (scipy promotes M @ X to float64)."""
+    CellMapper, Neighbors, NeighborsResults, AnnData = reference_shim.load()
+    xr, xq, cr, cq, labels, umap, score, expr = build_pair(n_q, n_r, d, n_comp, n_genes)
+    rng = np.random.default_rng(21)
+    ref_genes = np.array([f"g{i}" for i in range(n_genes)])
+    # query genes: a shuffled subset of the reference's plus genes the reference does not have
+    n_sh = (2 * n_genes) // 3
+    q_genes = np.concatenate([rng.permutation(ref_genes)[:n_sh], np.array([f"q_only{i}" for i in range(17)])])
+    q_genes = rng.permutation(q_genes)
+    # original query expression: the (noisy) expression of a same-type reference cell, so correlations are non-trivial
+    donor = np.array([rng.choice(np.flatnonzero(cr == c)) for c in cq])
+    dense = np.asarray(expr[donor].todense()).astype(np.float32)
+    dense = dense * (rng.random(dense.shape) < 0.8) + (rng.random(dense.shape) < 0.02) * rng.random(dense.shape).astype(np.float32)
+    col_of = {g: i for i, g in enumerate(ref_genes)}
+    qx = np.zeros((n_q, len(q_genes)), dtype=np.float32)
+    for j, g in enumerate(q_genes):
+        if g in col_of:
+            qx[:, j] = dense[:, col_of[g]]
+        else:
+            qx[:, j] = rng.random(n_q) < 0.1
+    qx[:, 3] = 0.0  # a gene without any mass in the query: NaN metrics
+    qx_csr = csr_matrix(qx)
+    batch = np.array(["b%d" % b for b in rng.integers(0, 3, n_q)], dtype=object)
+    is_test = rng.random(len(q_genes)) < 0.5
+    counts = csr_matrix((np.rint(np.expm1(expr.data) * 3).astype(np.int64), expr.indices, expr.indptr), shape=expr.shape)
+    ref = AnnData(
+        X=expr,
+        obs=pd.DataFrame({"celltype": pd.Categorical(labels)}, index=[f"r{i}" for i in range(n_r)]),
+        var=pd.DataFrame(index=ref_genes),
+        obsm={"X_joint": xr},
+        layers={"counts": counts},
+    )
+    qry = AnnData(
+        X=qx_csr,
+        obs=pd.DataFrame({"batch": pd.Categorical(batch)}, index=[f"q{i}" for i in range(n_q)]),
+        var=pd.DataFrame({"is_test": is_test}, index=q_genes),
+        obsm={"X_joint": xq},
+    )
+    cm = CellMapper(qry, ref)
+    cm.map(use_rep="X_joint", layer_key="X", n_neighbors=k, knn_method="sklearn", only_yx=True, mapping_method="gaussian")
+    out = dict(xr=xr, xq=xq, labels=labels.astype(str), k=np.int64(k), ref_genes=ref_genes.astype(str), q_genes=q_genes.astype(str),
+               batch=batch.astype(str), is_test=is_test, indices=cm.knn.yx.indices, distances=cm.knn.yx.distances)
+    out.update(csr_parts("expr", expr))
+    out.update(csr_parts("counts", counts))
+    out.update(csr_parts("qx", qx_csr))
+    out.update(csr_parts("imputed", cm.query_imputed.X))
+    import warnings
+
+    for method in ("pearson", "rmse", "js"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cm.evaluate_expression_transfer(layer_key="X", method=method, groupby="batch", test_var_key="is_test")
+        out[f"metric_{method}"] = qry.var[f"metric_{method}"].to_numpy().astype(np.float64)
+        out[f"valid_{method}"] = qry.var[f"_is_valid_test_gene_{method}"].to_numpy().astype(bool)
+        out[f"groups_{method}"] = qry.varm[f"metric_{method}"].to_numpy().astype(np.float64)
+        out[f"group_names_{method}"] = np.array([str(c) for c in qry.varm[f"metric_{method}"].columns])
+        out[f"average_{method}"] = np.float64(cm.expression_transfer_metrics["average"])
+        out[f"n_test_{method}"] = np.int64(cm.expression_transfer_metrics["n_test_genes"])
+    cm.estimate_presence_score(groupby="batch")
+    out["presence_all"] = ref.obs["presence_score"].to_numpy()
+    out["presence_groups"] = ref.obsm["presence_score"].to_numpy()
+    out["presence_group_names"] = np.array([str(c) for c in ref.obsm["presence_score"].columns])
+    out["presence_groups_dtype"] = np.array(str(ref.obsm["presence_score"].dtypes.iloc[0]))
+    cm.estimate_presence_score(groupby="batch", key_added="p_log", log=True, percentile=(5, 90))
+    out["presence_all_log"] = ref.obs["p_log"].to_numpy()
+    out["presence_groups_log"] = ref.obsm["p_log"].to_numpy()
+    cm.estimate_presence_score(groupby="batch", key_added="p_raw", percentile=(0, 100))
+    out["presence_all_raw"] = ref.obs["p_raw"].to_numpy()
+    out["presence_groups_raw"] = ref.obsm["p_raw"].to_numpy()
+    cm.map_layers("counts")
+    imp = cm.query_imputed.X
+    out["imputed_counts_dtype"] = np.array(str(imp.dtype))
+    out.update(csr_parts("imputed_counts", imp))
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+    print(name, "ok", {m: float(out[f"average_{m}"]) for m in ("pearson", "rmse", "js")}, out["presence_groups_dtype"], out["imputed_counts_dtype"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "evaluate":  # only the newest fixture
+        case_evaluate("evaluate", n_q=400, n_r=900, d=30, k=15, n_comp=6, n_genes=240)
+        sys.exit(0)
     case_query_to_reference("q2r_d30", n_q=300, n_r=700, d=30, k=30, n_comp=7, n_genes=200)
     case_query_to_reference("q2r_d10_kdtree", n_q=200, n_r=500, d=10, k=15, n_comp=5, n_genes=64, padded=False)
     case_query_to_reference("q2r_d50", n_q=257, n_r=1031, d=50, k=30, n_comp=12, n_genes=300, padded=False)
     case_four_graphs("four_graphs", n_q=300, n_r=400, d=20, k=10, n_comp=6)
     case_ragged("ragged_selfmap", n=300, d=16, k=12)
     case_reference_unit_fixtures("reference_unit_fixtures")
+    case_evaluate("evaluate", n_q=400, n_r=900, d=30, k=15, n_comp=6, n_genes=240)

@@ -14,6 +14,8 @@ HEADER = os.path.join(ROOT, "include", "cellmapper_b200.h")
 def declared_functions():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    # development-build-only probes (-DCM_DEV_PROBES) are not part of the shipping ABI
+    text = re.sub(r"#ifdef CM_DEV_PROBES.*?#endif", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(cm_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -93,3 +95,9 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(src), f"{f} imports the oracle or scikit-learn"
+
+
+def test_shipping_library_has_no_debug_switches(lib):
+    """The process-global development probes exist only in -DCM_DEV_PROBES builds (tools/), never in the product."""
+    for name in ("cm_debug_probe_flags", "cm_debug_probe_prof"):
+        assert not hasattr(lib, name), f"{name} is exported by the shipping library"

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import numpy as np
 import pytest
-from conftest import assert_csr_equal, golden_csr, load_golden, neighbours_match
+from conftest import agreeing_rows, assert_csr_equal, golden_csr, load_golden, neighbours_match
 
 pytestmark = pytest.mark.gpu
 
@@ -196,11 +196,7 @@ def test_pruned_search_is_exact(torch_cuda, name):
     qd, rd = dev(torch, q), dev(torch, r)
     lib = _lib.load()
     dd, ii, st = device.knn_search(qd, rd, k, return_stats=True)
-    try:
-        lib.cm_debug_probe_flags(32)  # exhaustive scan, no pruning
-        de, ie, se = device.knn_search(qd, rd, k, return_stats=True)
-    finally:
-        lib.cm_debug_probe_flags(0)
+    de, ie, se = device.knn_search(qd, rd, k, return_stats=True, algo=_lib.KNN_TENSOR_EXHAUSTIVE)  # no pruning
     dx, ix = device.knn_search(qd, rd, k, algo=_lib.KNN_EXACT_F64)
     dd, ii, de, ie, dx, ix = (t.cpu().numpy() for t in (dd, ii, de, ie, dx, ix))
     n_pairs = -(-q.shape[0] // 128) * -(-r.shape[0] // 128)
@@ -460,19 +456,21 @@ def test_cellmapper_map_matches_reference(torch_cuda, name, kernel):
     mm = cm.mapping_matrix
     refmm = golden_csr(g, f"mm_{kernel}")
     assert mm.dtype == np.float32 and mm.shape == refmm.shape
-    if np.array_equal(cm.knn.yx.indices, g["indices"]):
-        np.testing.assert_array_equal(mm.indices, refmm.indices)
-        rt = 1e-3 if kernel == "inverse_distance" else 1e-6
-        np.testing.assert_allclose(mm.data, refmm.data, rtol=rt)
-        # transferred labels: bit-exact given equal neighbours
-        np.testing.assert_array_equal(qry.obs["celltype_pred"].to_numpy().astype(str), g[f"pred_{kernel}"])
-        np.testing.assert_allclose(qry.obs["celltype_conf"].to_numpy(), g[f"conf_{kernel}"], rtol=1e-5)
-        np.testing.assert_allclose(qry.obs["score_pred"].to_numpy(), g[f"score_{kernel}"], rtol=1e-5)
-        np.testing.assert_allclose(qry.obs["score64_pred"].to_numpy(), g[f"score64_{kernel}"], rtol=1e-5)
-        np.testing.assert_allclose(qry.obsm["X_umap_pred"], g[f"umap_{kernel}"], rtol=1e-5, atol=1e-6)
-        np.testing.assert_allclose(qry.obsm["X_umap64_pred"], g[f"umap64_{kernel}"], rtol=1e-5, atol=1e-6)
-        imp = cm.query_imputed.X
-        assert_csr_equal(imp, golden_csr(g, f"imputed_{kernel}"), rtol=1e-5, atol=1e-7, structure=False)
+    # Values are compared on the rows whose neighbour lists equal the reference's entry for entry; the number of
+    # rows that order a (near-)tie differently is bounded (unconditional: one flipped tie must not skip the checks).
+    rows = agreeing_rows(cm.knn.yx.indices, g["indices"], max_differing=0.001)
+    np.testing.assert_array_equal(mm[rows].indices, refmm[rows].indices)
+    rt = 1e-3 if kernel == "inverse_distance" else 1e-6
+    np.testing.assert_allclose(mm[rows].data, refmm[rows].data, rtol=rt)
+    # transferred labels: bit-exact given equal neighbours
+    np.testing.assert_array_equal(qry.obs["celltype_pred"].to_numpy().astype(str)[rows], g[f"pred_{kernel}"][rows])
+    np.testing.assert_allclose(qry.obs["celltype_conf"].to_numpy()[rows], g[f"conf_{kernel}"][rows], rtol=1e-5)
+    np.testing.assert_allclose(qry.obs["score_pred"].to_numpy()[rows], g[f"score_{kernel}"][rows], rtol=1e-5)
+    np.testing.assert_allclose(qry.obs["score64_pred"].to_numpy()[rows], g[f"score64_{kernel}"][rows], rtol=1e-5)
+    np.testing.assert_allclose(qry.obsm["X_umap_pred"][rows], g[f"umap_{kernel}"][rows], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(qry.obsm["X_umap64_pred"][rows], g[f"umap64_{kernel}"][rows], rtol=1e-5, atol=1e-6)
+    imp = cm.query_imputed.X
+    assert_csr_equal(imp[rows], golden_csr(g, f"imputed_{kernel}")[rows], rtol=1e-5, atol=1e-7, structure=False)
     assert str(qry.obs["celltype_pred"].dtype) == "category"
     assert qry.obs["celltype_conf"].dtype == np.float32
     assert qry.obs["score_pred"].dtype == np.float32 and qry.obs["score64_pred"].dtype == np.float64
@@ -481,8 +479,10 @@ def test_cellmapper_map_matches_reference(torch_cuda, name, kernel):
     assert "celltype_pred_colors" in qry.uns
     np.testing.assert_allclose(np.asarray(mm.sum(1)).ravel(), 1.0, atol=1e-6)
     cm.estimate_presence_score()
-    if kernel == "gaussian" and np.array_equal(cm.knn.yx.indices, g["indices"]):
-        np.testing.assert_allclose(ref.obs["presence_score"].to_numpy(), g["presence_score"], atol=1e-9)
+    if kernel == "gaussian":
+        # a row that cuts a tie differently moves at most two reference cells' sums by one edge weight
+        tol = 1e-9 if len(rows) == qry.n_obs else 1e-3
+        np.testing.assert_allclose(ref.obs["presence_score"].to_numpy(), g["presence_score"], atol=tol)
 
 
 def test_spgemm_wide_layer(torch_cuda):
@@ -664,10 +664,12 @@ def test_cellmapper_four_graph_mapping(torch_cuda, method):
     for name in ("xx", "yy", "xy", "yx"):
         res = getattr(cm.knn, name)
         assert neighbours_match(res.indices, res.distances, g[f"{name}_indices"], g[f"{name}_distances"]) == 0
-    same = all(np.array_equal(getattr(cm.knn, n).indices, g[f"{n}_indices"]) for n in ("xx", "yy", "xy", "yx"))
-    if same:
-        assert_csr_equal(cm.mapping_matrix, golden_csr(g, f"mm_{method}"), rtol=1e-6, structure=False)
-        np.testing.assert_array_equal(qry.obs["celltype_pred"].to_numpy().astype(str), g[f"pred_{method}"])
+    # The jaccard counts of a query row depend on the lists of OTHER cells too, so the value checks need all four
+    # graphs to equal the reference's: asserted, not assumed (the golden inputs have no ties inside the top k).
+    for name in ("xx", "yy", "xy", "yx"):
+        np.testing.assert_array_equal(getattr(cm.knn, name).indices, g[f"{name}_indices"], err_msg=name)
+    assert_csr_equal(cm.mapping_matrix, golden_csr(g, f"mm_{method}"), rtol=1e-6, structure=False)
+    np.testing.assert_array_equal(qry.obs["celltype_pred"].to_numpy().astype(str), g[f"pred_{method}"])
     np.testing.assert_allclose(np.asarray(cm.mapping_matrix.sum(1)).ravel(), 1.0, atol=1e-6)
 
 

@@ -101,3 +101,63 @@ def test_finish_distances_matches_kernel_roundings():
     np.testing.assert_allclose(device.finish_distances(d2, _lib.DIST_SQRT_F64).numpy(), np.sqrt(d2.numpy()), rtol=4e-16)
     want = np.sqrt(d2.numpy().astype(np.float32)).astype(np.float64)
     np.testing.assert_allclose(device.finish_distances(d2, _lib.DIST_SKLEARN_F32).numpy(), want, rtol=2e-7)
+
+
+# --------------------------------------------------------------------------------------------
+# np.percentile split into order statistics + interpolation (cellmapper_b200/evaluate.py)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_percentile_plan_reproduces_numpy_bit_for_bit(dtype):
+    from cellmapper_b200.evaluate import percentile_from_order_stats, percentile_plan
+
+    rng = np.random.default_rng(0)
+    for n in [1, 2, 3, 7, 100, 101, 900, 4097, 100_003]:
+        x = (rng.standard_normal(n) * 10).astype(dtype)
+        xs = np.sort(x)
+        for q in [0, 1, 5, 25, 50, 90, 99, 99.9, 100, 33.3]:
+            a, b, gamma = percentile_plan(n, q, dtype)
+            got = percentile_from_order_stats(xs[a], xs[b], gamma)
+            want = np.percentile(x, q)
+            assert got.dtype == want.dtype == np.dtype(dtype)
+            assert got == want, (n, q, got, want)
+    # float32 virtual indices of a very long column round differently from float64: follow numpy there too
+    n = 10_000_019
+    for q in [1, 99]:
+        a, b, gamma = percentile_plan(n, q, np.float32)
+        ftype = np.float32
+        vi = (n - 1) * np.true_divide(q, ftype(100))
+        assert a == int(np.floor(vi)) and b == a + 1 and type(gamma) is np.float32
+
+
+@pytest.mark.parametrize("method", ["pearson", "rmse", "js"])
+def test_metric_from_sums_matches_reference(method):
+    """The closed forms that turn per-gene sums into the reference's per-gene metrics (host side of
+    evaluate_expression_transfer), fed with sums computed by numpy from the golden matrices."""
+    from cellmapper_b200.evaluate import _metric_from_sums
+
+    g = load_golden("evaluate")
+    ref_genes, q_genes = pd.Index(g["ref_genes"]), pd.Index(g["q_genes"])
+    shared = ref_genes.intersection(q_genes)
+    y = golden_csr(g, "imputed")[:, ref_genes.get_indexer(shared)].toarray().astype(np.float64)
+    x = golden_csr(g, "qx")[:, q_genes.get_indexer(shared)].toarray().astype(np.float64)
+    names = [str(n) for n in g[f"group_names_{method}"]]
+    masks = [np.ones(x.shape[0], bool)] + [g["batch"] == n for n in names]
+    mom = np.zeros((len(masks), 8, x.shape[1]))
+    js = np.zeros((len(masks), x.shape[1]))
+    for s, m in enumerate(masks):
+        xs, ys = x[m], y[m]
+        mom[s, 1], mom[s, 2], mom[s, 3], mom[s, 4], mom[s, 5] = xs.sum(0), (xs * xs).sum(0), ys.sum(0), (ys * ys).sum(0), (xs * ys).sum(0)
+        mom[s, 6], mom[s, 7] = np.clip(xs, 0, None).sum(0), np.clip(ys, 0, None).sum(0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            p, q = np.clip(xs, 0, None) / mom[s, 6], np.clip(ys, 0, None) / mom[s, 7]
+            mm = 0.5 * (p + q)
+            js[s] = np.nansum(np.where(p > 0, p * np.log(p / mm), 0.0) + np.where(q > 0, q * np.log(q / mm), 0.0), axis=0)
+    counts = np.array([m.sum() for m in masks], dtype=np.float64)
+    got = _metric_from_sums(method, mom, counts, js)
+    pos = q_genes.get_indexer(shared)
+    want = np.stack([g[f"metric_{method}"][pos]] + [g[f"groups_{method}"][pos, i] for i in range(len(names))])
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    # the reference evaluates scipy's formulas in float32 (both inputs are float32 arrays): 1e-4 absolute
+    np.testing.assert_allclose(got[ok], want[ok], atol=2e-4 if method != "js" else 5e-4)

@@ -180,3 +180,52 @@ def test_oracle_against_live_reference():
     np.testing.assert_array_equal(out["pred"].astype(str), qry.obs["celltype_pred"].to_numpy().astype(str))
     np.testing.assert_array_equal(out["conf"], qry.obs["celltype_conf"].to_numpy())
     np.testing.assert_array_equal(out["obsm_pred"], qry.obsm["X_umap_pred"])
+
+
+# --------------------------------------------------------------------------------------------
+# consumers of the path (evaluate.npz: evaluate_expression_transfer + presence score with groups)
+# --------------------------------------------------------------------------------------------
+def _aligned_evaluate_matrices(g):
+    """(imputed, original) restricted to the shared genes in the order the reference uses (evaluate.py:343-350)."""
+    import pandas as pd
+
+    ref_genes, q_genes = pd.Index(g["ref_genes"]), pd.Index(g["q_genes"])
+    shared = ref_genes.intersection(q_genes)
+    imp = golden_csr(g, "imputed")[:, ref_genes.get_indexer(shared)]
+    orig = golden_csr(g, "qx")[:, q_genes.get_indexer(shared)]
+    return imp, orig, shared, q_genes
+
+
+@pytest.mark.parametrize("method", ["pearson", "rmse", "js"])
+def test_expression_transfer_metrics_match_reference(method):
+    g = load_golden("evaluate")
+    imp, orig, shared, q_genes = _aligned_evaluate_matrices(g)
+    pos = q_genes.get_indexer(shared)
+    got = orc.expression_transfer_metrics(imp, orig, method)
+    np.testing.assert_array_equal(got.astype(np.float64), g[f"metric_{method}"][pos])
+    assert np.isnan(g[f"metric_{method}"][np.setdiff1d(np.arange(len(q_genes)), pos)]).all()
+    for gi, name in enumerate(g[f"group_names_{method}"]):
+        got = orc.expression_transfer_metrics(imp, orig, method, mask=g["batch"] == name)
+        np.testing.assert_array_equal(got.astype(np.float64), g[f"groups_{method}"][pos, gi])
+    valid = g[f"valid_{method}"]
+    assert int(valid.sum()) == int(g[f"n_test_{method}"])
+    np.testing.assert_allclose(np.mean(g[f"metric_{method}"][valid]), float(g[f"average_{method}"]), rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag,log,pct", [("", False, (1, 99)), ("_log", True, (5, 90)), ("_raw", False, (0, 100))])
+def test_presence_scores_with_groups_match_reference(tag, log, pct):
+    g = load_golden("evaluate")
+    overall, groups, names = orc.presence_scores_grouped(g["distances"], g["indices"], g["xr"].shape[0], g["batch"], log=log, percentile=pct)
+    assert [str(n) for n in names] == [str(n) for n in g["presence_group_names"]]
+    np.testing.assert_array_equal(overall, g[f"presence_all{tag}"])
+    assert str(g["presence_groups_dtype"]) == "float32" and groups.dtype == np.float32
+    np.testing.assert_array_equal(groups, g[f"presence_groups{tag}"])
+
+
+def test_integer_layer_is_transferred_in_float64():
+    """scipy promotes the float32 mapping matrix with an integer layer: float64 result (cellmapper.py:372-373)."""
+    g = load_golden("evaluate")
+    m = orc.mapping_matrix_from_neighbors(g["distances"], g["indices"], g["xr"].shape[0], "gaussian")
+    out = orc.map_layers(m, golden_csr(g, "counts"))
+    assert str(g["imputed_counts_dtype"]) == "float64" and out.dtype == np.float64
+    assert_csr_equal(out, golden_csr(g, "imputed_counts"))
