@@ -28,6 +28,7 @@ __all__ = [
     "allreduce_sum",
     "reference_sharded_search",
     "knn_reference_sharded",
+    "presence_reference_sharded",
     "gather_rows",
     "upload_replicated",
     "assign_reference_sharded",
@@ -120,6 +121,28 @@ def knn_reference_sharded(q: torch.Tensor, r_local: torch.Tensor, r_offset: int,
 
     d2, idx = reference_sharded_search(q, r_local, r_offset, k, search, device.knn_merge_topk)
     return device.finish_distances(d2, dist_mode), idx
+
+
+def presence_reference_sharded(q: torch.Tensor, r_local: torch.Tensor, r_offset: int, k: int, dist_mode: int, *,
+                               search_merge: Callable | None = None, edge_stats: Callable | None = None, block_sums: Callable | None = None):
+    """Raw presence score of EVERY reference cell of a row-sharded atlas (BASELINE config 5; evaluate.py:453-457).
+
+    Sharded search + merge (``knn_reference_sharded``: the merged graph is replicated, it is only n_q x k), the
+    bandwidth statistic from the replicated graph (no collective), the column sums of the un-normalised gaussian
+    graph over THIS rank's block of reference cells (``cm_presence_scores`` with a target range), and one all-gather
+    of the blocks (8 bytes per reference cell in total).  Returns (distances, indices, scores float64 (n_r,)), the
+    same on every rank and bit-identical to the single-GPU result: the per-cell sums run in ascending query row.
+    The three compute steps can be injected (CPU tests over gloo); by default they are the CUDA kernels."""
+    if search_merge is None:
+        from . import device
+
+        search_merge = knn_reference_sharded
+        edge_stats = lambda d, i: device.edge_stats(d, i, need_std=False)  # noqa: E731
+        block_sums = lambda d, i, st, n, lo: device.presence_scores(d, i, st, n, target_lo=lo)[0]  # noqa: E731
+    d, i = search_merge(q, r_local, r_offset, k, dist_mode)
+    stats = edge_stats(d, i)
+    local = block_sums(d, i, stats, r_local.shape[0], r_offset)
+    return d, i, gather_rows(local)
 
 
 def gather_rows(t: torch.Tensor, counts: list[int] | None = None) -> torch.Tensor | None:

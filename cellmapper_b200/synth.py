@@ -131,3 +131,45 @@ def sparse_expression(
     m = csr_matrix((data, indices, ip), shape=(n, n_genes))
     m.has_sorted_indices = True
     return m
+
+
+def sparse_expression_torch(comp: np.ndarray, device, n_genes: int = 30_000, mean_nnz: float = 2_000.0,
+                            nnz_clip: tuple[int, int] = (200, 8_000), n_top: int = 2_000, seed: int = 5, chunk: int = 4096):
+    """The distribution of ``sparse_expression`` drawn on a CUDA device with torch's generator, for the shapes where
+    the numpy loop (one Gumbel vector of ``n_genes`` per cell) would take minutes: BASELINE config 4 is 500 k cells x
+    30 k genes x ~2 k nnz = 1e9 entries.  Same construction -- per-cell nnz ~ clip(Poisson), genes by Gumbel top-k
+    without replacement with p ∝ 1/(rank + 50), a per-component permutation of the top ranks, values
+    log1p(1 + Poisson(2)), columns ascending per row -- but not the same random stream (input generation for
+    bench.py only; tests and golden vectors use the numpy version).
+    Returns device tensors (indptr int64 (n+1,), indices int32, data float32)."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    n = int(comp.shape[0])
+    n_comp = int(comp.max()) + 1 if n else 1
+    n_top = min(n_top, n_genes)
+    lo, hi = min(nnz_clip[0], n_genes), min(nnz_clip[1], n_genes)
+    nnz = torch.poisson(torch.full((n,), float(mean_nnz), device=device), generator=gen).clamp_(lo, hi).to(torch.int64)
+    logp = -torch.log(torch.arange(n_genes, device=device, dtype=torch.float32) + 50.0)
+    perms = torch.stack([torch.randperm(n_top, device=device, generator=gen) for _ in range(n_comp)])
+    comp_d = torch.from_numpy(np.ascontiguousarray(comp)).to(device).to(torch.int64)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    torch.cumsum(nnz, 0, out=indptr[1:])
+    total = int(indptr[-1].item())
+    indices = torch.empty(total, dtype=torch.int32, device=device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        u = torch.rand((e - s, n_genes), device=device, generator=gen).clamp_(1e-12, 1.0 - 1e-7)
+        g = logp[None, :] - torch.log(-torch.log(u))  # Gumbel perturbation
+        kmax = int(nnz[s:e].max().item())
+        ranks = torch.topk(g, kmax, dim=1, sorted=True).indices  # per row: genes in order of decreasing key
+        del g, u
+        keep = torch.arange(kmax, device=device)[None, :] < nnz[s:e, None]
+        top = ranks < n_top
+        ranks = torch.where(top, perms[comp_d[s:e]].gather(1, ranks.clamp(max=n_top - 1)), ranks)
+        ranks = torch.where(keep, ranks, torch.full_like(ranks, n_genes))  # dropped slots sort to the end
+        ranks = torch.sort(ranks, dim=1).values
+        indices[indptr[s] : indptr[e]] = ranks[keep.sum(1)[:, None] > torch.arange(kmax, device=device)[None, :]].to(torch.int32)
+    data = torch.log1p(1.0 + torch.poisson(torch.full((total,), 2.0, device=device), generator=gen)).to(torch.float32)
+    return indptr, indices, data

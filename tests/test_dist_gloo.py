@@ -69,6 +69,18 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         return torch.from_numpy(key[rows, order]), torch.from_numpy(ci2[rows, order])
 
     md, mi = cmd.reference_sharded_search(torch.from_numpy(xq), torch.from_numpy(xr[rlo:rhi]), rlo, k, search, merge)
+    # ---- reference-sharded presence score (BASELINE config 5): merged graph replicated, every rank sums the columns
+    # of ITS block of reference cells, all-gather of the blocks (uneven: 1203 rows over 2 ranks)
+    def block_sums(dd, ii, st, n_loc, lo_):
+        conn = orc.connectivities_csr(dd.numpy(), ii.numpy(), xr.shape[0], "gaussian")
+        return torch.from_numpy(np.asarray(conn.sum(axis=0)).ravel()[lo_ : lo_ + n_loc].copy())
+
+    pd_, pi_, presence = cmd.presence_reference_sharded(
+        torch.from_numpy(xq), torch.from_numpy(xr[rlo:rhi]), rlo, k, 0,
+        search_merge=lambda q, rl, off, kk, mode: cmd.reference_sharded_search(q, rl, off, kk, search, merge),
+        edge_stats=lambda dd, ii: None, block_sums=block_sums)
+    assert torch.equal(pi_, mi) and presence.shape == (xr.shape[0],)
+
     # ---- reference-sharded expression transfer: partial CSR x CSR products, all-gather, per-block sum
     import scipy.sparse as sp
 
@@ -131,7 +143,7 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
     if rank == 0:
         np.savez(
             os.path.join(out_dir, "out.npz"), w=gathered_w.numpy(), i=gathered_i.numpy(), mean=mean, std=std,
-            md=md.numpy(), mi=mi.numpy(),
+            md=md.numpy(), mi=mi.numpy(), presence=presence.numpy(),
         )  # fmt: skip
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
@@ -174,3 +186,6 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     gd, gi = orc.bruteforce_knn_f64(xr, xq, 15)
     np.testing.assert_array_equal(out["mi"], gi)
     np.testing.assert_allclose(out["md"], gd, rtol=1e-15)
+    # sharded presence sums == column sums of the global graph
+    conn = orc.connectivities_csr(gd, gi, xr.shape[0], "gaussian")
+    np.testing.assert_array_equal(out["presence"], np.asarray(conn.sum(axis=0)).ravel())

@@ -691,3 +691,219 @@ def test_self_mapping_identity(torch_cuda):
     CellMapper(ad).map(use_rep="X_joint", obs_keys="celltype", n_neighbors=1, only_yx=False, mapping_method="jaccard")
     np.testing.assert_array_equal(ad.obs["celltype_pred"].to_numpy().astype(str), g["labels"])
     np.testing.assert_array_equal(ad.obs["celltype_pred"].to_numpy().astype(str), g["self_pred"])
+
+
+# --------------------------------------------------------------------------------------------
+# consumers of the path: selection / presence score with groups / expression-transfer evaluation / streamed layers
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_select_ranks_matches_sort(torch_cuda, dtype):
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 33, 1000, 250_001):
+        x = (rng.standard_normal(n) * 7).astype(dtype)
+        x[rng.integers(0, n, max(1, n // 10))] = 0.0  # ties, and both signs around them
+        if n > 40:
+            x[:20] = -0.0
+        ranks = sorted({0, n - 1, n // 2, n // 100, (99 * n) // 100, min(n - 1, (99 * n) // 100 + 1)})
+        got = device.select_ranks(dev(torch, x), ranks).cpu().numpy()
+        np.testing.assert_array_equal(got, np.sort(x)[ranks])
+    # a strided column of a row-major matrix (the per-group presence scores)
+    m = rng.random((5_000, 7)).astype(dtype)
+    md = dev(torch, m)
+    for c in (0, 3, 6):
+        got = device.select_ranks(md[:, c], [0, 49, 50, 4_949, 4_950, 4_999]).cpu().numpy()
+        np.testing.assert_array_equal(got, np.sort(m[:, c])[[0, 49, 50, 4_949, 4_950, 4_999]])
+
+
+def make_evaluate_adatas(g):
+    import pandas as pd
+
+    from cellmapper_b200._anndata import AnnData
+
+    n_r, n_q = g["xr"].shape[0], g["xq"].shape[0]
+    ref = AnnData(
+        X=golden_csr(g, "expr").astype(np.float32),
+        obs=pd.DataFrame({"celltype": pd.Categorical(g["labels"])}, index=[f"r{i}" for i in range(n_r)]),
+        var=pd.DataFrame(index=g["ref_genes"]),
+        obsm={"X_joint": g["xr"]},
+        layers={"counts": golden_csr(g, "counts")},
+    )
+    qry = AnnData(
+        X=golden_csr(g, "qx").astype(np.float32),
+        obs=pd.DataFrame({"batch": pd.Categorical(g["batch"])}, index=[f"q{i}" for i in range(n_q)]),
+        var=pd.DataFrame({"is_test": g["is_test"]}, index=g["q_genes"]),
+        obsm={"X_joint": g["xq"]},
+    )
+    return qry, ref
+
+
+def test_presence_score_with_groups_matches_reference(torch_cuda):
+    """estimate_presence_score(groupby=...) on the device == the unmodified reference (evaluate.py:426-521):
+    overall float64 column, float32 per-group frame in order of first appearance, log / percentile variants."""
+    from cellmapper_b200 import CellMapper
+
+    g = load_golden("evaluate")
+    qry, ref = make_evaluate_adatas(g)
+    cm = CellMapper(qry, ref)
+    cm.compute_neighbors(n_neighbors=int(g["k"]), use_rep="X_joint", only_yx=True)
+    np.testing.assert_array_equal(cm.knn.yx.indices, g["indices"])  # every score depends on every query row
+    for tag, kw in (("", {}), ("_log", dict(log=True, percentile=(5, 90))), ("_raw", dict(percentile=(0, 100)))):
+        cm.estimate_presence_score(groupby="batch", key_added="p" + tag, **kw)
+        assert ref.obs["p" + tag].dtype == np.float64
+        np.testing.assert_allclose(ref.obs["p" + tag].to_numpy(), g[f"presence_all{tag}"], rtol=0, atol=1e-12)
+        frame = ref.obsm["p" + tag]
+        assert [str(c) for c in frame.columns] == [str(c) for c in g["presence_group_names"]]
+        assert all(str(t) == "float32" for t in frame.dtypes)
+        np.testing.assert_allclose(frame.to_numpy(), g[f"presence_groups{tag}"], rtol=0, atol=3e-7)
+    # deterministic: reverse-list sums, no floating-point atomics
+    a, ga = cm.presence_scores_device(dev(torch_cuda, pd_codes(qry.obs["batch"])), 3)
+    b, gb = cm.presence_scores_device(dev(torch_cuda, pd_codes(qry.obs["batch"])), 3)
+    assert torch_cuda.equal(a, b) and torch_cuda.equal(ga, gb)
+    # a block of the reference (what a rank of a reference-sharded run computes) == the same rows of the whole
+    c, gc = cm.presence_scores_device(dev(torch_cuda, pd_codes(qry.obs["batch"])), 3, target_lo=100, n_targets=333)
+    assert torch_cuda.equal(c, a[100:433]) and torch_cuda.equal(gc, ga[100:433])
+
+
+def pd_codes(series):
+    import pandas as pd
+
+    return pd.factorize(series)[0].astype(np.int32)
+
+
+@pytest.mark.parametrize("method", ["pearson", "rmse", "js"])
+@pytest.mark.parametrize("streamed", [False, True])
+def test_evaluate_expression_transfer_matches_reference(torch_cuda, method, streamed):
+    """Per-gene agreement of imputed and original expression from sums accumulated on the device -- from
+    query_imputed like the reference, or streamed out of the CSR x CSR kernel in small chunks without ever holding the
+    imputed matrix -- against the unmodified reference's values (scipy on densified float32 columns)."""
+    from cellmapper_b200 import CellMapper
+
+    g = load_golden("evaluate")
+    qry, ref = make_evaluate_adatas(g)
+    cm = CellMapper(qry, ref)
+    cm.compute_neighbors(n_neighbors=int(g["k"]), use_rep="X_joint", only_yx=True)
+    cm.compute_mapping_matrix("gaussian")
+    rows = agreeing_rows(cm.knn.yx.indices, g["indices"], max_differing=0.0)
+    assert len(rows) == qry.n_obs
+    if streamed:
+        cm.evaluate_expression_transfer(layer_key="X", method=method, groupby="batch", test_var_key="is_test", impute_key="X", max_chunk_nnz=5_000)
+        assert cm.query_imputed is None
+    else:
+        cm.map_layers("X")
+        cm.evaluate_expression_transfer(layer_key="X", method=method, groupby="batch", test_var_key="is_test")
+    tol = 5e-4 if method == "js" else 2e-4  # the reference evaluates scipy's formulas in float32
+    got, want = qry.var[f"metric_{method}"].to_numpy().astype(np.float64), g[f"metric_{method}"]
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got[~np.isnan(want)], want[~np.isnan(want)], atol=tol)
+    np.testing.assert_array_equal(qry.var[f"_is_valid_test_gene_{method}"].to_numpy().astype(bool), g[f"valid_{method}"])
+    frame = qry.varm[f"metric_{method}"]
+    assert [str(c) for c in frame.columns] == [str(c) for c in g[f"group_names_{method}"]]
+    gw = g[f"groups_{method}"]
+    np.testing.assert_array_equal(np.isnan(frame.to_numpy()), np.isnan(gw))
+    np.testing.assert_allclose(frame.to_numpy()[~np.isnan(gw)], gw[~np.isnan(gw)], atol=tol)
+    m = cm.expression_transfer_metrics
+    assert m["method"] == method and m["n_test_genes"] == int(g[f"n_test_{method}"])
+    np.testing.assert_allclose(m["average"], float(g[f"average_{method}"]), atol=tol)
+    with pytest.raises(NotImplementedError):
+        cm.evaluate_expression_transfer(method="spearman", impute_key="X")
+
+
+def test_integer_layer_gives_float64_like_scipy(torch_cuda):
+    """map_layers on an integer (or float64) layer: scipy promotes the float32 mapping matrix, the result is float64
+    (cellmapper.py:372-373); the float64 instantiation of the CSR x CSR kernel reproduces it bit for bit."""
+    from cellmapper_b200 import CellMapper
+
+    g = load_golden("evaluate")
+    qry, ref = make_evaluate_adatas(g)
+    cm = CellMapper(qry, ref)
+    cm.compute_neighbors(n_neighbors=int(g["k"]), use_rep="X_joint", only_yx=True)
+    cm.compute_mapping_matrix("gaussian")
+    rows = agreeing_rows(cm.knn.yx.indices, g["indices"], max_differing=0.001)
+    cm.map_layers("counts")
+    out = cm.query_imputed.X
+    assert out.dtype == np.float64 and str(g["imputed_counts_dtype"]) == "float64"
+    assert_csr_equal(out[rows], golden_csr(g, "imputed_counts")[rows], rtol=1e-6, atol=0, structure=False)
+    cm.map_layers("X")
+    assert cm.query_imputed.X.dtype == np.float32
+    assert_csr_equal(cm.query_imputed.X[rows], golden_csr(g, "imputed")[rows], rtol=1e-5, atol=1e-7, structure=False)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_map_layers_streams_in_chunks(torch_cuda, dtype):
+    """Row-chunked CSR x CSR transfer: the same bits as the one-shot kernel whatever the chunk size, delivered to a
+    consumer chunk by chunk (rows never split, a row larger than the chunk size gets its own chunk)."""
+    torch = torch_cuda
+    import scipy.sparse as sp
+    from cellmapper_b200 import CellMapper, device
+
+    g = load_golden("q2r_d50")
+    qry, ref = make_adatas(g, with_layers=False)
+    ref.X = golden_csr(g, "expr").astype(dtype)
+    cm = CellMapper(qry, ref)
+    cm.compute_neighbors(n_neighbors=int(g["k"]), use_rep="X_joint", only_yx=True)
+    cm.compute_mapping_matrix("scarches")
+    m = cm.mapping_matrix_device
+    x = ref.X
+    oip, ocols, ovals = device.spgemm(m.indptr, m.cols, m.vals, dev(torch, x.indptr.astype(np.int64)), dev(torch, x.indices), dev(torch, x.data), x.shape[1])
+    whole = sp.csr_matrix((ovals.cpu().numpy(), ocols.cpu().numpy(), oip.cpu().numpy()), shape=(qry.n_obs, x.shape[1]))
+    assert whole.dtype == dtype
+    for max_nnz in (1, 700, 5_000, 1 << 27):
+        blocks = []
+        cm.map_layers("X", chunk_consumer=lambda lo, hi, b: blocks.append((lo, hi, b.copy())), max_chunk_nnz=max_nnz)
+        assert cm.query_imputed is None
+        assert [b[0] for b in blocks] == [0] + [b[1] for b in blocks[:-1]] and blocks[-1][1] == qry.n_obs
+        if max_nnz == 1:
+            assert len(blocks) == qry.n_obs
+        got = sp.vstack([b[2] for b in blocks]).tocsr()
+        np.testing.assert_array_equal(got.indptr, whole.indptr)
+        np.testing.assert_array_equal(got.indices, whole.indices)
+        np.testing.assert_array_equal(got.data, whole.data)
+        cm.map_layers("X", max_chunk_nnz=max_nnz)  # no consumer: one host CSR assembled from the chunks
+        full = cm.query_imputed.X
+        np.testing.assert_array_equal(full.indptr, whole.indptr)
+        np.testing.assert_array_equal(full.indices, whole.indices)
+        np.testing.assert_array_equal(full.data, whole.data)
+        cm.query_imputed = None
+
+
+def test_neighbors_results_coerces_foreign_tensors(torch_cuda):
+    """float32 distances / int32 indices on the device (what faiss-GPU or torch.topk return) and CPU tensors are
+    converted, never read through the wrong element size."""
+    torch = torch_cuda
+    from cellmapper_b200.knn import NeighborsResults
+
+    g = load_golden("q2r_d30")
+    n_r = g["xr"].shape[0]
+    want = NeighborsResults(g["distances"], g["indices"], n_targets=n_r).knn_graph_connectivities("gaussian")
+    d32 = dev(torch, g["distances"].astype(np.float32))  # exactly representable: sklearn's brute-force distances are float32 values
+    i32 = dev(torch, g["indices"].astype(np.int32))
+    got = NeighborsResults(d32, i32, n_targets=n_r).knn_graph_connectivities("gaussian")
+    assert_csr_equal(got, want)
+    cpu = NeighborsResults(torch.from_numpy(g["distances"]), torch.from_numpy(g["indices"]), n_targets=n_r)
+    assert cpu.distances_device.is_cuda and cpu.indices_device.dtype == torch.int64
+    assert_csr_equal(cpu.knn_graph_connectivities("gaussian"), want)
+    with pytest.raises(TypeError):
+        NeighborsResults(d32, d32, n_targets=n_r)
+
+
+def test_two_gpu_sharded_modes_match_single_gpu(torch_cuda):
+    """Both multi-GPU decompositions over NCCL on two ranks (tools/dist_check.py under torchrun) against the
+    single-GPU results: query-sharded CellMapper.map, reference-sharded search + merge + presence score, and the
+    reference-sharded expression transfer.  Skipped on a box with one GPU."""
+    import json, os, subprocess, sys
+
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(root, "tools", "dist_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == 2
+    assert out["query_sharded_equal"] and out["reference_sharded_equal"] and out["presence_equal"]
+    assert out["reference_sharded_expression_equal_1e-6"]

@@ -63,10 +63,8 @@ xq5, _ = synth.mixture_embedding(n_q5, centres, seed=4)
 rlo, rhi = cmd.shard_bounds(n_r5, world, rank)
 q_d = torch.from_numpy(xq5).to(dev); r_loc = torch.from_numpy(xr5[rlo:rhi]).to(dev)
 def sharded():
-    md, mi = cmd.knn_reference_sharded(q_d, r_loc, rlo, k, _lib.DIST_SKLEARN_F32)
-    res = NeighborsResults(md, mi, n_targets=n_r5)
-    ip, cols, vals = res.connectivities_device("gaussian", normalize=False)
-    return md, mi, device.csr_col_sums(ip, cols, vals, n_r5)
+    # sharded search + merge, per-rank block of the column sums (deterministic reverse-list kernel), all-gather
+    return cmd.presence_reference_sharded(q_d, r_loc, rlo, k, _lib.DIST_SKLEARN_F32)
 sharded()
 (md, mi, score), ms = sync_time(sharded)
 out["reference_sharded_search_presence_ms"] = ms
@@ -99,10 +97,9 @@ out["reference_sharded_expression_equal_1e-6"] = bool(flag.item())
 if rank == 0:
     r_all = torch.from_numpy(xr5).to(dev)
     gd, gi = device.knn_search(q_d, r_all, k, dist_mode=_lib.DIST_SKLEARN_F32)
-    res = NeighborsResults(gd, gi, n_targets=n_r5)
-    ip, cols, vals = res.connectivities_device("gaussian", normalize=False)
-    gscore = device.csr_col_sums(ip, cols, vals, n_r5)
+    gscore, _ = device.presence_scores(gd, gi, device.edge_stats(gd, gi, need_std=False), n_r5)
     out["reference_sharded_equal"] = bool(torch.equal(gi, mi) and torch.equal(gd, md))
+    out["presence_equal"] = bool(torch.equal(gscore, score))  # ascending-row sums on every rank: bit-identical
     out["presence_max_abs_diff"] = float((gscore - score).abs().max().item())
     print(json.dumps(out), flush=True)
 if world > 1:

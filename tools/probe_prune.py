@@ -1,4 +1,7 @@
 """Development probe: pruned vs exhaustive tensor-core search (same results, tiles scanned, time)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+import _probe_lib  # noqa: F401  (-DCM_DEV_PROBES build: the shipping library has no probe switches)
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
