@@ -477,14 +477,14 @@ def run_map_workload(ctx, name, data, steps, warmup, with_e2e=True, with_cpu=Tru
     umap_t, umap_p = ctx.pin(umap)
     label_series = pd.Series(pd.Categorical(labels))
     cats, codes = sorted_category_codes(label_series)
-    codes_t, _ = ctx.pin(codes)
+    codes_t, _ = ctx.pin(codes.astype(np.uint8) if len(cats) <= 256 else codes)  # what CellMapper.map uploads
     allreduce = cmd.allreduce_sum if world > 1 else None
     mode = sklearn_like_dist_mode(np.float32, d, K, n_r)
 
     # ---------------- device-resident arm ----------------
     xr_d, xq_d = xr_t.to(dev), xq_t.to(dev)
     umap_d, codes_d = umap_t.to(dev), codes_t.to(dev)
-    PHASES = ["search", "edge_stats", "kernel_to_csr", "vote", "spmm"]
+    PHASES = ["search", "edge_stats", "fused_rows"]  # fused_rows: kernel -> CSR -> normalise + vote + SpMM in one row pass
     search_stats = []  # device int64[4] per search: [fallback rows, -, candidates re-ranked, (query tile, reference tile) pairs evaluated]
 
     def device_step(marks):
@@ -500,11 +500,7 @@ def run_map_workload(ctx, name, data, steps, warmup, with_e2e=True, with_cpu=Tru
         mark()
         st = device.edge_stats(dd, ii, allreduce=allreduce, need_std=False)
         mark()
-        ip, cols, vals = device.edge_kernel_to_csr(dd, ii, "gaussian", st, normalize=True)
-        mark()
-        code, conf = device.vote_argmax(ip, cols, vals, codes_d, len(cats))
-        mark()
-        emb = device.spmm(ip, cols, vals, umap_d)
+        ip, cols, vals, code, conf, emb = device.map_rows_fused(dd, ii, "gaussian", st, codes=codes_d, n_classes=len(cats), dense=umap_d, rows_full=True)
         mark()
         return dd, ii, code, conf, emb
 
@@ -585,12 +581,16 @@ def run_map_workload(ctx, name, data, steps, warmup, with_e2e=True, with_cpu=Tru
             roofline["exhaustive_scan_probe"] = {"queries": n_slice, "ms": t_ex * 1e3, "achieved": ach_ex, "frac": ach_ex / roofline["peak"]}
     out["roofline"] = roofline
     # HBM-side phases: algorithmic bytes per query (SURVEY.md 8d / DESIGN.md 4) over the CUDA-event time of the call
-    hbm_bytes = {"edge_stats": K * 16.0, "kernel_to_csr": 484.0, "vote": 368.0, "spmm": K * 8.0 + K * UMAP_DIMS * 4.0 + UMAP_DIMS * 4.0}
+    # fused_rows, bytes the fused kernel has to move per query: read (d, idx) 16 k, write CSR 8 k + 4, gather k class
+    # bytes and k payload rows, write code + conf + payload.  SURVEY 8d's P2 + P3a + P3b (484 + 368 + 488 B) counts
+    # the CSR three times (written, then read by each transfer): that re-reading is what the fusion removes.
+    hbm_bytes = {"edge_stats": K * 16.0, "fused_rows": K * 16.0 + K * 8.0 + 4.0 + K * 1.0 + K * UMAP_DIMS * 4.0 + 8.0 + UMAP_DIMS * 4.0}
     out["hbm_phases"] = {
         n: {"ms": path_ms[n], "achieved_gbs": hbm_bytes[n] * n_q / (path_ms[n] * 1e-3) / 1e9,
             "frac_of_hbm_peak": hbm_bytes[n] * n_q / (path_ms[n] * 1e-3) / 1e9 / ctx.peaks["hbm_gbs"]}
         for n in hbm_bytes
     }
+    out["hbm_phases"]["fused_rows"]["survey_8d_bytes_per_query"] = 484.0 + 368.0 + 488.0
 
     # ---------------- CPU baseline + recall / label agreement against it (rank 0's first queries) ----------------
     cpu = None

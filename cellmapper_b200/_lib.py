@@ -20,7 +20,7 @@ KERNELS = {"gaussian": 0, "scarches": 1, "inverse_distance": 2, "equal": 3}
 DIST_SQRT_F64, DIST_SKLEARN_F32, DIST_SQUARED = 0, 1, 2
 KNN_AUTO, KNN_EXACT_F64, KNN_TENSOR_EXHAUSTIVE = 0, 1, 2
 EDGE_STATS_WORKSPACE_BYTES = 32768
-SPGEMM_MAX_COLS = 49152
+SPGEMM_MAX_COLS = 43008
 SELECT_WORKSPACE_BYTES = 16384
 MOMENTS = 8
 
@@ -46,6 +46,10 @@ SIGNATURES = {
     "cm_knn_merge_topk": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
     "cm_edge_stats": (c_int, [_P, _P, c_int64, _P, _P, _P, c_size_t, _P]),
     "cm_edge_kernel_to_csr": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P]),
+    "cm_map_rows_fused": (
+        c_int,
+        [_P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int64, c_int, c_int, _P, c_int64, _P],
+    ),
     "cm_csr_row_normalize": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "cm_csr_col_sums": (c_int, [_P, _P, _P, c_int64, _P, _P]),
     "cm_vote_argmax": (c_int, [_P, _P, _P, c_int64, _P, c_int, _P, _P, _P, _P]),

@@ -301,6 +301,130 @@ edge_to_csr_small_kernel(const double* __restrict__ dist, const int64_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused row pass (k <= 32): kernel weights -> column sort -> row-normalised float32 CSR row, AND -- while the row
+// sits in the warp's registers -- the weighted label vote (cellmapper.py:591-605) and the k-sparse x dense product
+// for up to kFusedMaxM payload columns (cellmapper.py:338,628).  Replaces count_valid + 3 scan kernels +
+// edge_to_csr_small + vote_argmax_rows + spmm, each of which re-read what the previous one wrote (2.35 ms at
+// 1.5 M rows; the CSR alone is 366 MB written and read back twice).  Arithmetic is the same as in the separate
+// kernels, operation for operation: float64 weights and row sum in numpy's order, float32 class sums added in
+// ascending column order (ties -> lowest class), payload products rounded separately from their sums.
+// rows_full != 0: every row has k valid edges (the output of cm_knn_search), so row r starts at r * k and no
+// count / scan pass is needed; otherwise `indptr` must hold the scanned valid counts (ragged graphs).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedMaxM = 4;
+
+template <typename TC, typename TB, int M>
+__global__ void __launch_bounds__(kRowWarps * 32)
+map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n_q, int k, int kernel,
+                      const double* __restrict__ stats3, int rows_full, int32_t* __restrict__ indptr,
+                      int32_t* __restrict__ cols, float* __restrict__ vals_f32, const TC* __restrict__ codes,
+                      int32_t* __restrict__ out_code, float* __restrict__ out_conf, const TB* __restrict__ B, int64_t ldb,
+                      TB* __restrict__ out_dense, int64_t ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double p0 = kernel_param(kernel, stats3);
+  if (rows_full && blockIdx.x == 0 && threadIdx.x == 0) indptr[0] = 0;
+  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < n_q; row += (int64_t)gridDim.x * kRowWarps) {
+    double w = 0.0;
+    int32_t c = INT32_MAX;
+    if (lane < k) {
+      const double dv = dist[row * k + lane];
+      const int64_t iv = idx[row * k + lane];
+      if (edge_valid(dv, iv)) {
+        w = kernel_value(kernel, dv, p0);
+        c = (int32_t)iv;
+      }
+    }
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+        const int32_t oc = __shfl_xor_sync(0xffffffffu, c, stride);
+        const double ow = shfl_f64(w, lane ^ stride);
+        const bool up = ((lane & size) == 0);
+        const bool lower = ((lane & stride) == 0);
+        const bool take_min = (up == lower);
+        const bool swap = take_min ? (oc < c) : (oc > c);
+        if (swap) { c = oc; w = ow; }
+      }
+    }
+    int32_t start;
+    int n_valid;
+    if (rows_full) {
+      start = (int32_t)(row * k);
+      n_valid = k;
+      if (lane == 0) indptr[row + 1] = start + k;
+    } else {
+      start = indptr[row];
+      n_valid = indptr[row + 1] - start;
+    }
+    double rs = numpy_row_sum_lanes(w, n_valid);
+    if (rs == 0.0) rs = 1.0;  // zero rows are left unchanged (cellmapper.py:127-129)
+    const double inv = 1.0 / rs;
+    const float v = (float)(w * inv);
+    const bool on = lane < n_valid;
+    if (on) {
+      cols[start + lane] = c;
+      vals_f32[start + lane] = v;
+    }
+    // payload gathers of this lane's edge, all issued before the serial part
+    int cls = -1;
+    if (codes && on) cls = (int)codes[c];
+    TB b[M > 0 ? M : 1];
+#pragma unroll
+    for (int j = 0; j < M; ++j) b[j] = (B && on) ? B[(int64_t)c * ldb + j] : (TB)0;
+    // lanes whose edge has this lane's class
+    const unsigned same = codes ? __match_any_sync(0xffffffffu, cls) : 0u;
+    float csum = 0.f;
+    TB acc[M > 0 ? M : 1];
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc[j] = (TB)0;
+    for (int t = 0; t < n_valid; ++t) {  // ascending column: scipy's summation order
+      const float vt = __shfl_sync(0xffffffffu, v, t);
+      if ((same >> t) & 1u) csum = __fadd_rn(csum, vt);  // w * 1.0f == w
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        if constexpr (sizeof(TB) == 4) {
+          const float bt = __shfl_sync(0xffffffffu, b[j], t);
+          acc[j] = __fadd_rn(acc[j], __fmul_rn(vt, bt));
+        } else {
+          const double bt = shfl_f64(b[j], t);
+          acc[j] = __dadd_rn(acc[j], __dmul_rn((double)vt, bt));
+        }
+      }
+    }
+    if (codes) {
+      // arg-max over the classes present in the row; absent classes have sum 0 and win ties only through a lower
+      // index (scipy's sparse argmax compares against the implicit zeros too)
+      float best = on ? csum : -CUDART_INF_F;
+      int best_c = on ? cls : INT32_MAX;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+      }
+      if (lane == 0) {
+        // no positive class sum (an empty row, or weights that all rounded to 0: csr_matmat drops zero sums, so
+        // the row of M @ onehot is empty): scipy's sparse argmax / max return column 0 / 0
+        if (n_valid == 0 || !(best > 0.f)) {
+          best_c = 0;
+          best = 0.f;
+        }
+        out_code[row] = best_c;
+        out_conf[row] = best;
+      }
+    }
+    if (B && lane < M) {
+      TB r = acc[0];
+#pragma unroll
+      for (int j = 1; j < M; ++j)
+        if (lane == j) r = acc[j];
+      out_dense[row * ldo + lane] = r;
+    }
+  }
+}
+
 __global__ void csr_row_normalize_kernel(const int32_t* __restrict__ indptr, const double* __restrict__ vals_in,
                                          int64_t n_rows, float* __restrict__ vals_out, unsigned long long* zero_rows) {
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
@@ -384,6 +508,65 @@ extern "C" int cm_edge_kernel_to_csr(const double* dist, const int64_t* idx, int
     }
   }
   return CM_OK;
+}
+
+template <typename TC, typename TB>
+static int launch_fused(int m, int grid, cudaStream_t st, const double* dist, const int64_t* idx, int64_t n_q, int k, int kernel,
+                        const double* stats3, int rows_full, int32_t* indptr, int32_t* cols, float* vals_f32, const TC* codes,
+                        int32_t* out_code, float* out_conf, const TB* B, int64_t ldb, TB* out_dense, int64_t ldo) {
+#define CM_FUSED(M)                                                                                                       \
+  map_rows_fused_kernel<TC, TB, M><<<grid, kRowWarps * 32, 0, st>>>(dist, idx, n_q, k, kernel, stats3, rows_full, indptr, cols, \
+                                                                    vals_f32, codes, out_code, out_conf, B, ldb, out_dense, ldo)
+  switch (B ? m : 0) {
+    case 0: CM_FUSED(0); break;
+    case 1: CM_FUSED(1); break;
+    case 2: CM_FUSED(2); break;
+    case 3: CM_FUSED(3); break;
+    default: CM_FUSED(4); break;
+  }
+#undef CM_FUSED
+  CM_LAUNCH_CHECK("map_rows_fused_kernel");
+  return CM_OK;
+}
+
+extern "C" int cm_map_rows_fused(const double* dist, const int64_t* idx, int64_t n_q, int k, int kernel, const double* stats3,
+                                 int rows_full, int32_t* indptr, int32_t* cols, float* vals_f32, const void* codes,
+                                 int codes_are_u8, int n_classes, int32_t* out_code, float* out_conf, const void* B,
+                                 int64_t ldb, int m, int b_dtype, void* out_dense, int64_t ldo, void* stream) {
+  CM_REQUIRE(dist && idx && stats3 && indptr && cols && vals_f32, "null pointer argument");
+  CM_REQUIRE(n_q >= 0 && k >= 1 && k <= 32, "the fused row pass handles 1 <= k <= 32 (got %d)", k);
+  CM_REQUIRE(kernel >= 0 && kernel <= 3, "unknown kernel code %d", kernel);
+  CM_REQUIRE(n_q * (int64_t)k < (int64_t)INT32_MAX, "nnz must fit int32 (scipy CSR index type)");
+  CM_REQUIRE(!codes || (out_code && out_conf && n_classes >= 1 && (!codes_are_u8 || n_classes <= 256)), "bad vote arguments");
+  CM_REQUIRE(!B || (out_dense && m >= 1 && m <= kFusedMaxM && ldb >= m && ldo >= m && (b_dtype == CM_F32 || b_dtype == CM_F64)),
+             "bad payload arguments (1 <= m <= %d)", kFusedMaxM);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_q == 0) {
+    CM_CUDA_CHECK(cudaMemsetAsync(indptr, 0, sizeof(int32_t), st));
+    return CM_OK;
+  }
+  if (!rows_full) {  // ragged rows: valid counts + scan first (block sums live at the head of `cols` until it is filled)
+    int64_t blocks = ceil_div(n_q * 32, 256);
+    int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
+    count_valid_kernel<<<grid, 256, 0, st>>>(dist, idx, n_q, k, indptr);
+    CM_LAUNCH_CHECK("count_valid_kernel");
+    CM_REQUIRE(inclusive_scan_scratch_elems(n_q) <= n_q * (int64_t)k, "scratch too small");
+    const int rc = inclusive_scan_i32(indptr + 1, n_q, cols, st);
+    if (rc) return rc;
+  }
+  const int64_t blocks = ceil_div(n_q, kRowWarps);
+  const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  const bool f64 = B && b_dtype == CM_F64;
+#define CM_GO(TC, TB)                                                                                                            \
+  return launch_fused<TC, TB>(m, grid, st, dist, idx, n_q, k, kernel, stats3, rows_full, indptr, cols, vals_f32, (const TC*)codes, \
+                              out_code, out_conf, (const TB*)B, ldb, (TB*)out_dense, ldo)
+  if (codes_are_u8) {
+    if (f64) CM_GO(uint8_t, double);
+    CM_GO(uint8_t, float);
+  }
+  if (f64) CM_GO(int32_t, double);
+  CM_GO(int32_t, float);
+#undef CM_GO
 }
 
 extern "C" int cm_csr_row_normalize(const int32_t* indptr, const double* vals_in, int64_t n_rows, float* vals_out,

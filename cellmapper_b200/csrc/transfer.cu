@@ -139,13 +139,28 @@ __global__ void spmm_kernel(const int32_t* __restrict__ indptr, const int32_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// CSR x CSR row gather/accumulate: one CTA per query row, dense accumulator + touched-bitmap in smem
+// CSR x CSR row gather/accumulate: one CTA per query row, dense accumulator + touched-flags in shared memory
 // ------------------------------------------------------------------------------------------------
-constexpr int kSpgemmThreads = 512;
+// Two passes over the rows of a chunk: count (structure only: the union of the gathered rows' columns) and fill.
+//  * touched genes are marked with plain BYTE stores (every writer stores 1, so the race is benign); the first
+//    version set bits with atomicOr, and because an expression row is sorted by gene, the 32 lanes of a warp hit the
+//    same one or two bitmap words -- a 16-way serialised shared-memory atomic per warp instruction;
+//  * the accumulate of one neighbour's row touches every gene at most once (columns are unique inside a row), so it
+//    needs no atomics; neighbours are applied in ascending reference index with a barrier between them -- scipy's
+//    summation order, bit for bit;
+//  * the rows of kNbGroup neighbours are in flight before the first of them is accumulated (the barrier between
+//    neighbours then costs a barrier, not a trip to memory);
+//  * the result row is written by whole warps: a warp takes 32 consecutive genes, ballots their flags and stores the
+//    touched ones to consecutive output slots -- coalesced runs instead of one scattered 4-byte store per lane (the
+//    first version gave every thread one bitmap word and let it write its own entries: 8 partial-sector writes per
+//    sector of the 40-80 GB result).
+constexpr int kSpgemmFillThreads = 1024;   // one CTA per SM (the float32 accumulator of 30 k genes is 120 KB)
+constexpr int kSpgemmCountThreads = 512;   // four CTAs per SM
+
 __device__ __forceinline__ size_t align_up_dev(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// exclusive scan of one int per thread across the block; *total receives the block sum
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
-  // exclusive scan of one int per thread across the block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = v;
 #pragma unroll
@@ -174,10 +189,14 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
 __device__ __forceinline__ float mul_add_rn(float acc, float w, float x) { return __fadd_rn(acc, __fmul_rn(w, x)); }
 __device__ __forceinline__ double mul_add_rn(double acc, double w, double x) { return __dadd_rn(acc, __dmul_rn(w, x)); }
 
+// shared memory of one CTA for a window of n_genes columns: flags (bytes), per-32-gene counts, accumulator
+__host__ __device__ inline size_t spgemm_flag_bytes(int n_genes) { return ((size_t)n_genes + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t spgemm_group_bytes(int n_genes) { return ((((size_t)n_genes + 31) >> 5) * 4 + 15) & ~(size_t)15; }
+
 // T = float: float32 layers (result float32).  T = double: float64 and integer layers -- scipy promotes the
 // float32 mapping matrix to float64 for those and returns float64 (cellmapper.py:372-373).
-template <bool kFill, typename T>
-__global__ void __launch_bounds__(kSpgemmThreads)
+template <bool kFill, typename T, int kThreads>
+__global__ void __launch_bounds__(kThreads)
 spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_cols, const float* __restrict__ m_vals,
               int64_t n_q, const int64_t* __restrict__ x_indptr, const int32_t* __restrict__ x_cols,
               const T* __restrict__ x_vals, int32_t g_lo, int32_t n_genes, int32_t* __restrict__ out_row_nnz,
@@ -187,21 +206,24 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
   // columns than the shared-memory accumulator holds are processed window by window (spgemm_launch); `row_off`
   // then carries every row's write position from one window to the next.
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n_words = (n_genes + 31) >> 5;
-  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem_raw);
-  T* acc = reinterpret_cast<T*>(smem_raw + align_up_dev((size_t)n_words * 4, sizeof(T)));
+  uint8_t* flags = smem_raw;
+  int32_t* gcount = reinterpret_cast<int32_t*>(smem_raw + spgemm_flag_bytes(n_genes));
+  T* acc = reinterpret_cast<T*>(smem_raw + spgemm_flag_bytes(n_genes) + spgemm_group_bytes(n_genes));
   __shared__ int warp_sums[32];
   __shared__ int total_sh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int n_groups = (n_genes + 31) >> 5;
 
-  for (int w = threadIdx.x; w < n_words; w += blockDim.x) bitmap[w] = 0u;
+  for (int i = threadIdx.x; i < (int)(spgemm_flag_bytes(n_genes) >> 2); i += kThreads) reinterpret_cast<uint32_t*>(flags)[i] = 0u;
   if (kFill)
-    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) acc[g] = (T)0;
+    for (int g = threadIdx.x; g < n_genes; g += kThreads) acc[g] = (T)0;
   __syncthreads();
 
   __shared__ int64_t s_xs[32], s_xe[32];
   __shared__ T s_w[32];
-  constexpr int kNbGroup = 4;  // neighbours whose expression rows are fetched together
-  constexpr int kPer = 4;      // elements per thread and neighbour held in registers (rows up to 2048 nnz; longer: tail loop)
+  constexpr int kNbGroup = 8;                 // neighbours whose expression rows are fetched together
+  constexpr int kPer = 2048 / kThreads;       // elements per thread and neighbour held in registers (rows up to 2048 nnz; longer: tail loop)
 
   for (int64_t row = blockIdx.x; row < n_q; row += gridDim.x) {
     const int32_t lo = m_indptr[row], hi = m_indptr[row + 1];
@@ -217,8 +239,6 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
       }
       __syncthreads();
       for (int g0 = 0; g0 < n_nb; g0 += kNbGroup) {
-        // all loads of a group of neighbours are in flight before the first accumulate: the per-neighbour
-        // barrier below then costs a barrier, not a trip to memory
         int32_t gc[kNbGroup][kPer];
         T gv[kNbGroup][kPer];
 #pragma unroll
@@ -227,7 +247,7 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
           const int64_t xs = on ? s_xs[g0 + j] : 0, xe = on ? s_xe[g0 + j] : 0;
 #pragma unroll
           for (int u = 0; u < kPer; ++u) {
-            const int64_t p = xs + threadIdx.x + (int64_t)u * kSpgemmThreads;
+            const int64_t p = xs + threadIdx.x + (int64_t)u * kThreads;
             gc[j][u] = p < xe ? x_cols[p] - g_lo : -1;
             gv[j][u] = (kFill && p < xe) ? x_vals[p] : (T)0;
           }
@@ -240,14 +260,14 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
             for (int u = 0; u < kPer; ++u) {
               const int32_t g = gc[j][u];
               if ((uint32_t)g < (uint32_t)n_genes) {
-                atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+                flags[g] = 1;
                 if (kFill) acc[g] = mul_add_rn(acc[g], w, gv[j][u]);  // columns are unique inside one X row
               }
             }
-            for (int64_t p = s_xs[g0 + j] + threadIdx.x + (int64_t)kPer * kSpgemmThreads; p < s_xe[g0 + j]; p += kSpgemmThreads) {
+            for (int64_t p = s_xs[g0 + j] + threadIdx.x + (int64_t)kPer * kThreads; p < s_xe[g0 + j]; p += kThreads) {
               const int32_t g = x_cols[p] - g_lo;
               if ((uint32_t)g < (uint32_t)n_genes) {
-                atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+                flags[g] = 1;
                 if (kFill) acc[g] = mul_add_rn(acc[g], w, x_vals[p]);
               }
             }
@@ -258,33 +278,40 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
       __syncthreads();  // s_xs / s_xe / s_w are rewritten by the next chunk
     }
     __syncthreads();
-    // emit in ascending gene order: rank of every set bit by a block-wide scan over bitmap words
+    // touched genes per group of 32 (one warp per group), then their exclusive prefix over the row
+    for (int gi = warp; gi < n_groups; gi += kWarps) {
+      const int g = (gi << 5) + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, g < n_genes && flags[g] != 0);
+      if (lane == 0) gcount[gi] = __popc(m);
+    }
+    __syncthreads();
     int base_rank = 0;
-    for (int w0 = 0; w0 < n_words; w0 += blockDim.x) {
-      const int w = w0 + threadIdx.x;
-      const uint32_t bits = w < n_words ? bitmap[w] : 0u;
-      const int pc = __popc(bits);
-      int total;
+    for (int w0 = 0; w0 < n_groups; w0 += kThreads) {
+      const int gi = w0 + threadIdx.x;
+      const int pc = gi < n_groups ? gcount[gi] : 0;
       const int ex = block_exclusive_scan(pc, warp_sums, &total_sh);
-      total = total_sh;
-      if (kFill && bits) {
-        int64_t o = (row_off ? row_off[row] : out_indptr[row]) + base_rank + ex;
-        uint32_t b = bits;
-        while (b) {
-          const int bit = __ffs(b) - 1;
-          b &= b - 1;
-          const int g = (w << 5) + bit;
+      if (gi < n_groups) gcount[gi] = base_rank + ex;
+      base_rank += total_sh;
+      __syncthreads();
+    }
+    if (kFill) {
+      const int64_t o0 = row_off ? row_off[row] : out_indptr[row];
+      for (int gi = warp; gi < n_groups; gi += kWarps) {
+        const int g = (gi << 5) + lane;
+        const bool on = g < n_genes && flags[g] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) {
+          const int64_t o = o0 + gcount[gi] + __popc(m & ((1u << lane) - 1u));
           out_cols[o] = g + g_lo;
           out_vals[o] = acc[g];
           acc[g] = (T)0;
-          ++o;
+          flags[g] = 0;
         }
       }
-      if (w < n_words) bitmap[w] = 0u;
-      base_rank += total;
-      __syncthreads();
+    } else {
+      for (int i = threadIdx.x; i < (int)(spgemm_flag_bytes(n_genes) >> 2); i += kThreads) reinterpret_cast<uint32_t*>(flags)[i] = 0u;
+      if (threadIdx.x == 0) out_row_nnz[row] = base_rank + (accumulate_count ? out_row_nnz[row] : 0);
     }
-    if (!kFill && threadIdx.x == 0) out_row_nnz[row] = base_rank + (accumulate_count ? out_row_nnz[row] : 0);
     __syncthreads();  // (also: every thread has read row_off[row] before it moves)
     if (kFill && row_off && threadIdx.x == 0) row_off[row] += base_rank;
   }
@@ -349,9 +376,9 @@ static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_co
                          cudaStream_t st) {
   CM_REQUIRE(n_q >= 0 && n_genes >= 1, "n_genes = %d must be positive", n_genes);
   if (n_q == 0) return CM_OK;
-  // gene windows of at most max_cols columns (the dense accumulator of a CTA: CM_SPGEMM_MAX_COLS float32 values,
-  // half as many float64); one window in the usual case
-  const int max_cols = (int)(CM_SPGEMM_MAX_COLS * sizeof(float) / sizeof(T));
+  // gene windows of at most max_cols columns (the dense accumulator of a CTA); one window in the usual case
+  // sized so that flags (1 B / gene) + group counts + accumulator stay below 224 KB of shared memory
+  const int max_cols = sizeof(T) == 4 ? CM_SPGEMM_MAX_COLS : CM_SPGEMM_MAX_COLS_F64;
   const int n_win = (n_genes + max_cols - 1) / max_cols;
   int win = (n_genes + n_win - 1) / n_win;
   win = (win + 31) & ~31;
@@ -365,21 +392,21 @@ static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_co
     const int32_t g_lo = w * win;
     const int32_t g_n = n_genes - g_lo < win ? n_genes - g_lo : win;
     if (g_n <= 0) break;
-    const int n_words = (g_n + 31) >> 5;
-    size_t smem = align_up((size_t)n_words * 4, sizeof(T)) + (fill ? (size_t)g_n * sizeof(T) : 0);
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int64_t want = (int64_t)kNumSMs * per_sm;
-    int grid = (int)(n_q < want ? n_q : want);
+    size_t smem = spgemm_flag_bytes(g_n) + spgemm_group_bytes(g_n) + (fill ? (size_t)g_n * sizeof(T) : 0);
     if (fill) {
-      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      spgemm_kernel<true, T><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo,
-                                                                g_n, out_row_nnz, 0, out_indptr, row_off, out_cols, out_vals);
+      const int grid = (int)(n_q < (int64_t)kNumSMs ? n_q : (int64_t)kNumSMs);  // 1024 threads x 64 registers: one CTA per SM
+      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true, T, kSpgemmFillThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spgemm_kernel<true, T, kSpgemmFillThreads><<<grid, kSpgemmFillThreads, smem, st>>>(
+          m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n, out_row_nnz, 0, out_indptr, row_off, out_cols, out_vals);
     } else {
-      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      spgemm_kernel<false, T><<<grid, kSpgemmThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo,
-                                                                 g_n, out_row_nnz, w > 0, out_indptr, row_off, out_cols, out_vals);
+      int per_sm = (int)((220 * 1024) / (smem + 1024));
+      if (per_sm < 1) per_sm = 1;
+      if (per_sm > 4) per_sm = 4;
+      const int64_t want = (int64_t)kNumSMs * per_sm;
+      const int grid = (int)(n_q < want ? n_q : want);
+      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false, T, kSpgemmCountThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      spgemm_kernel<false, T, kSpgemmCountThreads><<<grid, kSpgemmCountThreads, smem, st>>>(
+          m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n, out_row_nnz, w > 0, out_indptr, row_off, out_cols, out_vals);
     }
     CM_LAUNCH_CHECK("spgemm_kernel");
   }

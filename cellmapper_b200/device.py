@@ -21,6 +21,7 @@ __all__ = [
     "edge_stats",
     "edge_kernel_to_csr",
     "csr_row_normalize",
+    "map_rows_fused",
     "csr_col_sums",
     "vote_argmax",
     "spmm",
@@ -262,6 +263,63 @@ def edge_kernel_to_csr(
             _ptr(cols), _ptr(vals) if normalize else None, None if normalize else _ptr(vals), _stream(),
         )  # fmt: skip
     return indptr, cols, vals
+
+
+FUSED_MAX_K, FUSED_MAX_M = 32, 4
+
+
+def map_rows_fused(dist, idx, kernel: str, stats3, codes: torch.Tensor | None = None, n_classes: int = 0,
+                   dense: torch.Tensor | None = None, rows_full: bool = False):
+    """One row pass: edge list -> row-normalised float32 CSR (== ``edge_kernel_to_csr(normalize=True)``) and, from the
+    same registers, the label vote (``codes``: uint8 or int32 class codes of the reference cells) and the product
+    with up to 4 dense payload columns (``dense``: (n_r, m) float32 / float64).  k <= 32.
+    ``rows_full``: every row has k valid edges (true for ``knn_search`` output) -- skips the count / scan pass.
+    Returns (indptr, cols, vals, code | None, conf | None, out_dense | None)."""
+    dev = _check_cuda(dist, idx, stats3, codes, dense)
+    if kernel not in _lib.KERNELS:
+        raise ValueError(f"Unknown kernel: {kernel}.")
+    dist = dist.to(torch.float64).contiguous()
+    idx = idx.to(torch.int64).contiguous()
+    n_q, k = dist.shape
+    if k > FUSED_MAX_K:
+        raise ValueError(f"the fused row pass handles k <= {FUSED_MAX_K}")
+    with torch.cuda.device(dev):
+        indptr = torch.empty(n_q + 1, dtype=torch.int32, device=dev)
+        cols = torch.empty(max(n_q * k, 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(max(n_q * k, 1), dtype=torch.float32, device=dev)
+        code = conf = out = None
+        u8 = 0
+        if codes is not None:
+            if codes.dtype == torch.uint8:
+                u8 = 1
+            else:
+                codes = codes.to(torch.int32)
+            codes = codes.contiguous()
+            code = torch.empty(n_q, dtype=torch.int32, device=dev)
+            conf = torch.empty(n_q, dtype=torch.float32, device=dev)
+        m = ldb = ldo = 0
+        squeeze = False
+        if dense is not None:
+            squeeze = dense.dim() == 1
+            if squeeze:
+                dense = dense.reshape(-1, 1)
+            if dense.dtype != torch.float32:
+                dense = dense.to(torch.float64)
+            if dense.stride(-1) != 1:
+                dense = dense.contiguous()
+            m = dense.shape[1]
+            if m > FUSED_MAX_M:
+                raise ValueError(f"the fused row pass handles at most {FUSED_MAX_M} payload columns")
+            out = torch.empty((n_q, m), dtype=dense.dtype, device=dev)
+            ldb, ldo = dense.stride(0), out.stride(0)
+        _call(
+            "cm_map_rows_fused", _ptr(dist), _ptr(idx), n_q, k, _lib.KERNELS[kernel], _ptr(stats3), int(bool(rows_full)), _ptr(indptr),
+            _ptr(cols), _ptr(vals), _ptr(codes), u8, int(n_classes), _ptr(code), _ptr(conf), _ptr(dense), ldb, m,
+            _dtype_code(dense) if dense is not None else 0, _ptr(out), ldo, _stream(),
+        )  # fmt: skip
+        if out is not None and squeeze:
+            out = out.reshape(-1)
+    return indptr, cols, vals, code, conf, out
 
 
 def csr_row_normalize(indptr: torch.Tensor, vals: torch.Tensor):

@@ -25,11 +25,48 @@ def _current_device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+# Pageable host arrays (what an AnnData read from disk holds) reach the device through a small ring of page-locked
+# staging buffers: the host copy of chunk i+1 overlaps the DMA of chunk i.  torch's own pageable path stages and
+# copies one after the other and measured ~13 GB/s on the GPU box (618 MB of embeddings: 47 ms of a 115 ms step).
+_STAGE_CHUNK_BYTES = 8 << 20
+_STAGE_SLOTS = 4
+_STAGE_MIN_BYTES = 4 << 20
+_stage_ring: dict = {}
+
+
+def _staged_upload(src: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """``src``: contiguous CPU tensor in pageable memory.  Returns its device copy (enqueued on the current stream)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ring = _stage_ring.get(key)
+    if ring is None:
+        ring = _stage_ring[key] = ([torch.empty(_STAGE_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(_STAGE_SLOTS)], [None] * _STAGE_SLOTS)
+    bufs, events = ring
+    out = torch.empty(src.shape, dtype=src.dtype, device=dev)
+    s8, d8 = src.reshape(-1).view(torch.uint8), out.reshape(-1).view(torch.uint8)
+    n = s8.numel()
+    for i, off in enumerate(range(0, n, _STAGE_CHUNK_BYTES)):
+        slot = i % _STAGE_SLOTS
+        m = min(_STAGE_CHUNK_BYTES, n - off)
+        if events[slot] is not None:
+            events[slot].synchronize()  # the DMA that last read this staging buffer has finished
+        bufs[slot][:m].copy_(s8[off : off + m])
+        d8[off : off + m].copy_(bufs[slot][:m], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        events[slot] = ev
+    return out
+
+
 def _to_device(a, dtype=None) -> torch.Tensor:
-    if isinstance(a, torch.Tensor):
-        t = a if a.is_cuda else a.to(_current_device(), non_blocking=True)
+    if isinstance(a, torch.Tensor) and a.is_cuda:
+        t = a
     else:
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(_current_device(), non_blocking=True)
+        src = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        dev = _current_device()
+        if src.numel() * src.element_size() >= _STAGE_MIN_BYTES and src.is_contiguous() and not src.is_pinned():
+            t = _staged_upload(src, dev)
+        else:
+            t = src.to(dev, non_blocking=True)
     return t if dtype is None or t.dtype == dtype else t.to(dtype)
 
 
@@ -65,6 +102,9 @@ class NeighborsResults:
         else:
             self._idx_host = indices.numpy() if isinstance(indices, torch.Tensor) else np.asarray(indices)
         self._shape2 = tuple(int(s) for s in indices.shape)
+        #: every row holds n_neighbors valid entries (set by the search, which always finds k <= n_r neighbours);
+        #: lets the row pass skip its count / scan of valid entries.  Ragged / user-supplied graphs: False.
+        self.rows_full = False
         self.n_targets = int(n_targets) if n_targets is not None else self._shape2[0]  # knn.py:49-51
         self._cache: dict = {}
 
@@ -132,6 +172,8 @@ class NeighborsResults:
             if normalize:
                 vals, _ = device.csr_row_normalize(indptr, vals)
             return indptr, cols, vals
+        if normalize and self.n_neighbors <= device.FUSED_MAX_K:  # one launch instead of count + scan + fill
+            return device.map_rows_fused(d, i, kernel, stats, rows_full=self.rows_full)[:3]
         return device.edge_kernel_to_csr(d, i, kernel, stats, normalize=normalize)
 
     @property
@@ -296,21 +338,26 @@ class Neighbors:
             d, i, st = device.knn_search(q, r, n_neighbors, dist_mode=mode, algo=algo, return_stats=True, ref_cells=cells)
             return d, i, st
 
+        def results(d, i, n_targets):
+            res = NeighborsResults(d, i, n_targets=n_targets)
+            res.rows_full = True  # n_neighbors <= n_samples_fit is checked by the search: every row is complete
+            return res
+
         d, i, st = search(y, x)
         self.search_stats["yx"] = st
-        yx = NeighborsResults(d, i, n_targets=x.shape[0])
+        yx = results(d, i, x.shape[0])
         if only_yx:
             self.yx = yx
             return
         d, i, st = search(x, x)
         self.search_stats["xx"] = st
-        self.xx = NeighborsResults(d, i, n_targets=None)
+        self.xx = results(d, i, None)
         d, i, st = search(y, y)
         self.search_stats["yy"] = st
-        self.yy = NeighborsResults(d, i, n_targets=None)
+        self.yy = results(d, i, None)
         d, i, st = search(x, y)
         self.search_stats["xy"] = st
-        self.xy = NeighborsResults(d, i, n_targets=y.shape[0])
+        self.xy = results(d, i, y.shape[0])
         self.yx = yx
 
     def get_adjacency_matrices(self):

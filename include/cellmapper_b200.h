@@ -127,6 +127,19 @@ int cm_edge_kernel_to_csr(const double* dist, const int64_t* idx, int64_t n_q, i
                           void* stream);
 /* stats3 layout: the reduced [sum d, sum (d-mean)^2, count] of cm_edge_stats. */
 
+/* The same row pass FUSED with the two small transfers (k <= 32): while a row's weights sit in a warp's registers
+ * it is written as a row of the row-normalised float32 CSR (exactly cm_edge_kernel_to_csr with normalize != 0) AND
+ * voted on (cm_vote_argmax: codes != NULL; codes_are_u8: uint8 class codes, n_classes <= 256, so the gather table
+ * of 1.5 M reference cells is 1.5 MB and lives in L2) AND multiplied with up to 4 dense payload columns
+ * (cm_spmm_csr_dense: B != NULL, 1 <= m <= 4, e.g. X_umap).  Same arithmetic as the separate kernels, operation for
+ * operation; one launch instead of seven, and the CSR is written once and not read back.
+ * rows_full != 0: every row has k valid edges (always true for cm_knn_search output): row r starts at r * k, no
+ * count / scan pass.  Replaces knn.py:79-111,166-226 + cellmapper.py:99-137 + :591-605 + :338,628. */
+int cm_map_rows_fused(const double* dist, const int64_t* idx, int64_t n_q, int k, int kernel, const double* stats3,
+                      int rows_full, int32_t* indptr, int32_t* cols, float* vals_f32, const void* codes, int codes_are_u8,
+                      int n_classes, int32_t* out_code, float* out_conf, const void* B, int64_t ldb, int m, int b_dtype,
+                      void* out_dense, int64_t ldo, void* stream);
+
 /* Row-normalise an arbitrary CSR (user-supplied mapping matrix / jaccard counts), float64 in,
  * float32 out: cellmapper.py:126-135. zero_rows_out (device int64, may be NULL) counts zero rows. */
 int cm_csr_row_normalize(const int32_t* indptr, const double* vals_in, int64_t n_rows, float* vals_out,
@@ -179,7 +192,8 @@ int cm_spmm_csr_dense(const int32_t* indptr, const int32_t* cols, const float* v
  * fill : out_indptr (n_q+1) int64 is the exclusive scan of out_row_nnz (caller computes it);
  *        writes sorted columns + float32 values.  Matrices with more than CM_SPGEMM_MAX_COLS columns (the dense
  *        accumulator of one CTA) are processed in gene windows, each re-reading the expression rows. */
-#define CM_SPGEMM_MAX_COLS 49152
+#define CM_SPGEMM_MAX_COLS 43008     /* float32 layers */
+#define CM_SPGEMM_MAX_COLS_F64 24576 /* float64 / integer layers */
 int cm_spgemm_count(const int32_t* m_indptr, const int32_t* m_cols, int64_t n_q, const int64_t* x_indptr,
                     const int32_t* x_cols, int32_t n_genes, int32_t* out_row_nnz, void* stream);
 int cm_spgemm_fill(const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,

@@ -486,7 +486,7 @@ def test_cellmapper_map_matches_reference(torch_cuda, name, kernel):
 
 
 def test_spgemm_wide_layer(torch_cuda):
-    """Sparse layers with more columns than one CTA's accumulator (CM_SPGEMM_MAX_COLS = 49 152; e.g. ATAC peaks)
+    """Sparse layers with more columns than one CTA's accumulator (CM_SPGEMM_MAX_COLS = 43 008; e.g. ATAC peaks)
     are processed in gene windows: same result as scipy's M @ X, bit for bit, rows sorted."""
     torch = torch_cuda
     import scipy.sparse as sp
@@ -494,7 +494,7 @@ def test_spgemm_wide_layer(torch_cuda):
 
     rng = np.random.default_rng(3)
     n_q, n_r, k = 300, 700, 12
-    for n_genes in (49_152, 49_153, 120_001):
+    for n_genes in (43_008, 43_009, 49_153, 120_001):
         cols = np.stack([rng.choice(n_r, k, replace=False) for _ in range(n_q)])
         cols.sort(axis=1)
         w = rng.random((n_q, k)).astype(np.float32)
@@ -907,3 +907,43 @@ def test_two_gpu_sharded_modes_match_single_gpu(torch_cuda):
     assert out["world"] == 2
     assert out["query_sharded_equal"] and out["reference_sharded_equal"] and out["presence_equal"]
     assert out["reference_sharded_expression_equal_1e-6"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_fused_row_pass_equals_separate_kernels(torch_cuda, kernel):
+    """cm_map_rows_fused (CSR + vote + SpMM in one row pass) == cm_edge_kernel_to_csr + cm_vote_argmax + cm_spmm_csr_dense
+    bit for bit: full rows (search output), ragged rows, uint8 / int32 class codes, 1..4 payload columns in float32 and
+    float64, duplicated weights that force class-sum ties, and rows whose weights all vanish."""
+    torch = torch_cuda
+    from cellmapper_b200 import device
+
+    rng = np.random.default_rng(17)
+    n_q, n_r, n_cls = 3_001, 5_000, 7
+    for k, ragged in ((30, False), (30, True), (32, False), (5, True), (1, False)):
+        idx = np.stack([rng.choice(n_r, k, replace=False) for _ in range(n_q)]).astype(np.int64)
+        dist = np.sort(rng.random((n_q, k)) * 3 + 0.05, axis=1)
+        dist[5] = dist[5, 0]          # equal weights: class sums tie exactly
+        dist[6] = 1e3 if kernel in ("gaussian", "scarches") else dist[6]  # weights underflow to 0 (gaussian)
+        if ragged:
+            cut = rng.integers(0, k + 1, n_q)
+            mask = np.arange(k)[None, :] >= cut[:, None]
+            idx[mask], dist[mask] = -1, np.inf
+        codes = rng.integers(0, n_cls, n_r).astype(np.int32)
+        codes[idx[5]] = np.arange(k) % 2 + 3  # two classes, same total weight: the lower class must win
+        d_dev, i_dev = dev(torch, dist), dev(torch, idx)
+        st = device.edge_stats(d_dev, i_dev)
+        ip0, c0, v0 = device.edge_kernel_to_csr(d_dev, i_dev, kernel, st, normalize=True)
+        for m, dt, code_dt in ((2, np.float32, np.uint8), (1, np.float64, np.int32), (4, np.float32, np.int32), (3, np.float64, np.uint8)):
+            payload = rng.standard_normal((n_r, m)).astype(dt)
+            code0, conf0 = device.vote_argmax(ip0, c0, v0, dev(torch, codes), n_cls)
+            out0 = device.spmm(ip0, c0, v0, dev(torch, payload))
+            ip1, c1, v1, code1, conf1, out1 = device.map_rows_fused(
+                d_dev, i_dev, kernel, st, codes=dev(torch, codes.astype(code_dt)), n_classes=n_cls, dense=dev(torch, payload), rows_full=not ragged)
+            nnz = int(ip0[-1])
+            assert torch.equal(ip0, ip1) and torch.equal(c0[:nnz], c1[:nnz]) and torch.equal(v0[:nnz], v1[:nnz])
+            assert torch.equal(code0, code1), (k, ragged, m)
+            assert torch.equal(conf0, conf1)
+            assert out1.dtype == out0.dtype and torch.equal(out0, out1)
+        # no payloads: just the mapping matrix
+        ip2, c2, v2, code2, conf2, out2 = device.map_rows_fused(d_dev, i_dev, kernel, st, rows_full=not ragged)
+        assert code2 is None and out2 is None and torch.equal(ip0, ip2) and torch.equal(v0[:nnz], v2[:nnz])

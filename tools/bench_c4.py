@@ -12,12 +12,14 @@ n_genes, d, k = 30_000, 50, 30
 centres = synth.mixture_centres(32, d)
 xr, cr = synth.mixture_embedding(n_r, centres, seed=1)
 xq, _ = synth.mixture_embedding(n_q, centres, seed=2)
-t0 = time.perf_counter()
-X = synth.sparse_expression(cr, n_genes=n_genes)
-print(f"synthetic X: {X.shape}, nnz/cell {X.nnz / n_r:.0f}, built in {time.perf_counter() - t0:.1f} s", flush=True)
 dev = torch.device("cuda")
+t0 = time.perf_counter()
+xi, xc, xv = synth.sparse_expression_torch(cr, dev, n_genes=n_genes)
+torch.cuda.synchronize()
+print(f"synthetic X: ({n_r}, {n_genes}), nnz/cell {xc.numel() / n_r:.0f}, built in {time.perf_counter() - t0:.1f} s", flush=True)
 q, r = torch.from_numpy(xq).to(dev), torch.from_numpy(xr).to(dev)
-xi, xc, xv = (torch.from_numpy(a).to(dev) for a in (X.indptr.astype(np.int64), X.indices.astype(np.int32), X.data.astype(np.float32)))
+class _X: pass
+X = _X(); X.indptr = xi.cpu().numpy()
 def ev():
     e = torch.cuda.Event(enable_timing=True); e.record(); return e
 for it in range(3):
