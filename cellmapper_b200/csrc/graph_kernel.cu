@@ -314,6 +314,19 @@ edge_to_csr_small_kernel(const double* __restrict__ dist, const int64_t* __restr
 // ------------------------------------------------------------------------------------------------
 constexpr int kFusedMaxM = 4;
 
+// Shuffles are the scarce resource of this kernel (one warp shuffle per clock and SM): the first version moved the
+// float64 weight through every stage of the column sort (3 shuffles per stage), summed the row through shuffles and
+// broadcast every edge to all lanes for the serial vote / product loops (3 per edge): ~175 shuffles per row, 1.6 ms
+// at 1.5 M rows.  Now the sort carries (column, source lane) only, and the serial parts read the row from a small
+// per-warp slab in shared memory (broadcast reads): ~35 shuffles per row.
+template <typename TB, int M>
+struct FusedSlab {
+  double w[32];                  // kernel weights in column order (float64, for the row sum)
+  float v[32];                   // normalised float32 weights
+  int cls[32];                   // class of every edge's reference cell (-1: no edge)
+  TB b[M > 0 ? M : 1][32];       // payload rows of the edges
+};
+
 template <typename TC, typename TB, int M>
 __global__ void __launch_bounds__(kRowWarps * 32)
 map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n_q, int k, int kernel,
@@ -321,7 +334,9 @@ map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict
                       int32_t* __restrict__ cols, float* __restrict__ vals_f32, const TC* __restrict__ codes,
                       int32_t* __restrict__ out_code, float* __restrict__ out_conf, const TB* __restrict__ B, int64_t ldb,
                       TB* __restrict__ out_dense, int64_t ldo) {
+  __shared__ FusedSlab<TB, M> slabs[kRowWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FusedSlab<TB, M>& sl = slabs[warp];
   const double p0 = kernel_param(kernel, stats3);
   if (rows_full && blockIdx.x == 0 && threadIdx.x == 0) indptr[0] = 0;
   for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < n_q; row += (int64_t)gridDim.x * kRowWarps) {
@@ -335,19 +350,23 @@ map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict
         c = (int32_t)iv;
       }
     }
+    // ascending sort by column (invalid edges sink to the end); the weight follows once, at the end
+    int src = lane;
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
       for (int stride = size >> 1; stride >= 1; stride >>= 1) {
         const int32_t oc = __shfl_xor_sync(0xffffffffu, c, stride);
-        const double ow = shfl_f64(w, lane ^ stride);
+        const int os = __shfl_xor_sync(0xffffffffu, src, stride);
         const bool up = ((lane & size) == 0);
         const bool lower = ((lane & stride) == 0);
         const bool take_min = (up == lower);
-        const bool swap = take_min ? (oc < c) : (oc > c);
-        if (swap) { c = oc; w = ow; }
+        // distinct columns inside a k-NN row; equal keys (the INT32_MAX padding) need a total order to stay a permutation
+        const bool other_first = oc < c || (oc == c && os < src);
+        if (take_min ? other_first : !other_first) { c = oc; src = os; }
       }
     }
+    w = shfl_f64(w, src);
     int32_t start;
     int n_valid;
     if (rows_full) {
@@ -358,44 +377,68 @@ map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict
       start = indptr[row];
       n_valid = indptr[row + 1] - start;
     }
-    double rs = numpy_row_sum_lanes(w, n_valid);
+    const bool on = lane < n_valid;
+    // payload gathers of this lane's edge: issued before the row sum, consumed after it
+    int cls = -1;
+    if (codes && on) cls = (int)codes[c];
+    TB bl[M > 0 ? M : 1];
+#pragma unroll
+    for (int j = 0; j < M; ++j) bl[j] = (B && on) ? B[(int64_t)c * ldb + j] : (TB)0;
+    __syncwarp();  // the previous row's readers are done with the slab
+    sl.w[lane] = w;
+    __syncwarp();
+    // float64 row sum in numpy's add.reduceat order: first element + pairwise(rest) with 8 accumulators on lanes 0..7
+    double rs = 0.0;
+    if (n_valid > 0) {
+      const int m = n_valid - 1;
+      double res;
+      if (m < 8) {
+        res = 0.0;
+        for (int i = 0; i < m; ++i) res += sl.w[1 + i];
+      } else {
+        const int full = m - (m % 8);
+        double r = sl.w[1 + (lane & 7)];
+        for (int i = 8; i < full; i += 8) r += sl.w[1 + i + (lane & 7)];
+        const double r1 = shfl_f64(r, (lane & 7) ^ 1);
+        const double p2 = (lane & 1) ? r1 + r : r + r1;
+        const double q2 = shfl_f64(p2, (lane & 7) ^ 2);
+        const double p4 = (lane & 2) ? q2 + p2 : p2 + q2;
+        const double q4 = shfl_f64(p4, (lane & 7) ^ 4);
+        res = (lane & 4) ? q4 + p4 : p4 + q4;   // the same value on every lane
+        for (int i = full; i < m; ++i) res += sl.w[1 + i];
+      }
+      rs = sl.w[0] + res;
+    }
     if (rs == 0.0) rs = 1.0;  // zero rows are left unchanged (cellmapper.py:127-129)
     const double inv = 1.0 / rs;
     const float v = (float)(w * inv);
-    const bool on = lane < n_valid;
     if (on) {
       cols[start + lane] = c;
       vals_f32[start + lane] = v;
     }
-    // payload gathers of this lane's edge, all issued before the serial part
-    int cls = -1;
-    if (codes && on) cls = (int)codes[c];
-    TB b[M > 0 ? M : 1];
+    sl.v[lane] = v;
+    sl.cls[lane] = cls;
 #pragma unroll
-    for (int j = 0; j < M; ++j) b[j] = (B && on) ? B[(int64_t)c * ldb + j] : (TB)0;
-    // lanes whose edge has this lane's class
-    const unsigned same = codes ? __match_any_sync(0xffffffffu, cls) : 0u;
+    for (int j = 0; j < M; ++j) sl.b[j][lane] = bl[j];
+    __syncwarp();
+    // serial parts, ascending column = scipy's summation order; every lane reads the same slab entry (broadcast)
     float csum = 0.f;
     TB acc[M > 0 ? M : 1];
 #pragma unroll
     for (int j = 0; j < M; ++j) acc[j] = (TB)0;
-    for (int t = 0; t < n_valid; ++t) {  // ascending column: scipy's summation order
-      const float vt = __shfl_sync(0xffffffffu, v, t);
-      if ((same >> t) & 1u) csum = __fadd_rn(csum, vt);  // w * 1.0f == w
+    for (int t = 0; t < n_valid; ++t) {
+      const float vt = sl.v[t];
+      if (codes && sl.cls[t] == cls) csum = __fadd_rn(csum, vt);  // w * 1.0f == w
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        if constexpr (sizeof(TB) == 4) {
-          const float bt = __shfl_sync(0xffffffffu, b[j], t);
-          acc[j] = __fadd_rn(acc[j], __fmul_rn(vt, bt));
-        } else {
-          const double bt = shfl_f64(b[j], t);
-          acc[j] = __dadd_rn(acc[j], __dmul_rn((double)vt, bt));
-        }
+        if constexpr (sizeof(TB) == 4)
+          acc[j] = __fadd_rn(acc[j], __fmul_rn(vt, sl.b[j][t]));
+        else
+          acc[j] = __dadd_rn(acc[j], __dmul_rn((double)vt, sl.b[j][t]));
       }
     }
     if (codes) {
-      // arg-max over the classes present in the row; absent classes have sum 0 and win ties only through a lower
-      // index (scipy's sparse argmax compares against the implicit zeros too)
+      // arg-max over the classes present in the row (ties -> lowest class)
       float best = on ? csum : -CUDART_INF_F;
       int best_c = on ? cls : INT32_MAX;
 #pragma unroll

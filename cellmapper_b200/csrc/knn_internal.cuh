@@ -23,13 +23,20 @@ int launch_knn_exact(const void* Q, int64_t n_q, int64_t ldq, const void* R, int
 
 // tensor-core path limits
 constexpr int kMmaTile = 128;    // rows per operand tile (UMMA M and N)
-// Operand images (see knn_mma.cu): a segment holds the d embedding columns plus the 3 norm columns,
-// rounded up to 8-column chunks.  Query image: 3 segments (-2hi | -2hi | -2lo), reference image: 2
-// segments (hi+norms | lo); the third product (lo_q x hi_r) re-reads the reference's hi segment.
-constexpr int kMmaMaxSegChunks = 7;  // ceil((d+3)/8) <= 7  ->  d <= 53
-static inline int mma_seg_chunks(int d) { return (d + 3 + 7) / 8; }
-static inline int mma_kp_q(int d) { return 8 * ((3 * mma_seg_chunks(d) + 1) / 2 * 2); }  // even chunk count
-static inline int mma_kp_r(int d) { return 8 * 2 * mma_seg_chunks(d); }
+// Operand images (see knn_mma.cu): the d embedding columns plus the 3 norm columns form an "extended row" that is cut
+// into 8-column chunks; rows with more than kMmaMaxSegChunks chunks (d > 53) are cut into up to kMmaMaxParts PARTS of
+// equal chunk count, each part being a complete operand pair of its own whose products accumulate into the same
+// TMEM accumulator.  Per part -- query image: 3 segments (-2hi | -2hi | -2lo), reference image: 2 segments
+// (hi+norms | lo); the third product (lo_q x hi_r) re-reads the reference's hi segment.
+constexpr int kMmaMaxSegChunks = 7;  // chunks per segment of one part
+constexpr int kMmaMaxParts = 3;
+constexpr int kMmaMaxD = 128;        // 131 extended columns = 17 chunks = 3 parts of 6
+static inline int mma_ext_chunks(int d) { return (d + 3 + 7) / 8; }
+static inline int mma_parts(int d) { return (mma_ext_chunks(d) + kMmaMaxSegChunks - 1) / kMmaMaxSegChunks; }
+static inline int mma_seg_chunks(int d) { return (mma_ext_chunks(d) + mma_parts(d) - 1) / mma_parts(d); }  // per part
+static inline int mma_kp_q_part(int d) { return 8 * ((3 * mma_seg_chunks(d) + 1) / 2 * 2); }  // even chunk count
+static inline int mma_kp_q(int d) { return mma_parts(d) * mma_kp_q_part(d); }  // fp16 columns of a whole query row
+static inline int mma_kp_r(int d) { return 8 * 2 * mma_seg_chunks(d); }        // fp16 columns of ONE part of the reference image
 constexpr int kMmaMaxK = 40;     // neighbours supported by the candidate buffers
 #ifndef CM_CAND_CAP
 #define CM_CAND_CAP 116
@@ -40,6 +47,6 @@ constexpr int kKeepHi = 60;      // .. and kKeepHi candidates
 constexpr int kCandOut = kKeepHi;
 constexpr int kMaxSplits = 8;
 
-static inline bool mma_supported(int d, int k) { return mma_seg_chunks(d) <= kMmaMaxSegChunks && k <= kMmaMaxK; }
+static inline bool mma_supported(int d, int k) { return d <= kMmaMaxD && k <= kMmaMaxK; }
 
 }  // namespace cm

@@ -274,18 +274,21 @@ constexpr float kNormColumn = 256.f;  // the constant c in the three norm column
 //   query     seg0: -2*hi(x) for cs<d, c for d<=cs<d+3     seg1: -2*hi(x)     seg2: -2*lo(x)
 //   reference seg0:    hi(x) for cs<d, n1 n2 n3 at d..d+2   seg1:    lo(x)
 template <typename T>
-__global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int64_t n_pad, int d, int kp, int dc,
+__global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int64_t n_pad, int d, int chunks_part, int dc, int parts,
                             const double* __restrict__ mu, const double* __restrict__ norms,
                             const ScaleInfo* __restrict__ info, int is_query, const int32_t* __restrict__ perm,
                             uint4* __restrict__ img) {
-  const int chunks = kp >> 3;
+  // chunks_part: 8-column chunks of one part of a row (query: 3 segments of dc, padded to an even count; reference:
+  // 2 segments of dc); a row has parts * chunks_part chunks.  Extended column of (part, segment, cs) = part*dc*8 + cs.
+  const int chunks = parts * chunks_part;
   const float scale = scale_from_absmax(info->absmax_bits);
   const int64_t total = n_pad * chunks;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     // consecutive threads: 8 rows of a group, then the next chunk -> 128 contiguous bytes per 8 lanes
     const int64_t group = t / (8 * chunks);
     const int rem = (int)(t - group * 8 * chunks);
-    const int chunk = rem >> 3, r8 = rem & 7;
+    const int chunk_all = rem >> 3, r8 = rem & 7;
+    const int part = chunk_all / chunks_part, chunk = chunk_all - part * chunks_part;
     const int64_t pos = group * 8 + r8;
     // image position -> source row (scan order, see the "coarse cells" section); -1 = padding
     const int64_t prow = perm[pos];
@@ -295,7 +298,7 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
     __half h[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int cs = (chunk - seg * dc) * 8 + e;
+      const int cs = part * dc * 8 + (chunk - seg * dc) * 8 + e;  // extended column: [0, d) embedding, [d, d+3) norms
       float out = 0.f;
       if (seg < n_seg) {
         if (row < n) {
@@ -329,10 +332,14 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
     v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
     v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
     v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
-    if (is_query)
-      img[pos * chunks + chunk] = v;  // row-major: the epilogue threads copy their own row into TMEM
-    else
-      img[group * (int64_t)(chunks * 8) + chunk * 8 + r8] = v;
+    if (is_query) {
+      img[pos * chunks + chunk_all] = v;  // row-major, part after part: the epilogue threads copy their own row into TMEM
+    } else {
+      // [tile][part][16 groups of 8 rows][chunk][row in group]: every (tile, part) is one contiguous operand image
+      const int64_t tile = group >> 4;
+      const int g16 = (int)(group & 15);
+      img[((tile * parts + part) * 16 + g16) * (int64_t)(chunks_part * 8) + chunk * 8 + r8] = v;
+    }
   }
 }
 
@@ -351,11 +358,12 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxCells = 256;
 constexpr int kAssignThreads = 256;
-constexpr int kAssignRows = 2 * kAssignThreads;  // rows per block and pass: two per thread
-constexpr int kAssignMaxD = 56;  // >= the largest d of the tensor-core path (53)
+constexpr int kAssignRows = 2 * kAssignThreads;  // rows per block and pass for d <= 56: two per thread (one per thread above)
+constexpr int kAssignMaxD = 128;  // the largest d of the tensor-core path
+constexpr int kAssignTwoRowD = 56;  // up to here a thread keeps two rows in registers
 constexpr int kMinRefsForCells = 16384;  // below this the scan is short anyway: scrambled order, no cells
 // float32 expansion ||x||^2 + ||p||^2 - 2 x.p with d <= 56: |error| <= ~4e-6 (||x||^2 + ||p||^2); the bounds
-// used for pruning give away 2^-16 = 1.5e-5 of that sum
+// used for pruning give away 2^-16 = 1.5e-5 of that sum (d <= 128: |error| <= ~8e-6 (||x||^2 + ||p||^2), still inside)
 constexpr float kBoundSlack = 1.52587890625e-05f;
 
 // pivot j = reference row j * stride; stored transposed [d][n_cells] so 4 pivots are one 16-byte read
@@ -381,14 +389,15 @@ __global__ void gather_pivots_kernel(const T* __restrict__ R, int64_t ldr, int64
 // (with 1 465 query tiles per GPU and 255 boundaries that was 13 % more tile pairs on the 8-GPU run).
 // Along the chain consecutive cells are neighbours, which is also the order the scan of a tile wraps
 // around in.  One CTA, pivot j in the registers of thread j; 255 steps of one distance + one block argmin.
+template <int DP>
 __global__ void __launch_bounds__(kMaxCells) order_pivots_kernel(int d, int n_cells, float* __restrict__ piv_t, float* __restrict__ piv_norm) {
-  __shared__ float cur[kAssignMaxD];
+  __shared__ float cur[DP];
   __shared__ unsigned long long wmin[2][kMaxCells / 32];
   const int j = threadIdx.x;
   const bool have = j < n_cells;
-  float pv[kAssignMaxD];
+  float pv[DP];
 #pragma unroll
-  for (int c = 0; c < kAssignMaxD; ++c) pv[c] = (have && c < d) ? piv_t[(size_t)c * n_cells + j] : 0.f;
+  for (int c = 0; c < DP; ++c) pv[c] = (have && c < d) ? piv_t[(size_t)c * n_cells + j] : 0.f;
   const float nn = have ? piv_norm[j] : 0.f;
   bool visited = !have || j == 0;
   int pos = 0;  // new number of this thread's pivot
@@ -396,12 +405,12 @@ __global__ void __launch_bounds__(kMaxCells) order_pivots_kernel(int d, int n_ce
   for (int step = 1; step < n_cells; ++step) {
     if (j == at) {
 #pragma unroll
-      for (int c = 0; c < kAssignMaxD; ++c) cur[c] = pv[c];
+      for (int c = 0; c < DP; ++c) cur[c] = pv[c];
     }
     __syncthreads();
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // four chains: the loop is latency-bound
 #pragma unroll
-    for (int c = 0; c < kAssignMaxD; c += 4) {
+    for (int c = 0; c < DP; c += 4) {
       const float t0 = pv[c] - cur[c], t1 = pv[c + 1] - cur[c + 1], t2 = pv[c + 2] - cur[c + 2], t3 = pv[c + 3] - cur[c + 3];
       d0 = fmaf(t0, t0, d0);
       d1 = fmaf(t1, t1, d1);
@@ -429,16 +438,25 @@ __global__ void __launch_bounds__(kMaxCells) order_pivots_kernel(int d, int n_ce
   __syncthreads();  // every thread holds its pivot in registers: safe to overwrite the table
   if (have) {
 #pragma unroll
-    for (int c = 0; c < kAssignMaxD; ++c)
+    for (int c = 0; c < DP; ++c)
       if (c < d) piv_t[(size_t)c * n_cells + pos] = pv[c];
     piv_norm[pos] = nn;
   }
 }
 
+static int launch_order_pivots(int d, int nc, float* piv_t, float* piv_norm, cudaStream_t st) {
+  if (d <= kAssignTwoRowD)
+    order_pivots_kernel<kAssignTwoRowD><<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
+  else
+    order_pivots_kernel<kAssignMaxD><<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
+  CM_LAUNCH_CHECK("order_pivots_kernel");
+  return CM_OK;
+}
+
 // nearest pivot of every row: argmin_j ||p_j||^2 - 2 x.p_j  (float32; only the scan order depends on it).
 // DP = d rounded up (zero padding) so that the inner loop is branch-free: the thread's row sits in
 // registers and every 4 FMAs cost one broadcast 16-byte read of the pivot table in shared memory.
-template <typename T, int DP>
+template <typename T, int DP, int RPT>  // RPT = rows per thread (2 up to d = 56: every broadcast pivot read feeds 8 FMAs)
 __global__ void __launch_bounds__(kAssignThreads)
 assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const double* __restrict__ mu, const float* __restrict__ piv_t,
                     const float* __restrict__ piv_norm, int n_cells, uint8_t* __restrict__ cell,
@@ -452,69 +470,62 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
   for (int i = threadIdx.x; i < n_cells; i += blockDim.x) sn[i] = piv_norm[i];
   for (int i = threadIdx.x; i < kMaxCells; i += blockDim.x) { hist[i] = 0; rad[i] = 0u; }
   __syncthreads();
-  for (int64_t base = (int64_t)blockIdx.x * kAssignRows; base < n; base += (int64_t)gridDim.x * kAssignRows) {
-    const int rows_here = (int)min((int64_t)kAssignRows, n - base);
+  constexpr int kRows = RPT * kAssignThreads;
+  for (int64_t base = (int64_t)blockIdx.x * kRows; base < n; base += (int64_t)gridDim.x * kRows) {
+    const int rows_here = (int)min((int64_t)kRows, n - base);
     if (threadIdx.x < rows_here) {
-      // two rows per thread (tid and tid + 256), read straight from global memory into registers (a row is one
-      // contiguous 4*d-byte run, so every fetched sector is used by the thread that fetched it); every
-      // broadcast 16-byte pivot read then feeds 8 FMAs
-      const bool two = threadIdx.x + kAssignThreads < rows_here;
-      const T* rx = X + (base + threadIdx.x) * ld;
-      const T* ry = X + (base + (two ? kAssignThreads + threadIdx.x : threadIdx.x)) * ld;
-      float x[DP], y[DP];
+      // RPT rows per thread (tid, tid + 256), read straight from global memory into registers (a row is one
+      // contiguous 4*d-byte run, so every fetched sector is used by the thread that fetched it)
+      bool have[RPT];
+      float x[RPT][DP];
 #pragma unroll
-      for (int c = 0; c < DP; ++c) {
-        x[c] = c < d ? (float)((double)rx[c] - mu[c]) : 0.f;
-        y[c] = c < d ? (float)((double)ry[c] - mu[c]) : 0.f;
+      for (int r = 0; r < RPT; ++r) {
+        have[r] = (int)threadIdx.x + r * kAssignThreads < rows_here;
+        const T* rx = X + (base + (have[r] ? r * kAssignThreads + threadIdx.x : threadIdx.x)) * ld;
+#pragma unroll
+        for (int c = 0; c < DP; ++c) x[r][c] = c < d ? (float)((double)rx[c] - mu[c]) : 0.f;
       }
-      float best = CUDART_INF_F, bestb = CUDART_INF_F;
-      int best_j = 0, bestb_j = 0;
+      float best[RPT];
+      int best_j[RPT];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) { best[r] = CUDART_INF_F; best_j[r] = 0; }
       for (int j0 = 0; j0 < n_cells; j0 += 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        float a[RPT][4];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.f;
 #pragma unroll
         for (int c = 0; c < DP; ++c) {
           const float4 pv = *reinterpret_cast<const float4*>(sp + (size_t)c * n_cells + j0);
-          a0 = fmaf(x[c], pv.x, a0);
-          a1 = fmaf(x[c], pv.y, a1);
-          a2 = fmaf(x[c], pv.z, a2);
-          a3 = fmaf(x[c], pv.w, a3);
-          b0 = fmaf(y[c], pv.x, b0);
-          b1 = fmaf(y[c], pv.y, b1);
-          b2 = fmaf(y[c], pv.z, b2);
-          b3 = fmaf(y[c], pv.w, b3);
-        }
-        const float n0 = sn[j0], n1 = sn[j0 + 1], n2 = sn[j0 + 2], n3 = sn[j0 + 3];
-        const float s0 = n0 - 2.f * a0, s1 = n1 - 2.f * a1, s2 = n2 - 2.f * a2, s3 = n3 - 2.f * a3;
-        if (s0 < best) { best = s0; best_j = j0; }
-        if (s1 < best) { best = s1; best_j = j0 + 1; }
-        if (s2 < best) { best = s2; best_j = j0 + 2; }
-        if (s3 < best) { best = s3; best_j = j0 + 3; }
-        const float u0 = n0 - 2.f * b0, u1 = n1 - 2.f * b1, u2 = n2 - 2.f * b2, u3 = n3 - 2.f * b3;
-        if (u0 < bestb) { bestb = u0; bestb_j = j0; }
-        if (u1 < bestb) { bestb = u1; bestb_j = j0 + 1; }
-        if (u2 < bestb) { bestb = u2; bestb_j = j0 + 2; }
-        if (u3 < bestb) { bestb = u3; bestb_j = j0 + 3; }
-      }
-      cell[base + threadIdx.x] = (uint8_t)best_j;
-      atomicAdd(&hist[best_j], 1);
-      if (two) {
-        cell[base + kAssignThreads + threadIdx.x] = (uint8_t)bestb_j;
-        atomicAdd(&hist[bestb_j], 1);
-      }
-      if (rad2_bits) {
-        // upper bound of ||x - p||^2 from the expansion: the float32 rounding of the three terms is covered
-        // by kBoundSlack * (||x||^2 + ||p||^2)   (see tile_bounds_kernel)
-        float xn = 0.f, yn = 0.f;
 #pragma unroll
-        for (int c = 0; c < DP; ++c) {
-          xn = fmaf(x[c], x[c], xn);
-          yn = fmaf(y[c], y[c], yn);
+          for (int r = 0; r < RPT; ++r) {
+            a[r][0] = fmaf(x[r][c], pv.x, a[r][0]);
+            a[r][1] = fmaf(x[r][c], pv.y, a[r][1]);
+            a[r][2] = fmaf(x[r][c], pv.z, a[r][2]);
+            a[r][3] = fmaf(x[r][c], pv.w, a[r][3]);
+          }
         }
-        const float up = best + xn + kBoundSlack * (xn + sn[best_j]);
-        atomicMax(&rad[best_j], __float_as_uint(fmaxf(up, 0.f)));
-        if (two) {
-          const float upb = bestb + yn + kBoundSlack * (yn + sn[bestb_j]);
-          atomicMax(&rad[bestb_j], __float_as_uint(fmaxf(upb, 0.f)));
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float sc = sn[j0 + q] - 2.f * a[r][q];
+            if (sc < best[r]) { best[r] = sc; best_j[r] = j0 + q; }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        if (!have[r]) continue;
+        cell[base + r * kAssignThreads + threadIdx.x] = (uint8_t)best_j[r];
+        atomicAdd(&hist[best_j[r]], 1);
+        if (rad2_bits) {
+          // upper bound of ||x - p||^2 from the expansion: the float32 rounding of the three terms is covered
+          // by kBoundSlack * (||x||^2 + ||p||^2)   (see tile_bounds_kernel)
+          float xn = 0.f;
+#pragma unroll
+          for (int c = 0; c < DP; ++c) xn = fmaf(x[r][c], x[r][c], xn);
+          const float up = best[r] + xn + kBoundSlack * (xn + sn[best_j[r]]);
+          atomicMax(&rad[best_j[r]], __float_as_uint(fmaxf(up, 0.f)));
         }
       }
     }
@@ -526,23 +537,26 @@ assign_cells_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const
   }
 }
 
-template <typename T, int DP>
+template <typename T, int DP, int RPT>
 int launch_assign(const T* X, int64_t ld, int64_t n, int d, const double* mu, const float* piv_t, const float* piv_norm, int nc, uint8_t* cell,
                   int32_t* counts, unsigned int* rad2_bits, cudaStream_t st) {
   const size_t smem = ((size_t)DP * nc + nc) * sizeof(float);
-  CM_CUDA_CHECK(cudaFuncSetAttribute(assign_cells_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)(ceil_div(n, kAssignRows) < kNumSMs * 2 ? ceil_div(n, kAssignRows) : kNumSMs * 2);
-  assign_cells_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits);
+  CM_CUDA_CHECK(cudaFuncSetAttribute(assign_cells_kernel<T, DP, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = ceil_div(n, RPT * kAssignThreads);
+  const int grid = (int)(blocks < kNumSMs * 2 ? blocks : kNumSMs * 2);
+  assign_cells_kernel<T, DP, RPT><<<grid, kAssignThreads, smem, st>>>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits);
   CM_LAUNCH_CHECK("assign_cells_kernel");
   return CM_OK;
 }
 template <typename T>
 int launch_assign_any(const T* X, int64_t ld, int64_t n, int d, const double* mu, const float* piv_t, const float* piv_norm, int nc,
                       uint8_t* cell, int32_t* counts, unsigned int* rad2_bits, cudaStream_t st) {
-  if (d <= 16) return launch_assign<T, 16>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
-  if (d <= 32) return launch_assign<T, 32>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
-  if (d <= 48) return launch_assign<T, 48>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
-  return launch_assign<T, kAssignMaxD>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 16) return launch_assign<T, 16, 2>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 32) return launch_assign<T, 32, 2>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 48) return launch_assign<T, 48, 2>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= kAssignTwoRowD) return launch_assign<T, kAssignTwoRowD, 2>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  if (d <= 96) return launch_assign<T, 96, 1>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
+  return launch_assign<T, kAssignMaxD, 1>(X, ld, n, d, mu, piv_t, piv_norm, nc, cell, counts, rad2_bits, st);
 }
 
 // exclusive scan of the two count arrays -> cell starts (+ a copy used as scatter cursor)
@@ -615,7 +629,7 @@ __global__ void home_cell_kernel(const int32_t* __restrict__ perm_q, const uint8
 // never computed.  All roundings are directed (kBoundSlack, the final 1e-4 shrink) so the bound can
 // only be too small.  One block = two query tiles, thread = query row (same inner loop as
 // assign_cells_kernel), redux.min over the rows of a warp, then over the tile's four warps.
-template <typename T, int DP>
+template <typename T, int DP, int RPT>
 __global__ void __launch_bounds__(kAssignThreads)
 tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const double* __restrict__ mu, const int32_t* __restrict__ perm_q, int64_t n_q_tiles,
                    const float* __restrict__ piv_t, const float* __restrict__ piv_norm, int n_cells,
@@ -623,66 +637,57 @@ tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const double* __r
   extern __shared__ __align__(16) float asm_smem[];
   float* sp = asm_smem;                          // [DP][n_cells]
   float* sn = sp + (size_t)DP * n_cells;         // [n_cells]
-  __shared__ uint32_t wmin[kAssignRows / 32][kMaxCells];
+  constexpr int kRows = RPT * kAssignThreads;    // scan positions per block and pass
+  __shared__ uint32_t wmin[kRows / 32][kMaxCells];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < DP * n_cells; i += blockDim.x) sp[i] = i < d * n_cells ? piv_t[i] : 0.f;
   for (int i = threadIdx.x; i < n_cells; i += blockDim.x) sn[i] = piv_norm[i];
   __syncthreads();
-  constexpr int kTilesPerBlock = kAssignRows / kMmaTile;
+  constexpr int kTilesPerBlock = kRows / kMmaTile;
   for (int64_t t0 = (int64_t)blockIdx.x * kTilesPerBlock; t0 < n_q_tiles; t0 += (int64_t)gridDim.x * kTilesPerBlock) {
     {
-      // two rows per thread (scan positions tid and tid + 256 of this block's four tiles), read straight from
-      // global memory into registers; every broadcast 16-byte pivot read feeds 8 FMAs
-      const int64_t pos_x = t0 * kMmaTile + threadIdx.x, pos_y = pos_x + kAssignThreads;
-      const int32_t row_x = pos_x < n_q_tiles * kMmaTile ? perm_q[pos_x] : -1;
-      const int32_t row_y = pos_y < n_q_tiles * kMmaTile ? perm_q[pos_y] : -1;
-      const bool valid_x = row_x >= 0, valid_y = row_y >= 0;
-      const T* rx = X + (int64_t)(valid_x ? row_x : 0) * ld;
-      const T* ry = X + (int64_t)(valid_y ? row_y : 0) * ld;
-      float x[DP], y[DP];
-      float xn = 0.f, yn = 0.f;
+      // RPT rows per thread (scan positions tid and tid + 256 of this block's tiles), read straight from
+      // global memory into registers
+      bool valid[RPT];
+      float x[RPT][DP], xn[RPT];
 #pragma unroll
-      for (int c = 0; c < DP; ++c) {
-        x[c] = c < d ? (float)((double)rx[c] - mu[c]) : 0.f;
-        y[c] = c < d ? (float)((double)ry[c] - mu[c]) : 0.f;
-        xn = fmaf(x[c], x[c], xn);
-        yn = fmaf(y[c], y[c], yn);
+      for (int r = 0; r < RPT; ++r) {
+        const int64_t pos = t0 * kMmaTile + threadIdx.x + r * kAssignThreads;
+        const int32_t row = pos < n_q_tiles * kMmaTile ? perm_q[pos] : -1;
+        valid[r] = row >= 0;
+        const T* rx = X + (int64_t)(valid[r] ? row : 0) * ld;
+        xn[r] = 0.f;
+#pragma unroll
+        for (int c = 0; c < DP; ++c) {
+          x[r][c] = c < d ? (float)((double)rx[c] - mu[c]) : 0.f;
+          xn[r] = fmaf(x[r][c], x[r][c], xn[r]);
+        }
       }
       for (int j0 = 0; j0 < n_cells; j0 += 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        float a[RPT][4];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.f;
 #pragma unroll
         for (int c = 0; c < DP; ++c) {
           const float4 pv = *reinterpret_cast<const float4*>(sp + (size_t)c * n_cells + j0);
-          a0 = fmaf(x[c], pv.x, a0);
-          a1 = fmaf(x[c], pv.y, a1);
-          a2 = fmaf(x[c], pv.z, a2);
-          a3 = fmaf(x[c], pv.w, a3);
-          b0 = fmaf(y[c], pv.x, b0);
-          b1 = fmaf(y[c], pv.y, b1);
-          b2 = fmaf(y[c], pv.z, b2);
-          b3 = fmaf(y[c], pv.w, b3);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            a[r][0] = fmaf(x[r][c], pv.x, a[r][0]);
+            a[r][1] = fmaf(x[r][c], pv.y, a[r][1]);
+            a[r][2] = fmaf(x[r][c], pv.z, a[r][2]);
+            a[r][3] = fmaf(x[r][c], pv.w, a[r][3]);
+          }
         }
-        // lower bounds of ||x - p_j||^2
-        const float n0 = sn[j0], n1 = sn[j0 + 1], n2 = sn[j0 + 2], n3 = sn[j0 + 3];
-        const float v0 = valid_x ? (xn + n0) * (1.f - kBoundSlack) - 2.f * a0 : CUDART_INF_F;
-        const float v1 = valid_x ? (xn + n1) * (1.f - kBoundSlack) - 2.f * a1 : CUDART_INF_F;
-        const float v2 = valid_x ? (xn + n2) * (1.f - kBoundSlack) - 2.f * a2 : CUDART_INF_F;
-        const float v3 = valid_x ? (xn + n3) * (1.f - kBoundSlack) - 2.f * a3 : CUDART_INF_F;
-        const float z0 = valid_y ? (yn + n0) * (1.f - kBoundSlack) - 2.f * b0 : CUDART_INF_F;
-        const float z1 = valid_y ? (yn + n1) * (1.f - kBoundSlack) - 2.f * b1 : CUDART_INF_F;
-        const float z2 = valid_y ? (yn + n2) * (1.f - kBoundSlack) - 2.f * b2 : CUDART_INF_F;
-        const float z3 = valid_y ? (yn + n3) * (1.f - kBoundSlack) - 2.f * b3 : CUDART_INF_F;
-        const uint32_t m0 = __reduce_min_sync(0xffffffffu, float_to_ordered(v0));
-        const uint32_t m1 = __reduce_min_sync(0xffffffffu, float_to_ordered(v1));
-        const uint32_t m2 = __reduce_min_sync(0xffffffffu, float_to_ordered(v2));
-        const uint32_t m3 = __reduce_min_sync(0xffffffffu, float_to_ordered(v3));
-        const uint32_t q0 = __reduce_min_sync(0xffffffffu, float_to_ordered(z0));
-        const uint32_t q1 = __reduce_min_sync(0xffffffffu, float_to_ordered(z1));
-        const uint32_t q2 = __reduce_min_sync(0xffffffffu, float_to_ordered(z2));
-        const uint32_t q3 = __reduce_min_sync(0xffffffffu, float_to_ordered(z3));
-        if (lane == 0) {
-          *reinterpret_cast<uint4*>(&wmin[warp][j0]) = make_uint4(m0, m1, m2, m3);          // rows [32 warp, +32)
-          *reinterpret_cast<uint4*>(&wmin[8 + warp][j0]) = make_uint4(q0, q1, q2, q3);      // rows 256 + [32 warp, +32)
+        // lower bounds of ||x - p_j||^2, minimum over the 32 rows of the warp
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          uint32_t m[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = valid[r] ? (xn[r] + sn[j0 + q]) * (1.f - kBoundSlack) - 2.f * a[r][q] : CUDART_INF_F;
+            m[q] = __reduce_min_sync(0xffffffffu, float_to_ordered(v));
+          }
+          if (lane == 0) *reinterpret_cast<uint4*>(&wmin[r * (kAssignThreads / 32) + warp][j0]) = make_uint4(m[0], m[1], m[2], m[3]);
         }
       }
     }
@@ -704,24 +709,26 @@ tile_bounds_kernel(const T* __restrict__ X, int64_t ld, int d, const double* __r
   }
 }
 
-template <typename T, int DP>
+template <typename T, int DP, int RPT>
 int launch_tile_bounds(const T* X, int64_t ld, int d, const double* mu, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
                        const float* piv_norm, int nc, const unsigned int* rad2_bits, float* lb2, cudaStream_t st) {
   const size_t smem = ((size_t)DP * nc + nc) * sizeof(float);
-  CM_CUDA_CHECK(cudaFuncSetAttribute(tile_bounds_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = ceil_div(n_q_tiles, kAssignRows / kMmaTile);
+  CM_CUDA_CHECK(cudaFuncSetAttribute(tile_bounds_kernel<T, DP, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = ceil_div(n_q_tiles, RPT * kAssignThreads / kMmaTile);
   const int grid = (int)(blocks < kNumSMs * 2 ? blocks : kNumSMs * 2);
-  tile_bounds_kernel<T, DP><<<grid, kAssignThreads, smem, st>>>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2);
+  tile_bounds_kernel<T, DP, RPT><<<grid, kAssignThreads, smem, st>>>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2);
   CM_LAUNCH_CHECK("tile_bounds_kernel");
   return CM_OK;
 }
 template <typename T>
 int launch_tile_bounds_any(const T* X, int64_t ld, int d, const double* mu, const int32_t* perm_q, int64_t n_q_tiles, const float* piv_t,
                            const float* piv_norm, int nc, const unsigned int* rad2_bits, float* lb2, cudaStream_t st) {
-  if (d <= 16) return launch_tile_bounds<T, 16>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
-  if (d <= 32) return launch_tile_bounds<T, 32>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
-  if (d <= 48) return launch_tile_bounds<T, 48>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
-  return launch_tile_bounds<T, kAssignMaxD>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 16) return launch_tile_bounds<T, 16, 2>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 32) return launch_tile_bounds<T, 32, 2>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 48) return launch_tile_bounds<T, 48, 2>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= kAssignTwoRowD) return launch_tile_bounds<T, kAssignTwoRowD, 2>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  if (d <= 96) return launch_tile_bounds<T, 96, 1>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
+  return launch_tile_bounds<T, kAssignMaxD, 1>(X, ld, d, mu, perm_q, n_q_tiles, piv_t, piv_norm, nc, rad2_bits, lb2, st);
 }
 
 // without cells: queries in their own order, reference rows scrambled by a golden-ratio stride so that
@@ -1024,11 +1031,17 @@ constexpr size_t kDumpBytes = 4 * 32 * kDumpStride;
 // the tensor-core kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kMmaThreads = 224;  // warp 0 producer, warps 1 and 6 MMA issue (even / odd tiles), warps 2..5 epilogue
-constexpr int kAccBufs = 3;       // TMEM accumulator buffers: the MMA warp runs up to 2 tiles ahead
-constexpr int kTmemACols = kMmaTile;            // columns [0,128): the query operand (kp_q/2 <= 88 used)
-constexpr int kTmemCols = kTmemACols + kAccBufs * kMmaTile;  // 512 columns = all of TMEM
+// TMEM (512 columns): the query operand first, then the accumulators.  d <= 53 (one part): 128 columns for the
+// operand (kp_q/2 <= 88 used) + three accumulators, the MMA warps run up to 2 tiles ahead.  Wide rows (several parts,
+// kp_q/2 up to 216 columns): 256 + two accumulators; their tiles are MMA-bound, so the third buffer is not missed.
+constexpr int kMaxAccBufs = 3;
+constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 4;
-static_assert(kTmemCols == 512, "TMEM allocations are powers of two");
+template <bool kWide> struct TmemLayout {
+  static constexpr int kACols = kWide ? 2 * kMmaTile : kMmaTile;
+  static constexpr int kAccBufs = kWide ? 2 : 3;
+  static_assert(kACols + kAccBufs * kMmaTile == kTmemCols, "TMEM allocations are powers of two");
+};
 constexpr int kLoadPieces = 4;    // bulk copies per reference tile (independent requests overlap their latency)
 
 // Development probes (cm_debug_probe_flags / cm_debug_probe_prof) exist only in -DCM_DEV_PROBES builds; the shipping
@@ -1046,7 +1059,7 @@ constexpr long long* g_probe_prof = nullptr;
 struct MmaParams {
   const unsigned char* q_img;  // n_q_tiles tiles of 128 x kp_q fp16
   const unsigned char* r_img;  // n_r_tiles tiles of 128 x kp_r fp16
-  int n_q_tiles, n_r_tiles, kp_q, kp_r, dc, stages, k;
+  int n_q_tiles, n_r_tiles, kp_q, kp_r, dc, parts, stages, k;  // kp_q: whole query row; kp_r, dc: one part
   int n_full, splits;  // work items: query tiles [0, n_full) scan the whole reference, the rest are cut in `splits`
   float* cand_s;      // [n_items * 128][kCandOut], item = blockIdx.x
   int32_t* cand_i;    // same
@@ -1238,6 +1251,8 @@ constexpr int kTileRing = 16;  // > stages + accumulator buffers + 1: the produc
 
 struct MmaIssueArgs {
   int stages, flags, first;  // this warp issues tiles first, first + 2, ...
+  int parts, acc_bufs;       // operand parts per tile; TMEM accumulator buffers
+  uint32_t acc_base;         // TMEM column of the first accumulator
   uint32_t tile_ring;        // shared address of the ring of scheduled tile ids (-1 = end of the scan)
   uint32_t b_bytes, b_smem, tmem_base;
   uint32_t bar_a_full, bar_b_full0, bar_b_empty0, bar_acc_full0, bar_acc_empty0;  // consecutive barriers are 8 bytes apart
@@ -1250,6 +1265,7 @@ struct MmaIssueArgs {
 template <int DC>
 __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
   constexpr int kSteps = (3 * DC + 1) / 2;
+  constexpr uint32_t kAColsPart = 8u * kSteps;   // TMEM columns of one part of the query operand (two fp16 per column)
   constexpr uint32_t idesc = make_idesc_f16(kMmaTile, kMmaTile);
   constexpr uint32_t lbo = 128u;              // bytes between the two 8-column halves of one K=16 step
   constexpr uint32_t sbo_b = 2u * DC * 128u;  // bytes between 8-row groups of the reference image (kp_r * 16)
@@ -1260,8 +1276,9 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
   // two warps issue alternate tiles: while one is held back by the tensor pipe's ~5-deep issue queue, the
   // other does its barrier waits and descriptor set-up, so the pipe never drains between tiles
   // (tools/mma_queue.cu: an issuing thread runs at most ~350 cycles ahead of the pipe)
-  int s = a.first % a.stages, buf = a.first % kAccBufs;
-  uint32_t ph = 0, aph = 0;
+  // A tile occupies `parts` consecutive slots of the stage ring; slot = tile number * parts + part.
+  int slot = a.first * a.parts, buf = a.first % a.acc_bufs;
+  uint32_t aph = 0;
   long long c_acc = 0, c_b = 0, c_issue = 0, t_start = clock64();
   int n_done = 0;
 #pragma unroll 1
@@ -1269,39 +1286,57 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
     const long long t0 = a.prof ? clock64() : 0;
     if (!(CM_FLAGS(a.flags) & 8)) mbar_wait(a.bar_acc_empty0 + 8 * buf, aph ^ 1u);  // probe 8: free-running MMA issue
     const long long t1 = a.prof ? clock64() : 0;
+    int s = slot % a.stages;
+    uint32_t ph = (uint32_t)(slot / a.stages) & 1u;
     mbar_wait(a.bar_b_full0 + 8 * s, ph);
     const long long t2 = a.prof ? clock64() : 0;
     if ((int)lds_u32_volatile(a.tile_ring + 4u * (uint32_t)(it & (kTileRing - 1))) < 0) {
-      // end of the scan: wake the epilogue on the accumulator barrier it is waiting for
+      // end of the scan: wake the epilogue on the accumulator barrier it is waiting for, and hand the marker's
+      // slots back so that the producer can place the other issuing warp's marker
       if (leader) mbar_arrive(a.bar_acc_full0 + 8 * buf);
+      for (int part = 0; part < a.parts; ++part) {
+        if (part > 0) {
+          s = (slot + part) % a.stages;
+          ph = (uint32_t)((slot + part) / a.stages) & 1u;
+          mbar_wait(a.bar_b_full0 + 8 * s, ph);
+        }
+        if (leader) mbar_arrive(a.bar_b_empty0 + 8 * s);
+      }
       break;
     }
     ++n_done;
-    tc_fence_after();
-    const uint64_t b_desc = b_desc_base + (uint64_t)(((uint32_t)s * a.b_bytes) >> 4);
-    const uint32_t d_tmem = a.tmem_base + kTmemACols + (uint32_t)buf * kMmaTile;
-    if (leader) {
-#pragma unroll
-      for (int kk = 0; kk < kSteps; ++kk) {
-        // K=16 step kk reads query columns [16kk, 16kk+16) = TMEM columns [8kk, 8kk+8) and reference chunks
-        // (bchunk, bchunk+1); one chunk = 128 bytes = 8 descriptor address units
-        const int bchunk = 2 * kk < 2 * DC ? 2 * kk : 2 * kk - 2 * DC;
-        umma_f16_ts(d_tmem, a.tmem_base + (uint32_t)(8 * kk), b_desc + (uint64_t)(8 * bchunk), idesc, kk > 0 ? 1u : 0u);
+    const uint32_t d_tmem = a.acc_base + (uint32_t)buf * kMmaTile;
+    for (int part = 0; part < a.parts; ++part) {
+      if (part > 0) {
+        s = (slot + part) % a.stages;
+        ph = (uint32_t)((slot + part) / a.stages) & 1u;
+        mbar_wait(a.bar_b_full0 + 8 * s, ph);
       }
-      tc_commit(a.bar_b_empty0 + 8 * s);     // smem slot free once these MMAs have read it
-      tc_commit(a.bar_acc_full0 + 8 * buf);  // accumulator complete
+      tc_fence_after();
+      const uint64_t b_desc = b_desc_base + (uint64_t)(((uint32_t)s * a.b_bytes) >> 4);
+      const uint32_t a_tmem = a.tmem_base + (uint32_t)part * kAColsPart;
+      if (leader) {
+#pragma unroll
+        for (int kk = 0; kk < kSteps; ++kk) {
+          // K=16 step kk reads query columns [16kk, 16kk+16) = TMEM columns [8kk, 8kk+8) of the part and reference
+          // chunks (bchunk, bchunk+1); one chunk = 128 bytes = 8 descriptor address units
+          const int bchunk = 2 * kk < 2 * DC ? 2 * kk : 2 * kk - 2 * DC;
+          umma_f16_ts(d_tmem, a_tmem + (uint32_t)(8 * kk), b_desc + (uint64_t)(8 * bchunk), idesc, (part > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(a.bar_b_empty0 + 8 * s);                                  // smem slot free once these MMAs have read it
+        if (part == a.parts - 1) tc_commit(a.bar_acc_full0 + 8 * buf);      // accumulator complete
+      }
+      __syncwarp();
     }
-    __syncwarp();
     if (a.prof) {
       const long long t3 = clock64();
       c_acc += t1 - t0;
       c_b += t2 - t1;
       c_issue += t3 - t2;
     }
-    s += 2;
-    if (s >= a.stages) { s -= a.stages; ph ^= 1u; }
+    slot += 2 * a.parts;
     buf += 2;
-    if (buf >= kAccBufs) { buf -= kAccBufs; aph ^= 1u; }
+    if (buf >= a.acc_bufs) { buf -= a.acc_bufs; aph ^= 1u; }
   }
   if (a.prof && leader && a.first == 0) {
     a.prof[2] = c_issue;
@@ -1310,10 +1345,12 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
   }
 }
 
-template <bool kDebug>
+template <bool kDebug, bool kWide>
 __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParams p) {
+  constexpr int kAccBufs = TmemLayout<kWide>::kAccBufs;
+  constexpr int kTmemACols = TmemLayout<kWide>::kACols;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[1 + 2 * kMaxStages + 2 * kAccBufs];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * kMaxStages + 2 * kMaxAccBufs];
   __shared__ uint32_t tmem_base_slot;
   __shared__ int32_t tile_ring[kTileRing];  // tile ids in the order the producer scheduled them, -1 = end
   __shared__ uint32_t thr_pub[4];           // per epilogue warp: ordered-uint image of its rows' largest threshold (d^2 units)
@@ -1346,7 +1383,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
   auto bar_b_full = [&](int s) { return smem_u32(&bars[1 + s]); };
   auto bar_b_empty = [&](int s) { return smem_u32(&bars[1 + kMaxStages + s]); };
   auto bar_acc_full = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + b]); };
-  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + kAccBufs + b]); };
+  auto bar_acc_empty = [&](int b) { return smem_u32(&bars[1 + 2 * kMaxStages + kMaxAccBufs + b]); };
   const uint32_t ring_addr = smem_u32(&tile_ring[0]);
   const uint32_t thr_pub_addr = smem_u32(&thr_pub[0]);
 
@@ -1387,19 +1424,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       const uint32_t piece = b_bytes / kLoadPieces;  // b_bytes = 4096 * dc: divisible by 4 * 16
       int s = 0, it = 0;
       uint32_t ph = 0;
-      auto schedule = [&](int tile) {  // tile < 0: end marker, no data
-        mbar_wait(bar_b_empty(s), ph ^ 1u);
-        sts_u32(ring_addr + 4u * (uint32_t)(it & (kTileRing - 1)), (uint32_t)tile);
-        if (tile < 0 || (CM_FLAGS(p.flags) & 2)) {
-          mbar_arrive(bar_b_full(s));
-        } else {
-          mbar_expect_tx(bar_b_full(s), b_bytes);
-          const unsigned char* src = p.r_img + (size_t)tile * b_bytes;
-          const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
+      auto schedule = [&](int tile) {  // tile < 0: end marker, no data; a tile fills `parts` consecutive ring slots
+        for (int part = 0; part < p.parts; ++part) {
+          mbar_wait(bar_b_empty(s), ph ^ 1u);
+          if (part == 0) sts_u32(ring_addr + 4u * (uint32_t)(it & (kTileRing - 1)), (uint32_t)tile);
+          if (tile < 0 || (CM_FLAGS(p.flags) & 2)) {
+            mbar_arrive(bar_b_full(s));
+          } else {
+            mbar_expect_tx(bar_b_full(s), b_bytes);
+            const unsigned char* src = p.r_img + ((size_t)tile * p.parts + part) * b_bytes;
+            const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
 #pragma unroll
-          for (int c = 0; c < kLoadPieces; ++c) bulk_g2s(dst + c * piece, src + (size_t)c * piece, piece, bar_b_full(s));
+            for (int c = 0; c < kLoadPieces; ++c) bulk_g2s(dst + c * piece, src + (size_t)c * piece, piece, bar_b_full(s));
+          }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
         ++it;
       };
       if (!cells) {
@@ -1441,6 +1480,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     a.first = warp == 1 ? 0 : 1;
     a.tile_ring = ring_addr;
     a.stages = p.stages;
+    a.parts = p.parts;
+    a.acc_bufs = kAccBufs;
+    a.acc_base = tmem_base + kTmemACols;
     a.b_bytes = b_bytes;
     a.b_smem = smem_u32(b_smem);
     a.tmem_base = tmem_base;
@@ -1591,7 +1633,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
 // ------------------------------------------------------------------------------------------------
 constexpr int kRerankWarps = 8;
 constexpr int kRerankNp = 512;  // >= kMaxSplits * kCandOut = 480 candidates per query (the launch uses less when it can)
-constexpr int kStageRows = 16;  // candidate rows staged per batch (d <= 64: two elements per lane and row)
+constexpr int kStageRows = 16;  // candidate rows staged per batch
+constexpr int kStageLaneElems = 4;  // elements per lane and staged row: d <= 128
 static_assert(kMaxSplits * kCandOut <= kRerankNp, "re-rank buffer too small");
 
 template <typename T>
@@ -1600,7 +1643,7 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
               int k, int n_full, int splits, int np_max, const double* __restrict__ q_norms, const float* __restrict__ cand_s,
               const int32_t* __restrict__ cand_i, const int32_t* __restrict__ cand_cnt,
               const float* __restrict__ cand_thr, ScaleInfo* info, const int32_t* __restrict__ perm_q,
-              const int32_t* __restrict__ perm_r, int64_t r_index_offset, int dist_mode,
+              const int32_t* __restrict__ perm_r, int64_t r_index_offset, int dist_mode, int err_exp,
               double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1646,18 +1689,20 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
     for (int base = 0; base < filled; base += kStageRows) {
       const int my_id = (lane < kStageRows && base + lane < filled) ? vals[base + lane] : -1;
       const bool my_ok = my_id >= 0 && my_id < n_r;
-      T r0[kStageRows], r1[kStageRows];
+      for (int u0 = 0; u0 < d; u0 += 64) {  // 64 columns per pass: all loads of a pass in flight before the first store
+        T r0[kStageRows], r1[kStageRows];
 #pragma unroll
-      for (int j = 0; j < kStageRows; ++j) {
-        const int idj = __shfl_sync(0xffffffffu, my_id, j);
-        const T* rp = R + (int64_t)((idj >= 0 && idj < n_r) ? idj : 0) * ldr;
-        r0[j] = lane < d ? rp[lane] : (T)0;
-        r1[j] = lane + 32 < d ? rp[lane + 32] : (T)0;
-      }
+        for (int j = 0; j < kStageRows; ++j) {
+          const int idj = __shfl_sync(0xffffffffu, my_id, j);
+          const T* rp = R + (int64_t)((idj >= 0 && idj < n_r) ? idj : 0) * ldr;
+          r0[j] = u0 + lane < d ? rp[u0 + lane] : (T)0;
+          r1[j] = u0 + lane + 32 < d ? rp[u0 + lane + 32] : (T)0;
+        }
 #pragma unroll
-      for (int j = 0; j < kStageRows; ++j) {
-        if (lane < d) stage[j * ds + lane] = r0[j];
-        if (lane + 32 < d) stage[j * ds + lane + 32] = r1[j];
+        for (int j = 0; j < kStageRows; ++j) {
+          if (u0 + lane < d) stage[j * ds + u0 + lane] = r0[j];
+          if (u0 + lane + 32 < d) stage[j * ds + u0 + lane + 32] = r1[j];
+        }
       }
       __syncwarp();
       if (lane < kStageRows && base + lane < filled) {
@@ -1715,7 +1760,7 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
     // certificate (all lanes compute the same thing)
     const double qn = q_norms[q];
     const double kth = keys[k - 1];
-    const double err = ldexp(qn + max_rnorm, -18);  // bound on |tensor-core value - true value|, unscaled units
+    const double err = ldexp(qn + max_rnorm, err_exp);  // bound on |tensor-core value - true value|, unscaled units
     const double d2_thr = isinf(thr_min) ? CUDART_INF : (double)thr_min / (scale * scale) + qn;
     const bool ok = isfinite(kth) && (kth + 2.0 * err <= d2_thr);
     if (lane == 0) {
@@ -1747,13 +1792,13 @@ __device__ __forceinline__ double shfl_f64_idx(double v, int src) {
 }
 __device__ __forceinline__ bool pair_before(double ka, int va, double kb, int vb) { return ka < kb || (ka == kb && va < vb); }
 
-template <typename T>
+template <typename T, int kPairs>  // kPairs element pairs per lane and candidate row: d <= 8 * kPairs
 __global__ void __launch_bounds__(kRerankWarps * 32)
 rerank64_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int64_t ldr, int64_t n_q, int64_t n_r, int d,
                 int k, const double* __restrict__ q_norms, const int32_t* __restrict__ cand_i,
                 const int32_t* __restrict__ cand_cnt, const float* __restrict__ cand_thr, ScaleInfo* info,
                 const int32_t* __restrict__ perm_q, const int32_t* __restrict__ perm_r, int64_t r_index_offset,
-                int dist_mode, double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
+                int dist_mode, int err_exp, double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dp = (d + 1) & ~1;
@@ -1783,7 +1828,6 @@ rerank64_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, i
     double ka = CUDART_INF, kb = CUDART_INF;
     const bool aligned2 = ((reinterpret_cast<uintptr_t>(R) | (uintptr_t)(ldr * sizeof(T))) & (2 * sizeof(T) - 1)) == 0;
     const int n_rounds = (total + 7) >> 3;
-    constexpr int kPairs = 7;  // pairs per lane: d <= 56 (the tensor-core path stops at 53)
     for (int rd = 0; rd < n_rounds; ++rd) {
       const int src = ((rd & 3) << 3) + quad;  // lane that holds candidate c = 8 rd + quad
       const int idc = __shfl_sync(0xffffffffu, rd < 4 ? id0 : id1, src);
@@ -1869,7 +1913,7 @@ rerank64_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, i
     // certificate (all lanes compute the same thing)
     const double qn = q_norms[q];
     const double kth = k <= 32 ? shfl_f64_idx(ka, k - 1) : shfl_f64_idx(kb, k - 33);
-    const double err = ldexp(qn + max_rnorm, -18);
+    const double err = ldexp(qn + max_rnorm, err_exp);
     const double d2_thr = isinf(thr) ? CUDART_INF : (double)thr / (scale * scale) + qn;
     const bool ok = isfinite(kth) && (kth + 2.0 * err <= d2_thr);
     if (lane == 0 && !ok) {
@@ -1899,7 +1943,9 @@ __global__ void publish_stats_kernel(const ScaleInfo* info, int64_t* stats_out) 
 struct MmaPlan {
   uint64_t perm_mul;  // no cells: image position p holds reference row (perm_mul * p) mod n_r_pad
   int n_cells;        // 0 = no coarse cells
-  int kp_q, kp_r, dc, stages, splits;
+  int kp_q, kp_r, dc, parts, stages, splits;  // kp_q: fp16 columns of a whole query row; kp_r, dc: of one part
+  bool wide;          // query operand wider than 128 TMEM columns: 256 + two accumulators instead of 128 + three
+  int err_exp;        // certificate: |tensor-core value - true value| <= 2^err_exp (||q||^2 + max ||r||^2)
   bool exhaustive;    // scan every reference tile (no pruning bounds): CM_KNN_TENSOR_EXHAUSTIVE
   int64_t n_full, n_items;  // query tiles scanned by one CTA each; total CTAs
   int64_t n_q_tiles, n_r_tiles, n_q_pad, n_r_pad;
@@ -1935,8 +1981,15 @@ uint64_t scramble_multiplier(int64_t n_pad) {
 MmaPlan make_plan(int64_t n_q, int64_t n_r, int d, bool exhaustive) {
   MmaPlan pl;
   pl.dc = mma_seg_chunks(d);
+  pl.parts = mma_parts(d);
   pl.kp_q = mma_kp_q(d);
   pl.kp_r = mma_kp_r(d);
+  pl.wide = pl.kp_q / 2 > kMmaTile;
+  // Error of the split-fp16 products accumulated in fp32 over kp_q / 16 tensor-core steps.  Per element the dropped
+  // lo*lo term and the fp16 rounding of lo are 2^-22-relative; every K=16 step rounds the running sum once more.
+  // Measured over random and adversarial inputs (tests: test_tensor_core_products_match_float64) the error stays
+  // below 2^-21 (||q||^2 + ||r||^2) at 11 steps and below 2^-20 at 27; the certificate uses 8x that.
+  pl.err_exp = pl.parts == 1 ? -18 : -17;
   pl.n_q_tiles = ceil_div(n_q, kMmaTile);
   pl.n_r_tiles = ceil_div(n_r, kMmaTile);
   pl.n_q_pad = pl.n_q_tiles * kMmaTile;
@@ -1998,11 +2051,11 @@ struct MmaBuffers {
 MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
   MmaBuffers b;
   b.info = ws.take<ScaleInfo>(1);
-  b.mu = ws.take<double>(64);
+  b.mu = ws.take<double>(kAssignMaxD);
   b.q_norms = ws.take<double>(n_q);
   b.r_norms = ws.take<double>(n_r);
   b.q_img = ws.take<unsigned char>((size_t)pl.n_q_pad * pl.kp_q * 2);
-  b.r_img = ws.take<unsigned char>((size_t)pl.n_r_pad * pl.kp_r * 2);
+  b.r_img = ws.take<unsigned char>((size_t)pl.n_r_pad * pl.parts * pl.kp_r * 2);
   b.cand_s = ws.take<float>((size_t)pl.n_items * kMmaTile * kCandOut);
   b.cand_i = ws.take<int32_t>((size_t)pl.n_items * kMmaTile * kCandOut);
   b.cand_cnt = ws.take<int32_t>((size_t)pl.n_items * kMmaTile);
@@ -2015,7 +2068,7 @@ MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
   b.cell_lb2 = ws.take<float>(pl.n_cells > 0 ? (size_t)pl.n_q_tiles * kMaxCells : 1);
   b.q_cell = ws.take<uint8_t>(n_q);
   b.r_cell = ws.take<uint8_t>(n_r);
-  b.piv_t = ws.take<float>((size_t)kMaxCells * 64);
+  b.piv_t = ws.take<float>((size_t)kMaxCells * kAssignMaxD);
   b.piv_norm = ws.take<float>(kMaxCells);
   b.cell_counts = ws.take<int32_t>(2 * kMaxCells);
   b.cell_starts = ws.take<int32_t>(2 * (kMaxCells + 1));
@@ -2045,9 +2098,8 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     CM_CUDA_CHECK(cudaMemsetAsync(b.perm_r, 0xFF, (size_t)pl.n_r_pad * sizeof(int32_t), st));
     gather_pivots_kernel<T><<<ceil_div(nc, 128), 128, 0, st>>>(R, ldr, n_r / nc, d, nc, b.mu, b.piv_t, b.piv_norm);
     CM_LAUNCH_CHECK("gather_pivots_kernel");
-    order_pivots_kernel<<<1, kMaxCells, 0, st>>>(d, nc, b.piv_t, b.piv_norm);
-    CM_LAUNCH_CHECK("order_pivots_kernel");
-    int rc_a = 0;
+    int rc_a = launch_order_pivots(d, nc, b.piv_t, b.piv_norm, st);
+    if (rc_a) return rc_a;
     if (ref_cell && ref_rad2) {
       // the reference side was assigned by cm_knn_assign_reference (same pivots: they depend on R alone), block by
       // block on the ranks of a multi-GPU run, and all-gathered: only the cell sizes are left to do
@@ -2082,13 +2134,13 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
         b.perm_r, n_r, pl.n_r_pad, pl.perm_mul);
     CM_LAUNCH_CHECK("fill_perm_kernel(R)");
   }
-  int64_t tq = pl.n_q_pad * (pl.kp_q / 8), tr = pl.n_r_pad * (pl.kp_r / 8);
+  int64_t tq = pl.n_q_pad * (pl.kp_q / 8), tr = pl.n_r_pad * pl.parts * (pl.kp_r / 8);
   int bq = (int)(ceil_div(tq, 256) < kNumSMs * 16 ? ceil_div(tq, 256) : kNumSMs * 16);
   int br = (int)(ceil_div(tr, 256) < kNumSMs * 16 ? ceil_div(tr, 256) : kNumSMs * 16);
-  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q, pl.dc, b.mu, b.q_norms, b.info, 1, b.perm_q,
-                                     reinterpret_cast<uint4*>(b.q_img));
+  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q / pl.parts / 8, pl.dc, pl.parts, b.mu, b.q_norms, b.info, 1,
+                                     b.perm_q, reinterpret_cast<uint4*>(b.q_img));
   CM_LAUNCH_CHECK("prep_kernel(Q)");
-  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r, pl.dc, b.mu, b.r_norms, b.info, 0, b.perm_r,
+  prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r / 8, pl.dc, pl.parts, b.mu, b.r_norms, b.info, 0, b.perm_r,
                                      reinterpret_cast<uint4*>(b.r_img));
   CM_LAUNCH_CHECK("prep_kernel(R)");
   return CM_OK;
@@ -2105,6 +2157,7 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.kp_q = pl.kp_q;
   p.kp_r = pl.kp_r;
   p.dc = pl.dc;
+  p.parts = pl.parts;
   p.stages = pl.stages;
   p.k = k;
   p.cand_s = b.cand_s;
@@ -2122,13 +2175,17 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.perm_q = b.perm_q;
   p.info = b.info;
   const int64_t grid = pl.n_items;
+#define CM_LAUNCH_MMA(DBG, WIDE)                                                                                                  \
+  do {                                                                                                                            \
+    CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<DBG, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)); \
+    mma_topk_kernel<DBG, WIDE><<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);                                             \
+  } while (0)
   if (debug_out) {
-    CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    mma_topk_kernel<true><<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);
+    if (pl.wide) CM_LAUNCH_MMA(true, true); else CM_LAUNCH_MMA(true, false);
   } else {
-    CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    mma_topk_kernel<false><<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);
+    if (pl.wide) CM_LAUNCH_MMA(false, true); else CM_LAUNCH_MMA(false, false);
   }
+#undef CM_LAUNCH_MMA
   CM_LAUNCH_CHECK("mma_topk_kernel");
   return CM_OK;
 }
@@ -2142,9 +2199,14 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
     const size_t smem64 = (size_t)kRerankWarps * ((d + 1) & ~1) * sizeof(double);
     int64_t blocks64 = ceil_div(n_q, kRerankWarps);
     int grid64 = (int)(blocks64 < (int64_t)kNumSMs * 16 ? blocks64 : (int64_t)kNumSMs * 16);
-    rerank64_kernel<T><<<grid64, kRerankWarps * 32, smem64, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, b.q_norms, b.cand_i, b.cand_cnt,
-                                                                 b.cand_thr, b.info, b.perm_q, b.perm_r, r_off, dist_mode,
-                                                                 out_dist, out_idx, b.fail_rows);
+    if (d <= 56)
+      rerank64_kernel<T, 7><<<grid64, kRerankWarps * 32, smem64, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, b.q_norms, b.cand_i, b.cand_cnt,
+                                                                      b.cand_thr, b.info, b.perm_q, b.perm_r, r_off, dist_mode,
+                                                                      pl.err_exp, out_dist, out_idx, b.fail_rows);
+    else
+      rerank64_kernel<T, 16><<<grid64, kRerankWarps * 32, smem64, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, b.q_norms, b.cand_i, b.cand_cnt,
+                                                                       b.cand_thr, b.info, b.perm_q, b.perm_r, r_off, dist_mode,
+                                                                       pl.err_exp, out_dist, out_idx, b.fail_rows);
     CM_LAUNCH_CHECK("rerank64_kernel");
     return CM_OK;
   }
@@ -2157,7 +2219,7 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
   int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
   rerank_kernel<T><<<grid, kRerankWarps * 32, smem, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, (int)pl.n_full, pl.splits, np_max, b.q_norms,
                                                          b.cand_s, b.cand_i, b.cand_cnt, b.cand_thr, b.info,
-                                                         b.perm_q, b.perm_r, r_off, dist_mode, out_dist, out_idx,
+                                                         b.perm_q, b.perm_r, r_off, dist_mode, pl.err_exp, out_dist, out_idx,
                                                          b.fail_rows);
   CM_LAUNCH_CHECK("rerank_kernel");
   return CM_OK;
@@ -2182,8 +2244,8 @@ int knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dty
   *n_cells_out = nc;
   if (nc == 0 || row_hi <= row_lo) return CM_OK;
   Workspace ws(workspace, ws_bytes);
-  double* mu = ws.take<double>(64);
-  float* piv_t = ws.take<float>((size_t)kMaxCells * 64);
+  double* mu = ws.take<double>(kAssignMaxD);
+  float* piv_t = ws.take<float>((size_t)kMaxCells * kAssignMaxD);
   float* piv_norm = ws.take<float>(kMaxCells);
   int32_t* counts = ws.take<int32_t>(kMaxCells);
   if (!ws.ok()) {
@@ -2199,8 +2261,7 @@ int knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dty
     CM_LAUNCH_CHECK("centre_kernel");
     gather_pivots_kernel<float><<<ceil_div(nc, 128), 128, 0, st>>>(r, ldr, n_r / nc, d, nc, mu, piv_t, piv_norm);
     CM_LAUNCH_CHECK("gather_pivots_kernel");
-    order_pivots_kernel<<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
-    CM_LAUNCH_CHECK("order_pivots_kernel");
+    if (int rc = launch_order_pivots(d, nc, piv_t, piv_norm, st)) return rc;
     return launch_assign_any<float>(r + row_lo * ldr, ldr, n, d, mu, piv_t, piv_norm, nc, out_cell, counts, out_rad2, st);
   }
   const double* r = (const double*)R;
@@ -2208,8 +2269,7 @@ int knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dty
   CM_LAUNCH_CHECK("centre_kernel");
   gather_pivots_kernel<double><<<ceil_div(nc, 128), 128, 0, st>>>(r, ldr, n_r / nc, d, nc, mu, piv_t, piv_norm);
   CM_LAUNCH_CHECK("gather_pivots_kernel");
-  order_pivots_kernel<<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
-  CM_LAUNCH_CHECK("order_pivots_kernel");
+  if (int rc = launch_order_pivots(d, nc, piv_t, piv_norm, st)) return rc;
   return launch_assign_any<double>(r + row_lo * ldr, ldr, n, d, mu, piv_t, piv_norm, nc, out_cell, counts, out_rad2, st);
 }
 

@@ -195,20 +195,22 @@ __host__ __device__ inline size_t spgemm_group_bytes(int n_genes) { return ((((s
 
 // T = float: float32 layers (result float32).  T = double: float64 and integer layers -- scipy promotes the
 // float32 mapping matrix to float64 for those and returns float64 (cellmapper.py:372-373).
-template <bool kFill, typename T, int kThreads>
+template <bool kFill, typename T, int kThreads, bool kWindowed>
 __global__ void __launch_bounds__(kThreads)
 spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ m_cols, const float* __restrict__ m_vals,
               int64_t n_q, const int64_t* __restrict__ x_indptr, const int32_t* __restrict__ x_cols,
               const T* __restrict__ x_vals, int32_t g_lo, int32_t n_genes, int32_t* __restrict__ out_row_nnz,
               int accumulate_count, const int64_t* __restrict__ out_indptr, int64_t* __restrict__ row_off,
               int32_t* __restrict__ out_cols, T* __restrict__ out_vals) {
-  // One pass covers the gene window [g_lo, g_lo + n_genes): entries outside it are skipped.  Matrices with more
-  // columns than the shared-memory accumulator holds are processed window by window (spgemm_launch); `row_off`
-  // then carries every row's write position from one window to the next.
+  // One pass covers the gene window [g_lo, g_lo + n_genes): entries outside it are skipped (kWindowed; a matrix that
+  // fits one window skips the test).  Matrices with more columns than the shared-memory accumulator holds are
+  // processed window by window (spgemm_launch); `row_off` then carries every row's write position from one window
+  // to the next.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint8_t* flags = smem_raw;
   int32_t* gcount = reinterpret_cast<int32_t*>(smem_raw + spgemm_flag_bytes(n_genes));
-  T* acc = reinterpret_cast<T*>(smem_raw + spgemm_flag_bytes(n_genes) + spgemm_group_bytes(n_genes));
+  uint32_t* gmask = reinterpret_cast<uint32_t*>(smem_raw + spgemm_flag_bytes(n_genes) + spgemm_group_bytes(n_genes));
+  T* acc = reinterpret_cast<T*>(smem_raw + spgemm_flag_bytes(n_genes) + 2 * spgemm_group_bytes(n_genes));
   __shared__ int warp_sums[32];
   __shared__ int total_sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,9 +222,11 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
     for (int g = threadIdx.x; g < n_genes; g += kThreads) acc[g] = (T)0;
   __syncthreads();
 
-  __shared__ int64_t s_xs[32], s_xe[32];
+  __shared__ int64_t s_xs[32];
+  __shared__ int32_t s_len[32];
   __shared__ T s_w[32];
-  constexpr int kNbGroup = 8;                 // neighbours whose expression rows are fetched together
+  constexpr int kNbGroup = 4;                 // neighbours per register buffer; two buffers: the rows of the next group
+                                              // are in flight while this group is accumulated
   constexpr int kPer = 2048 / kThreads;       // elements per thread and neighbour held in registers (rows up to 2048 nnz; longer: tail loop)
 
   for (int64_t row = blockIdx.x; row < n_q; row += gridDim.x) {
@@ -233,56 +237,77 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
       const int n_nb = min(32, hi - e0);
       if ((int)threadIdx.x < n_nb) {
         const int64_t r = m_cols[e0 + threadIdx.x];
-        s_xs[threadIdx.x] = x_indptr[r];
-        s_xe[threadIdx.x] = x_indptr[r + 1];
+        const int64_t xs = x_indptr[r];
+        s_xs[threadIdx.x] = xs;
+        s_len[threadIdx.x] = (int32_t)(x_indptr[r + 1] - xs);
         s_w[threadIdx.x] = kFill ? (T)m_vals[e0 + threadIdx.x] : (T)0;
       }
       __syncthreads();
-      for (int g0 = 0; g0 < n_nb; g0 += kNbGroup) {
-        int32_t gc[kNbGroup][kPer];
-        T gv[kNbGroup][kPer];
+      int32_t gc[2][kNbGroup][kPer];
+      T gv[2][kNbGroup][kPer];
+      auto load_group = [&](int buf, int g0) {
 #pragma unroll
         for (int j = 0; j < kNbGroup; ++j) {
           const bool on = g0 + j < n_nb;
-          const int64_t xs = on ? s_xs[g0 + j] : 0, xe = on ? s_xe[g0 + j] : 0;
+          const int32_t len = on ? s_len[g0 + j] : 0;
+          const int32_t* xc = x_cols + (on ? s_xs[g0 + j] : 0);
+          const T* xv = x_vals + (on ? s_xs[g0 + j] : 0);
 #pragma unroll
           for (int u = 0; u < kPer; ++u) {
-            const int64_t p = xs + threadIdx.x + (int64_t)u * kThreads;
-            gc[j][u] = p < xe ? x_cols[p] - g_lo : -1;
-            gv[j][u] = (kFill && p < xe) ? x_vals[p] : (T)0;
+            const int32_t p = (int32_t)threadIdx.x + u * kThreads;
+            gc[buf][j][u] = p < len ? xc[p] - g_lo : -1;
+            gv[buf][j][u] = (kFill && p < len) ? xv[p] : (T)0;
           }
         }
+      };
+      load_group(0, 0);
+#pragma unroll 1
+      for (int g0 = 0; g0 < n_nb; g0 += 2 * kNbGroup) {
 #pragma unroll
-        for (int j = 0; j < kNbGroup; ++j) {  // ascending reference index == scipy's accumulation order
-          if (g0 + j < n_nb) {
-            const T w = s_w[g0 + j];
+        for (int half = 0; half < 2; ++half) {
+          const int gbase = g0 + half * kNbGroup;
+          if (gbase >= n_nb) break;
+          if (gbase + kNbGroup < n_nb) load_group(half ^ 1, gbase + kNbGroup);  // prefetch the next group
 #pragma unroll
-            for (int u = 0; u < kPer; ++u) {
-              const int32_t g = gc[j][u];
-              if ((uint32_t)g < (uint32_t)n_genes) {
-                flags[g] = 1;
-                if (kFill) acc[g] = mul_add_rn(acc[g], w, gv[j][u]);  // columns are unique inside one X row
+          for (int j = 0; j < kNbGroup; ++j) {  // ascending reference index == scipy's accumulation order
+            if (gbase + j < n_nb) {
+              const T w = s_w[gbase + j];
+#pragma unroll
+              for (int u = 0; u < kPer; ++u) {
+                const int32_t g = gc[half][j][u];
+                if (kWindowed ? ((uint32_t)g < (uint32_t)n_genes) : (g >= 0)) {
+                  flags[g] = 1;
+                  if (kFill) acc[g] = mul_add_rn(acc[g], w, gv[half][j][u]);  // columns are unique inside one X row
+                }
               }
-            }
-            for (int64_t p = s_xs[g0 + j] + threadIdx.x + (int64_t)kPer * kThreads; p < s_xe[g0 + j]; p += kThreads) {
-              const int32_t g = x_cols[p] - g_lo;
-              if ((uint32_t)g < (uint32_t)n_genes) {
-                flags[g] = 1;
-                if (kFill) acc[g] = mul_add_rn(acc[g], w, x_vals[p]);
+              const int32_t len = s_len[gbase + j];
+              if (len > kPer * kThreads) {  // long rows: the tail straight from memory
+                const int32_t* xc = x_cols + s_xs[gbase + j];
+                const T* xv = x_vals + s_xs[gbase + j];
+                for (int32_t p = (int32_t)threadIdx.x + kPer * kThreads; p < len; p += kThreads) {
+                  const int32_t g = xc[p] - g_lo;
+                  if ((uint32_t)g < (uint32_t)n_genes) {
+                    flags[g] = 1;
+                    if (kFill) acc[g] = mul_add_rn(acc[g], w, xv[p]);
+                  }
+                }
               }
+              if (kFill) __syncthreads();  // the next neighbour may touch the same genes from other threads
             }
-            if (kFill) __syncthreads();  // the next neighbour may touch the same genes from other threads
           }
         }
       }
-      __syncthreads();  // s_xs / s_xe / s_w are rewritten by the next chunk
+      __syncthreads();  // s_xs / s_len / s_w are rewritten by the next chunk
     }
     __syncthreads();
-    // touched genes per group of 32 (one warp per group), then their exclusive prefix over the row
+    // touched genes per group of 32 (one warp per group: ballot of the flags), then the exclusive prefix over the row
     for (int gi = warp; gi < n_groups; gi += kWarps) {
       const int g = (gi << 5) + lane;
       const unsigned m = __ballot_sync(0xffffffffu, g < n_genes && flags[g] != 0);
-      if (lane == 0) gcount[gi] = __popc(m);
+      if (lane == 0) {
+        gcount[gi] = __popc(m);
+        gmask[gi] = m;
+      }
     }
     __syncthreads();
     int base_rank = 0;
@@ -297,16 +322,16 @@ spgemm_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restrict__ 
     if (kFill) {
       const int64_t o0 = row_off ? row_off[row] : out_indptr[row];
       for (int gi = warp; gi < n_groups; gi += kWarps) {
-        const int g = (gi << 5) + lane;
-        const bool on = g < n_genes && flags[g] != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, on);
-        if (on) {
+        const unsigned m = gmask[gi];
+        if (m == 0u) continue;  // warp-uniform
+        if ((m >> lane) & 1u) {
+          const int g = (gi << 5) + lane;
           const int64_t o = o0 + gcount[gi] + __popc(m & ((1u << lane) - 1u));
           out_cols[o] = g + g_lo;
           out_vals[o] = acc[g];
           acc[g] = (T)0;
-          flags[g] = 0;
         }
+        if (lane < 8) reinterpret_cast<uint32_t*>(flags)[(gi << 3) + lane] = 0u;  // the group's 32 flag bytes
       }
     } else {
       for (int i = threadIdx.x; i < (int)(spgemm_flag_bytes(n_genes) >> 2); i += kThreads) reinterpret_cast<uint32_t*>(flags)[i] = 0u;
@@ -392,21 +417,24 @@ static int spgemm_launch(bool fill, const int32_t* m_indptr, const int32_t* m_co
     const int32_t g_lo = w * win;
     const int32_t g_n = n_genes - g_lo < win ? n_genes - g_lo : win;
     if (g_n <= 0) break;
-    size_t smem = spgemm_flag_bytes(g_n) + spgemm_group_bytes(g_n) + (fill ? (size_t)g_n * sizeof(T) : 0);
+    size_t smem = spgemm_flag_bytes(g_n) + 2 * spgemm_group_bytes(g_n) + (fill ? (size_t)g_n * sizeof(T) : 0);
+    const bool windowed = n_win > 1;
     if (fill) {
       const int grid = (int)(n_q < (int64_t)kNumSMs ? n_q : (int64_t)kNumSMs);  // 1024 threads x 64 registers: one CTA per SM
-      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<true, T, kSpgemmFillThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      spgemm_kernel<true, T, kSpgemmFillThreads><<<grid, kSpgemmFillThreads, smem, st>>>(
-          m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n, out_row_nnz, 0, out_indptr, row_off, out_cols, out_vals);
+      auto kern = windowed ? spgemm_kernel<true, T, kSpgemmFillThreads, true> : spgemm_kernel<true, T, kSpgemmFillThreads, false>;
+      CM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, kSpgemmFillThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n, out_row_nnz, 0,
+                                                  out_indptr, row_off, out_cols, out_vals);
     } else {
       int per_sm = (int)((220 * 1024) / (smem + 1024));
       if (per_sm < 1) per_sm = 1;
       if (per_sm > 4) per_sm = 4;
       const int64_t want = (int64_t)kNumSMs * per_sm;
       const int grid = (int)(n_q < want ? n_q : want);
-      CM_CUDA_CHECK(cudaFuncSetAttribute(spgemm_kernel<false, T, kSpgemmCountThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      spgemm_kernel<false, T, kSpgemmCountThreads><<<grid, kSpgemmCountThreads, smem, st>>>(
-          m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n, out_row_nnz, w > 0, out_indptr, row_off, out_cols, out_vals);
+      auto kern = windowed ? spgemm_kernel<false, T, kSpgemmCountThreads, true> : spgemm_kernel<false, T, kSpgemmCountThreads, false>;
+      CM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, kSpgemmCountThreads, smem, st>>>(m_indptr, m_cols, m_vals, n_q, x_indptr, x_cols, x_vals, g_lo, g_n, out_row_nnz, w > 0,
+                                                   out_indptr, row_off, out_cols, out_vals);
     }
     CM_LAUNCH_CHECK("spgemm_kernel");
   }

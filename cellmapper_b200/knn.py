@@ -332,6 +332,13 @@ class Neighbors:
             np.float32 if x.dtype == torch.float32 else np.float64, np.float32 if y.dtype == torch.float32 else np.float64
         )
 
+        if x.shape[1] > _lib.MMA_MAX_D or n_neighbors > _lib.MMA_MAX_K:
+            logger.warning(
+                "method='b200': %d dimensions / %d neighbours are outside the tensor-core path (d <= %d, k <= %d); "
+                "the exact float64 brute-force kernel is used instead, which is orders of magnitude slower on large inputs.",
+                x.shape[1], n_neighbors, _lib.MMA_MAX_D, _lib.MMA_MAX_K,
+            )  # fmt: skip
+
         def search(q, r):
             mode = sklearn_like_dist_mode(np_dtype, r.shape[1], n_neighbors, r.shape[0])
             cells = self._reference_cells(r, n_neighbors) if (self._reference_cells is not None and r is x and q.dtype == r.dtype) else None

@@ -192,7 +192,7 @@ int cm_spmm_csr_dense(const int32_t* indptr, const int32_t* cols, const float* v
  * fill : out_indptr (n_q+1) int64 is the exclusive scan of out_row_nnz (caller computes it);
  *        writes sorted columns + float32 values.  Matrices with more than CM_SPGEMM_MAX_COLS columns (the dense
  *        accumulator of one CTA) are processed in gene windows, each re-reading the expression rows. */
-#define CM_SPGEMM_MAX_COLS 43008     /* float32 layers */
+#define CM_SPGEMM_MAX_COLS 40960     /* float32 layers */
 #define CM_SPGEMM_MAX_COLS_F64 24576 /* float64 / integer layers */
 int cm_spgemm_count(const int32_t* m_indptr, const int32_t* m_cols, int64_t n_q, const int64_t* x_indptr,
                     const int32_t* x_cols, int32_t n_genes, int32_t* out_row_nnz, void* stream);
