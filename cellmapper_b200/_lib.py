@@ -20,6 +20,7 @@ KERNELS = {"gaussian": 0, "scarches": 1, "inverse_distance": 2, "equal": 3}
 DIST_SQRT_F64, DIST_SKLEARN_F32, DIST_SQUARED = 0, 1, 2
 KNN_AUTO, KNN_EXACT_F64, KNN_TENSOR_EXHAUSTIVE = 0, 1, 2
 EDGE_STATS_WORKSPACE_BYTES = 32768
+KNN_ASSIGN_WORKSPACE_BYTES = 262144
 SPGEMM_MAX_COLS = 40960
 MMA_MAX_D, MMA_MAX_K = 128, 40  # limits of the tensor-core search (csrc/knn_internal.cuh)
 SELECT_WORKSPACE_BYTES = 16384

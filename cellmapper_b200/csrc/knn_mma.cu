@@ -1252,6 +1252,7 @@ constexpr int kTileRing = 16;  // > stages + accumulator buffers + 1: the produc
 struct MmaIssueArgs {
   int stages, flags, first;  // this warp issues tiles first, first + 2, ...
   int parts, acc_bufs;       // operand parts per tile; TMEM accumulator buffers
+  int n_issuers;             // issuing warps: 2 for single-part tiles, 1 for multi-part tiles (see mma_issue_loop)
   uint32_t acc_base;         // TMEM column of the first accumulator
   uint32_t tile_ring;        // shared address of the ring of scheduled tile ids (-1 = end of the scan)
   uint32_t b_bytes, b_smem, tmem_base;
@@ -1277,12 +1278,17 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
   // other does its barrier waits and descriptor set-up, so the pipe never drains between tiles
   // (tools/mma_queue.cu: an issuing thread runs at most ~350 cycles ahead of the pipe)
   // A tile occupies `parts` consecutive slots of the stage ring; slot = tile number * parts + part.
+  // Multi-part tiles have ONE issuing warp: a parity wait on a stage is only unambiguous if the stage's previous use is
+  // known to be complete, which holds when the same warp consumed it (with two warps and 3 parts over 3 stages, warp A
+  // waiting for tile 2 saw the completed phase of tile 0 -- same parity -- before tile 1's copies, warp B's, had landed:
+  // it multiplied a half-loaded tile and the pipeline deadlocked).  Their tiles are 18-27 MMAs long, so the issue
+  // queue does not drain between tiles anyway.
   int slot = a.first * a.parts, buf = a.first % a.acc_bufs;
   uint32_t aph = 0;
   long long c_acc = 0, c_b = 0, c_issue = 0, t_start = clock64();
   int n_done = 0;
 #pragma unroll 1
-  for (int it = a.first;; it += 2) {
+  for (int it = a.first;; it += a.n_issuers) {
     const long long t0 = a.prof ? clock64() : 0;
     if (!(CM_FLAGS(a.flags) & 8)) mbar_wait(a.bar_acc_empty0 + 8 * buf, aph ^ 1u);  // probe 8: free-running MMA issue
     const long long t1 = a.prof ? clock64() : 0;
@@ -1334,8 +1340,8 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
       c_b += t2 - t1;
       c_issue += t3 - t2;
     }
-    slot += 2 * a.parts;
-    buf += 2;
+    slot += a.n_issuers * a.parts;
+    buf += a.n_issuers;
     if (buf >= a.acc_bufs) { buf -= a.acc_bufs; aph ^= 1u; }
   }
   if (a.prof && leader && a.first == 0) {
@@ -1470,17 +1476,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
         }
       }
       const int n_sched = it;
-      schedule(-1);  // one end marker per MMA warp (they own alternate iterations)
-      schedule(-1);
+      schedule(-1);  // one end marker per issuing warp (two warps own alternate iterations of single-part tiles)
+      if (p.parts == 1) schedule(-1);
       if (p.info) atomicAdd(&p.info->tiles_scanned, (unsigned long long)n_sched);
     }
-  } else if (warp == 1 || warp == 6) {
+  } else if (warp == 1 || (warp == 6 && p.parts == 1)) {
     // ===== MMA issuers: the whole warp runs the loop, one elected lane drives the tensor core =====
     MmaIssueArgs a;
     a.first = warp == 1 ? 0 : 1;
     a.tile_ring = ring_addr;
     a.stages = p.stages;
     a.parts = p.parts;
+    a.n_issuers = p.parts == 1 ? 2 : 1;
     a.acc_bufs = kAccBufs;
     a.acc_base = tmem_base + kTmemACols;
     a.b_bytes = b_bytes;
@@ -1502,7 +1509,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       case 6: mma_issue_loop<6>(a); break;
       default: mma_issue_loop<7>(a); break;
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4, one query row per thread =====
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;

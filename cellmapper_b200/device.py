@@ -167,7 +167,7 @@ def knn_assign_reference(r: torch.Tensor, k: int, row_lo: int = 0, row_hi: int |
     with torch.cuda.device(dev):
         cell = torch.empty(max(row_hi - row_lo, 1), dtype=torch.uint8, device=dev)
         rad2 = torch.zeros(256, dtype=torch.int32, device=dev)
-        ws = torch.empty(128 * 1024, dtype=torch.uint8, device=dev)
+        ws = torch.empty(_lib.KNN_ASSIGN_WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
         _call(
             "cm_knn_assign_reference", _ptr(r), n_r, r.stride(0), d, _dtype_code(r), int(k), int(row_lo), int(row_hi),
             _ptr(cell), _ptr(rad2), ctypes.addressof(n_cells), _ptr(ws), ws.numel(), _stream(),

@@ -87,8 +87,10 @@ int cm_knn_search(const void* Q, int64_t n_q, int64_t ldq, const void* R, int64_
  * out_cell (row_hi - row_lo bytes), out_rad2_bits (256 float bit patterns of squared radii over these rows; combine
  * the blocks of all ranks with an integer max) --, the host side all-gathers the blocks (cellmapper_b200/dist.py),
  * and cm_knn_search_cells takes the assembled arrays (ref_cell: n_r bytes; both NULL: same as cm_knn_search).
- * n_cells_out (host) = 0: this reference is searched without cells, pass NULL.  workspace: >= 128 KB.
+ * n_cells_out (host) = 0: this reference is searched without cells, pass NULL.
+ * workspace: >= CM_KNN_ASSIGN_WORKSPACE_BYTES.
  * Replaces nothing in the reference (it has no sharded search). */
+#define CM_KNN_ASSIGN_WORKSPACE_BYTES 262144
 int cm_knn_assign_reference(const void* R, int64_t n_r, int64_t ldr, int d, int dtype, int k, int64_t row_lo, int64_t row_hi,
                             uint8_t* out_cell, uint32_t* out_rad2_bits, int* n_cells_out, void* workspace,
                             size_t workspace_bytes, void* stream);
