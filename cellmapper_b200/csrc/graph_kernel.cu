@@ -314,156 +314,173 @@ edge_to_csr_small_kernel(const double* __restrict__ dist, const int64_t* __restr
 // ------------------------------------------------------------------------------------------------
 constexpr int kFusedMaxM = 4;
 
-// Shuffles are the scarce resource of this kernel (one warp shuffle per clock and SM): the first version moved the
-// float64 weight through every stage of the column sort (3 shuffles per stage), summed the row through shuffles and
-// broadcast every edge to all lanes for the serial vote / product loops (3 per edge): ~175 shuffles per row, 1.6 ms
-// at 1.5 M rows.  Now the sort carries (column, source lane) only, and the serial parts read the row from a small
-// per-warp slab in shared memory (broadcast reads): ~35 shuffles per row.
+// Two phases per batch of 32 rows and warp.  Phase A, one ROW per step, lane = edge: kernel weight, column sort
+// ((column, source lane) through the bitonic network, the float64 weight follows once), float64 row sum in numpy's
+// order, normalise, coalesced CSR store; the normalised weights and the gathered payloads of the row are parked in a
+// shared-memory slab.  Phase B, lane = ROW: the inherently serial parts -- class sums and payload products, added in
+// ascending column order like scipy -- run as 32 independent chains, one per lane, reading the slab without bank
+// conflicts (row stride 33).  History: with every lane of a warp executing the serial loop of ONE row (broadcast by
+// shuffles, then by slab reads) the kernel issued ~600 warp instructions per row, 1.4-1.6 ms at 1.5 M rows.
+constexpr int kFusedWarps = 4;
+constexpr int kSlabStride = 33;
+
 template <typename TB, int M>
 struct FusedSlab {
-  double w[32];                  // kernel weights in column order (float64, for the row sum)
-  float v[32];                   // normalised float32 weights
-  int cls[32];                   // class of every edge's reference cell (-1: no edge)
-  TB b[M > 0 ? M : 1][32];       // payload rows of the edges
+  double w[32];                           // phase A: kernel weights of the current row in column order
+  int n_valid[32];                        // per row of the batch
+  float v[32 * kSlabStride];              // [row][edge] normalised float32 weights
+  int cls[32 * kSlabStride];              // [row][edge] class of the edge's reference cell
+  TB b[(M > 0 ? M : 1) * 32 * kSlabStride];  // [payload column][row][edge]
 };
 
 template <typename TC, typename TB, int M>
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kFusedWarps * 32)
 map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int64_t n_q, int k, int kernel,
                       const double* __restrict__ stats3, int rows_full, int32_t* __restrict__ indptr,
                       int32_t* __restrict__ cols, float* __restrict__ vals_f32, const TC* __restrict__ codes,
                       int32_t* __restrict__ out_code, float* __restrict__ out_conf, const TB* __restrict__ B, int64_t ldb,
                       TB* __restrict__ out_dense, int64_t ldo) {
-  __shared__ FusedSlab<TB, M> slabs[kRowWarps];
+  extern __shared__ __align__(16) unsigned char fused_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  FusedSlab<TB, M>& sl = slabs[warp];
+  FusedSlab<TB, M>& sl = reinterpret_cast<FusedSlab<TB, M>*>(fused_smem)[warp];
   const double p0 = kernel_param(kernel, stats3);
   if (rows_full && blockIdx.x == 0 && threadIdx.x == 0) indptr[0] = 0;
-  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < n_q; row += (int64_t)gridDim.x * kRowWarps) {
-    double w = 0.0;
-    int32_t c = INT32_MAX;
-    if (lane < k) {
-      const double dv = dist[row * k + lane];
-      const int64_t iv = idx[row * k + lane];
-      if (edge_valid(dv, iv)) {
-        w = kernel_value(kernel, dv, p0);
-        c = (int32_t)iv;
+  const bool payloads = codes != nullptr || B != nullptr;
+  for (int64_t row0 = ((int64_t)blockIdx.x * kFusedWarps + warp) * 32; row0 < n_q; row0 += (int64_t)gridDim.x * kFusedWarps * 32) {
+    const int rows_here = (int)min((int64_t)32, n_q - row0);
+    __syncwarp();  // phase B of the previous batch has read the slab
+    // ---------------- phase A: one row per step, lane = edge ----------------
+    for (int r = 0; r < rows_here; ++r) {
+      const int64_t row = row0 + r;
+      double w = 0.0;
+      int32_t c = INT32_MAX;
+      if (lane < k) {
+        const double dv = dist[row * k + lane];
+        const int64_t iv = idx[row * k + lane];
+        if (edge_valid(dv, iv)) {
+          w = kernel_value(kernel, dv, p0);
+          c = (int32_t)iv;
+        }
       }
-    }
-    // ascending sort by column (invalid edges sink to the end); the weight follows once, at the end
-    int src = lane;
+      // ascending sort by column (invalid edges sink to the end); the weight follows once, at the end
+      int src = lane;
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
+      for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
-      for (int stride = size >> 1; stride >= 1; stride >>= 1) {
-        const int32_t oc = __shfl_xor_sync(0xffffffffu, c, stride);
-        const int os = __shfl_xor_sync(0xffffffffu, src, stride);
-        const bool up = ((lane & size) == 0);
-        const bool lower = ((lane & stride) == 0);
-        const bool take_min = (up == lower);
-        // distinct columns inside a k-NN row; equal keys (the INT32_MAX padding) need a total order to stay a permutation
-        const bool other_first = oc < c || (oc == c && os < src);
-        if (take_min ? other_first : !other_first) { c = oc; src = os; }
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+          const int32_t oc = __shfl_xor_sync(0xffffffffu, c, stride);
+          const int os = __shfl_xor_sync(0xffffffffu, src, stride);
+          const bool up = ((lane & size) == 0);
+          const bool lower = ((lane & stride) == 0);
+          const bool take_min = (up == lower);
+          // distinct columns inside a k-NN row; equal keys (the INT32_MAX padding) need a total order to stay a permutation
+          const bool other_first = oc < c || (oc == c && os < src);
+          if (take_min ? other_first : !other_first) { c = oc; src = os; }
+        }
       }
-    }
-    w = shfl_f64(w, src);
-    int32_t start;
-    int n_valid;
-    if (rows_full) {
-      start = (int32_t)(row * k);
-      n_valid = k;
-      if (lane == 0) indptr[row + 1] = start + k;
-    } else {
-      start = indptr[row];
-      n_valid = indptr[row + 1] - start;
-    }
-    const bool on = lane < n_valid;
-    // payload gathers of this lane's edge: issued before the row sum, consumed after it
-    int cls = -1;
-    if (codes && on) cls = (int)codes[c];
-    TB bl[M > 0 ? M : 1];
-#pragma unroll
-    for (int j = 0; j < M; ++j) bl[j] = (B && on) ? B[(int64_t)c * ldb + j] : (TB)0;
-    __syncwarp();  // the previous row's readers are done with the slab
-    sl.w[lane] = w;
-    __syncwarp();
-    // float64 row sum in numpy's add.reduceat order: first element + pairwise(rest) with 8 accumulators on lanes 0..7
-    double rs = 0.0;
-    if (n_valid > 0) {
-      const int m = n_valid - 1;
-      double res;
-      if (m < 8) {
-        res = 0.0;
-        for (int i = 0; i < m; ++i) res += sl.w[1 + i];
+      w = shfl_f64(w, src);
+      int32_t start;
+      int n_valid;
+      if (rows_full) {
+        start = (int32_t)(row * k);
+        n_valid = k;
+        if (lane == 0) indptr[row + 1] = start + k;
       } else {
-        const int full = m - (m % 8);
-        double r = sl.w[1 + (lane & 7)];
-        for (int i = 8; i < full; i += 8) r += sl.w[1 + i + (lane & 7)];
-        const double r1 = shfl_f64(r, (lane & 7) ^ 1);
-        const double p2 = (lane & 1) ? r1 + r : r + r1;
-        const double q2 = shfl_f64(p2, (lane & 7) ^ 2);
-        const double p4 = (lane & 2) ? q2 + p2 : p2 + q2;
-        const double q4 = shfl_f64(p4, (lane & 7) ^ 4);
-        res = (lane & 4) ? q4 + p4 : p4 + q4;   // the same value on every lane
-        for (int i = full; i < m; ++i) res += sl.w[1 + i];
+        start = indptr[row];
+        n_valid = indptr[row + 1] - start;
       }
-      rs = sl.w[0] + res;
-    }
-    if (rs == 0.0) rs = 1.0;  // zero rows are left unchanged (cellmapper.py:127-129)
-    const double inv = 1.0 / rs;
-    const float v = (float)(w * inv);
-    if (on) {
-      cols[start + lane] = c;
-      vals_f32[start + lane] = v;
-    }
-    sl.v[lane] = v;
-    sl.cls[lane] = cls;
+      const bool on = lane < n_valid;
+      // payload gathers of this lane's edge: issued before the row sum, consumed after it
+      int cls = -1;
+      if (codes && on) cls = (int)codes[c];
+      TB bl[M > 0 ? M : 1];
 #pragma unroll
-    for (int j = 0; j < M; ++j) sl.b[j][lane] = bl[j];
+      for (int j = 0; j < M; ++j) bl[j] = (B && on) ? B[(int64_t)c * ldb + j] : (TB)0;
+      __syncwarp();  // the previous row's readers are done with sl.w
+      sl.w[lane] = w;
+      __syncwarp();
+      // float64 row sum in numpy's add.reduceat order: first element + pairwise(rest) with 8 accumulators on lanes 0..7
+      double rs = 0.0;
+      if (n_valid > 0) {
+        const int m = n_valid - 1;
+        double res;
+        if (m < 8) {
+          res = 0.0;
+          for (int i = 0; i < m; ++i) res += sl.w[1 + i];
+        } else {
+          const int full = m - (m % 8);
+          double rr = sl.w[1 + (lane & 7)];
+          for (int i = 8; i < full; i += 8) rr += sl.w[1 + i + (lane & 7)];
+          const double r1 = shfl_f64(rr, (lane & 7) ^ 1);
+          const double p2 = (lane & 1) ? r1 + rr : rr + r1;
+          const double q2 = shfl_f64(p2, (lane & 7) ^ 2);
+          const double p4 = (lane & 2) ? q2 + p2 : p2 + q2;
+          const double q4 = shfl_f64(p4, (lane & 7) ^ 4);
+          res = (lane & 4) ? q4 + p4 : p4 + q4;   // the same value on every lane
+          for (int i = full; i < m; ++i) res += sl.w[1 + i];
+        }
+        rs = sl.w[0] + res;
+      }
+      if (rs == 0.0) rs = 1.0;  // zero rows are left unchanged (cellmapper.py:127-129)
+      const double inv = 1.0 / rs;
+      const float v = (float)(w * inv);
+      if (on) {
+        cols[start + lane] = c;
+        vals_f32[start + lane] = v;
+      }
+      if (payloads) {
+        sl.v[r * kSlabStride + lane] = v;
+        sl.cls[r * kSlabStride + lane] = cls;
+#pragma unroll
+        for (int j = 0; j < M; ++j) sl.b[(j * 32 + r) * kSlabStride + lane] = bl[j];
+        if (lane == 0) sl.n_valid[r] = n_valid;
+      }
+    }
+    if (!payloads) continue;
     __syncwarp();
-    // serial parts, ascending column = scipy's summation order; every lane reads the same slab entry (broadcast)
-    float csum = 0.f;
-    TB acc[M > 0 ? M : 1];
-#pragma unroll
-    for (int j = 0; j < M; ++j) acc[j] = (TB)0;
-    for (int t = 0; t < n_valid; ++t) {
-      const float vt = sl.v[t];
-      if (codes && sl.cls[t] == cls) csum = __fadd_rn(csum, vt);  // w * 1.0f == w
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
-        if constexpr (sizeof(TB) == 4)
-          acc[j] = __fadd_rn(acc[j], __fmul_rn(vt, sl.b[j][t]));
-        else
-          acc[j] = __dadd_rn(acc[j], __dmul_rn((double)vt, sl.b[j][t]));
-      }
-    }
-    if (codes) {
-      // arg-max over the classes present in the row (ties -> lowest class)
-      float best = on ? csum : -CUDART_INF_F;
-      int best_c = on ? cls : INT32_MAX;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-        if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
-      }
-      if (lane == 0) {
-        // no positive class sum (an empty row, or weights that all rounded to 0: csr_matmat drops zero sums, so
-        // the row of M @ onehot is empty): scipy's sparse argmax / max return column 0 / 0
-        if (n_valid == 0 || !(best > 0.f)) {
-          best_c = 0;
-          best = 0.f;
+    // ---------------- phase B: lane = row; serial sums in ascending column order (scipy's) ----------------
+    if (lane < rows_here) {
+      const int64_t row = row0 + lane;
+      const int n = sl.n_valid[lane];
+      const float* vrow = sl.v + lane * kSlabStride;
+      if (codes) {
+        const int* crow = sl.cls + lane * kSlabStride;
+        float best = 0.f;  // an empty row, or weights that all rounded to 0 (csr_matmat drops zero sums, so the row
+        int best_c = 0;    // of M @ onehot is empty): scipy's sparse argmax / max return column 0 / 0
+        unsigned done = 0u;
+        for (int t = 0; t < n; ++t) {
+          if ((done >> t) & 1u) continue;
+          const int cl = crow[t];
+          float sum = 0.f;
+          for (int u = t; u < n; ++u) {
+            if (crow[u] == cl) {
+              sum = __fadd_rn(sum, vrow[u]);  // w * 1.0f == w
+              done |= 1u << u;
+            }
+          }
+          if (sum > best || (sum == best && sum > 0.f && cl < best_c)) { best = sum; best_c = cl; }  // ties -> lowest class
         }
         out_code[row] = best_c;
         out_conf[row] = best;
       }
-    }
-    if (B && lane < M) {
-      TB r = acc[0];
+      if (B) {
+        TB acc[M > 0 ? M : 1];
 #pragma unroll
-      for (int j = 1; j < M; ++j)
-        if (lane == j) r = acc[j];
-      out_dense[row * ldo + lane] = r;
+        for (int j = 0; j < M; ++j) acc[j] = (TB)0;
+        for (int t = 0; t < n; ++t) {
+          const float vt = vrow[t];
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+            const TB bt = sl.b[(j * 32 + lane) * kSlabStride + t];
+            if constexpr (sizeof(TB) == 4)
+              acc[j] = __fadd_rn(acc[j], __fmul_rn(vt, bt));
+            else
+              acc[j] = __dadd_rn(acc[j], __dmul_rn((double)vt, bt));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < M; ++j) out_dense[row * ldo + j] = acc[j];
+      }
     }
   }
 }
@@ -557,9 +574,14 @@ template <typename TC, typename TB>
 static int launch_fused(int m, int grid, cudaStream_t st, const double* dist, const int64_t* idx, int64_t n_q, int k, int kernel,
                         const double* stats3, int rows_full, int32_t* indptr, int32_t* cols, float* vals_f32, const TC* codes,
                         int32_t* out_code, float* out_conf, const TB* B, int64_t ldb, TB* out_dense, int64_t ldo) {
-#define CM_FUSED(M)                                                                                                       \
-  map_rows_fused_kernel<TC, TB, M><<<grid, kRowWarps * 32, 0, st>>>(dist, idx, n_q, k, kernel, stats3, rows_full, indptr, cols, \
-                                                                    vals_f32, codes, out_code, out_conf, B, ldb, out_dense, ldo)
+#define CM_FUSED(M)                                                                                                             \
+  do {                                                                                                                          \
+    const size_t smem = kFusedWarps * sizeof(FusedSlab<TB, M>);                                                                \
+    CM_CUDA_CHECK(cudaFuncSetAttribute(map_rows_fused_kernel<TC, TB, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    map_rows_fused_kernel<TC, TB, M><<<grid, kFusedWarps * 32, smem, st>>>(dist, idx, n_q, k, kernel, stats3, rows_full, indptr,  \
+                                                                           cols, vals_f32, codes, out_code, out_conf, B, ldb,     \
+                                                                           out_dense, ldo);                                      \
+  } while (0)
   switch (B ? m : 0) {
     case 0: CM_FUSED(0); break;
     case 1: CM_FUSED(1); break;
@@ -597,8 +619,8 @@ extern "C" int cm_map_rows_fused(const double* dist, const int64_t* idx, int64_t
     const int rc = inclusive_scan_i32(indptr + 1, n_q, cols, st);
     if (rc) return rc;
   }
-  const int64_t blocks = ceil_div(n_q, kRowWarps);
-  const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  const int64_t blocks = ceil_div(n_q, kFusedWarps * 32);
+  const int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
   const bool f64 = B && b_dtype == CM_F64;
 #define CM_GO(TC, TB)                                                                                                            \
   return launch_fused<TC, TB>(m, grid, st, dist, idx, n_q, k, kernel, stats3, rows_full, indptr, cols, vals_f32, (const TC*)codes, \
