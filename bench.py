@@ -201,6 +201,16 @@ class CpuPath:
         self.kind = "reference" if self.shim is not None else "port"
 
     def run(self, name, xr, xq, labels=None, umap=None, layer=None):
+        # under torchrun every rank starts with OMP_NUM_THREADS=1; the CPU arm gets the host's cores back
+        try:
+            from threadpoolctl import threadpool_limits
+
+            with threadpool_limits(limits=_host_cores()):
+                return self._run(name, xr, xq, labels, umap, layer)
+        except ImportError:
+            return self._run(name, xr, xq, labels, umap, layer)
+
+    def _run(self, name, xr, xq, labels=None, umap=None, layer=None):
         kind = WORKLOADS[name][0]
         t0 = time.perf_counter()
         if self.shim is not None:

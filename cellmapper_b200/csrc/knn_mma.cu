@@ -390,7 +390,8 @@ __global__ void gather_pivots_kernel(const T* __restrict__ R, int64_t ldr, int64
 // Along the chain consecutive cells are neighbours, which is also the order the scan of a tile wraps
 // around in.  One CTA, pivot j in the registers of thread j; 255 steps of one distance + one block argmin.
 template <int DP>
-__global__ void __launch_bounds__(kMaxCells) order_pivots_kernel(int d, int n_cells, float* __restrict__ piv_t, float* __restrict__ piv_norm) {
+__global__ void __launch_bounds__(kMaxCells) order_pivots_kernel(int d, int n_cells, float* __restrict__ piv_t, float* __restrict__ piv_norm,
+                                                                 int64_t stride, int32_t* __restrict__ piv_rows) {
   __shared__ float cur[DP];
   __shared__ unsigned long long wmin[2][kMaxCells / 32];
   const int j = threadIdx.x;
@@ -441,14 +442,17 @@ __global__ void __launch_bounds__(kMaxCells) order_pivots_kernel(int d, int n_ce
     for (int c = 0; c < DP; ++c)
       if (c < d) piv_t[(size_t)c * n_cells + pos] = pv[c];
     piv_norm[pos] = nn;
+    if (piv_rows) piv_rows[pos] = (int32_t)(j * stride);  // pivot j was reference row j * stride (gather_pivots_kernel)
   }
+  if (piv_rows && !have && j < kMaxCells) piv_rows[j] = -1;
 }
 
-static int launch_order_pivots(int d, int nc, float* piv_t, float* piv_norm, cudaStream_t st) {
+static int launch_order_pivots(int d, int nc, float* piv_t, float* piv_norm, cudaStream_t st, int64_t stride = 0,
+                               int32_t* piv_rows = nullptr) {
   if (d <= kAssignTwoRowD)
-    order_pivots_kernel<kAssignTwoRowD><<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
+    order_pivots_kernel<kAssignTwoRowD><<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm, stride, piv_rows);
   else
-    order_pivots_kernel<kAssignMaxD><<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm);
+    order_pivots_kernel<kAssignMaxD><<<1, kMaxCells, 0, st>>>(d, nc, piv_t, piv_norm, stride, piv_rows);
   CM_LAUNCH_CHECK("order_pivots_kernel");
   return CM_OK;
 }
@@ -738,6 +742,242 @@ __global__ void fill_perm_kernel(int32_t* __restrict__ perm, int64_t n, int64_t 
     const int64_t row = mul ? (int64_t)((mul * (uint64_t)pos) % (uint64_t)n_pad) : pos;
     perm[pos] = row < n ? (int32_t)row : -1;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// coarse cells on the tensor cores (single-part rows, d <= 53)
+//
+// Nearest pivot of every reference / query row and the (query tile, cell) pruning bounds are one n x 256 x d
+// contraction each.  As SIMT float32 kernels (assign_cells_kernel, tile_bounds_kernel: still used for d > 53 and by
+// cm_knn_assign_reference) they were 3.6 ms of a 48 ms step at 1.5 M rows and 8.4 of 37 ms at a 10 M-row
+// reference.  Here the 256 pivots are a two-tile operand image resident in shared memory, a CTA turns 128 rows at a
+// time into the split-fp16 query operand ON THE FLY (straight from the caller's array into tensor memory: no operand
+// image is needed yet, which matters because the scan order -- the images' row order -- is what this step decides)
+// and multiplies them with both pivot tiles; the accumulator holds s^2 (||p||^2 - 2 x.p) for the 128 x 128 pairs.
+//   kAssign : arg-min over the 256 pivots per row -> cell number, cell histogram, and (reference side) the cell
+//             radii  max ||x - p||^2, rounded up
+//   kBounds : rows in scan order; per tile and pivot the minimum over the tile's rows of a LOWER bound of
+//             ||x - p||^2, then lb2 as in tile_bounds_kernel
+// The products carry a relative error of 2^-18 (||x||^2 + ||p||^2) at most (test_tensor_core_products_match_float64);
+// the bounds give away kBoundSlack = 2^-16 of that sum, like the float32 kernels did.
+// Two CTAs per SM (256 of the 512 TMEM columns each: 128 operand + 128 accumulator), phases of a tile in sequence;
+// the other CTA fills the gaps.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPivThreads = 160;  // warp 0: operand copies + MMA issue; warps 1..4: one row per thread
+enum PivMode { kPivAssign = 0, kPivBounds = 1 };
+
+struct PivParams {
+  int64_t ld, n;              // rows of X
+  int d, dc, kp_q, kp_r, n_cells;
+  const double* mu;
+  const double* norms;        // ||x - mu||^2 per row (rowstats_kernel)
+  const ScaleInfo* info;
+  const unsigned char* piv_img;  // operand image of the pivots: 2 tiles of 128 x kp_r fp16
+  const float* piv_norm;      // [n_cells] ||p - mu||^2, float32
+  int64_t n_tiles;            // 128-row tiles
+  // kPivAssign
+  uint8_t* cell;
+  int32_t* counts;
+  unsigned int* rad2_bits;    // null on the query side
+  // kPivBounds
+  const int32_t* perm;        // scan position -> row, -1 = padding
+  const unsigned int* rad2_in;
+  float* lb2;                 // [n_tiles][kMaxCells]
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __restrict__ X, const PivParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float sn[kMaxCells];
+  __shared__ int hist[kMaxCells];
+  __shared__ unsigned int rad[kMaxCells];
+  __shared__ uint32_t wmin[4][MODE == kPivBounds ? kMaxCells : 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_bytes = (uint32_t)kMmaTile * p.kp_r * 2;
+  const uint32_t bar_b = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+  for (int i = threadIdx.x; i < kMaxCells; i += kPivThreads) {
+    sn[i] = i < p.n_cells ? p.piv_norm[i] : 0.f;
+    hist[i] = 0;
+    rad[i] = 0u;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar_b, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_slot), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) {  // the pivot image: both tiles, once per CTA
+    mbar_expect_tx(bar_b, 2 * b_bytes);
+    bulk_g2s(smem_u32(smem), p.piv_img, b_bytes, bar_b);
+    bulk_g2s(smem_u32(smem) + b_bytes, p.piv_img + b_bytes, b_bytes, bar_b);
+  }
+  const float scale = scale_from_absmax(p.info->absmax_bits);
+  const float inv_s2 = 1.f / (scale * scale);  // exact: a power of two
+  const int quad = warp & 3;                   // TMEM lane quadrant of warps 1..4
+  const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const uint32_t t_lane_acc = t_lane_a + kMmaTile;
+  const int chunks = p.kp_q >> 3;
+  const int k_steps = p.kp_q >> 4;
+  const uint32_t idesc = make_idesc_f16(kMmaTile, kMmaTile);
+  uint32_t mma_phase = 0;
+  bool b_ready = false;
+
+  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    int64_t row = -1;
+    float xn_up = 0.f, xn_dn = 0.f;
+    if (warp >= 1) {
+      // this thread's row -> split-fp16 query operand [-2hi, c c c | -2hi | -2lo] -> tensor memory (lane = row)
+      const int64_t pos = tile * kMmaTile + quad * 32 + lane;
+      if (MODE == kPivBounds)
+        row = p.perm[pos];
+      else
+        row = pos < p.n ? pos : -1;
+      if (row >= 0) {
+        const double nn = p.norms[row];
+        xn_up = __double2float_ru(nn);
+        xn_dn = __double2float_rd(nn);
+      }
+      const T* xr = X + (row >= 0 ? row : 0) * p.ld;
+      auto make_chunk = [&](int chunk) {
+        const int seg = chunk / p.dc;
+        const int cs0 = (chunk - seg * p.dc) * 8;
+        __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int cs = cs0 + e;
+          float out = 0.f;
+          if (row >= 0 && seg < 3) {
+            if (cs < p.d) {
+              const float xs = (float)(((double)xr[cs] - p.mu[cs]) * (double)scale);
+              const __half hi = __float2half_rn(xs);
+              const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
+              out = seg == 2 ? -2.f * lo : -2.f * __half2float(hi);
+            } else if (seg == 0 && cs < p.d + 3) {
+              out = kNormColumn;
+            }
+          }
+          h[e] = __float2half_rn(out);
+        }
+        uint4 v;
+        v.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
+        v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
+        return v;
+      };
+      for (int c = 0; c < chunks; c += 2) {
+        const uint4 a = make_chunk(c), b = make_chunk(c + 1);
+        tmem_st_32x32b_x8(t_lane_a + 4 * c, a, b);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    }
+    __syncthreads();  // the operand is in tensor memory; the previous tile's accumulator has been read
+    float best = CUDART_INF_F;
+    int best_j = 0;
+    for (int nt = 0; nt < 2; ++nt) {
+      if (warp == 0) {
+        if (!b_ready) {
+          mbar_wait(bar_b, 0);
+          b_ready = true;
+        }
+        tc_fence_after();
+        const uint64_t b_desc = make_smem_desc(smem_u32(smem) + nt * b_bytes, 128u, 2u * p.dc * 128u);
+        if (elect_one()) {
+          for (int kk = 0; kk < k_steps; ++kk) {
+            const int bchunk = 2 * kk < 2 * p.dc ? 2 * kk : 2 * kk - 2 * p.dc;
+            umma_f16_ts(tmem_base + kMmaTile, tmem_base + (uint32_t)(8 * kk), b_desc + (uint64_t)(8 * bchunk), idesc, kk > 0 ? 1u : 0u);
+          }
+          tc_commit(bar_mma);
+        }
+        __syncwarp();
+      } else {
+        mbar_wait(bar_mma, mma_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[64];
+          tmem_ld_32x32b_x64(t_lane_acc + 64 * half, v);
+          tmem_ld_wait();
+          const int j0 = nt * 128 + half * 64;
+          if (MODE == kPivAssign) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const float sc = __uint_as_float(v[j]);
+              if (j0 + j < p.n_cells && sc < best) { best = sc; best_j = j0 + j; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              // lower bound of ||x - p_j||^2: the product's error and the roundings are inside kBoundSlack
+              float lb = CUDART_INF_F;
+              if (row >= 0) lb = fmaf(__uint_as_float(v[j]), inv_s2, xn_dn) - kBoundSlack * (xn_up + sn[j0 + j]);
+              const uint32_t m = __reduce_min_sync(0xffffffffu, float_to_ordered(lb));
+              if (lane == 0) wmin[quad][j0 + j] = m;
+            }
+          }
+        }
+        tc_fence_before();
+      }
+      mma_phase ^= 1u;
+      __syncthreads();  // accumulator free for the next pivot tile / the next row tile
+    }
+    if (MODE == kPivAssign) {
+      if (warp >= 1 && row >= 0) {
+        p.cell[row] = (uint8_t)best_j;
+        atomicAdd(&hist[best_j], 1);
+        if (p.rad2_bits) {
+          // upper bound of ||x - p||^2 = ||x||^2 + (||p||^2 - 2 x.p)
+          const float up = fmaf(best, inv_s2, xn_up) + kBoundSlack * (xn_up + sn[best_j]);
+          atomicMax(&rad[best_j], __float_as_uint(fmaxf(up, 0.f)));
+        }
+      }
+    } else {
+      for (int c = threadIdx.x; c < p.n_cells; c += kPivThreads) {
+        const uint32_t m = min(min(wmin[0][c], wmin[1][c]), min(wmin[2][c], wmin[3][c]));
+        const float dmin2 = fmaxf(ordered_to_float(m), 0.f);  // +inf for a tile of padding rows only
+        const float rho = sqrtf(__uint_as_float(p.rad2_in[c])) * (1.f + 1e-6f);
+        const float lb = fmaxf(sqrtf(dmin2) * (1.f - 1e-6f) - rho, 0.f);
+        p.lb2[tile * kMaxCells + c] = lb * lb * (1.f - 1e-4f);
+      }
+      __syncthreads();  // wmin is rewritten by the next tile
+    }
+  }
+  if (MODE == kPivAssign) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n_cells; i += kPivThreads) {
+      if (hist[i]) atomicAdd(&p.counts[i], hist[i]);
+      if (p.rad2_bits && rad[i]) atomicMax(&p.rad2_bits[i], rad[i]);
+    }
+  }
+  if (warp == 0 && !b_ready) mbar_wait(bar_b, 0);  // never leave with a bulk copy in flight
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+template <typename T, int MODE>
+int launch_pivot_tc(const T* X, PivParams p, cudaStream_t st) {
+  const size_t smem = (size_t)2 * kMmaTile * p.kp_r * 2;
+  CM_CUDA_CHECK(cudaFuncSetAttribute(pivot_tc_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t want = (int64_t)kNumSMs * 2;
+  const int grid = (int)(p.n_tiles < want ? p.n_tiles : want);
+  if (grid <= 0) return CM_OK;
+  pivot_tc_kernel<T, MODE><<<grid, kPivThreads, smem, st>>>(X, p);
+  CM_LAUNCH_CHECK("pivot_tc_kernel");
+  return CM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2053,6 +2293,8 @@ struct MmaBuffers {
   int32_t* cell_counts; // [2][kMaxCells]  (0 = reference, 1 = query)
   int32_t* cell_starts; // [2][kMaxCells + 1]
   int32_t* cell_cursor; // [2][kMaxCells]
+  unsigned char* piv_img;  // operand image of the pivots (two tiles), tensor-core cell assignment
+  int32_t* piv_rows;       // [kMaxCells] reference row of every pivot, in cell order
 };
 
 MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
@@ -2080,6 +2322,8 @@ MmaBuffers carve(Workspace& ws, const MmaPlan& pl, int64_t n_q, int64_t n_r) {
   b.cell_counts = ws.take<int32_t>(2 * kMaxCells);
   b.cell_starts = ws.take<int32_t>(2 * (kMaxCells + 1));
   b.cell_cursor = ws.take<int32_t>(2 * kMaxCells);
+  b.piv_img = ws.take<unsigned char>((size_t)2 * kMmaTile * pl.kp_r * 2);
+  b.piv_rows = ws.take<int32_t>(kMaxCells);
   return b;
 }
 
@@ -2105,8 +2349,26 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     CM_CUDA_CHECK(cudaMemsetAsync(b.perm_r, 0xFF, (size_t)pl.n_r_pad * sizeof(int32_t), st));
     gather_pivots_kernel<T><<<ceil_div(nc, 128), 128, 0, st>>>(R, ldr, n_r / nc, d, nc, b.mu, b.piv_t, b.piv_norm);
     CM_LAUNCH_CHECK("gather_pivots_kernel");
-    int rc_a = launch_order_pivots(d, nc, b.piv_t, b.piv_norm, st);
+    int rc_a = launch_order_pivots(d, nc, b.piv_t, b.piv_norm, st, n_r / nc, b.piv_rows);
     if (rc_a) return rc_a;
+    // single-part rows: nearest pivots and pruning bounds on the tensor cores (pivot_tc_kernel); wide rows: SIMT float32
+    const bool tc = pl.parts == 1;
+    PivParams pp{};
+    if (tc) {
+      prep_kernel<T><<<ceil_div((int64_t)kMaxCells * (pl.kp_r / 8), 256), 256, 0, st>>>(R, ldr, n_r, kMaxCells, d, pl.kp_r / 8, pl.dc, 1, b.mu,
+                                                                                     b.r_norms, b.info, 0, b.piv_rows,
+                                                                                     reinterpret_cast<uint4*>(b.piv_img));
+      CM_LAUNCH_CHECK("prep_kernel(pivots)");
+      pp.d = d;
+      pp.dc = pl.dc;
+      pp.kp_q = pl.kp_q;
+      pp.kp_r = pl.kp_r;
+      pp.n_cells = nc;
+      pp.mu = b.mu;
+      pp.info = b.info;
+      pp.piv_img = b.piv_img;
+      pp.piv_norm = b.piv_norm;
+    }
     if (ref_cell && ref_rad2) {
       // the reference side was assigned by cm_knn_assign_reference (same pivots: they depend on R alone), block by
       // block on the ranks of a multi-GPU run, and all-gathered: only the cell sizes are left to do
@@ -2115,11 +2377,23 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
       const int gh = (int)(ceil_div(n_r, kAssignThreads * 8) < kNumSMs * 4 ? ceil_div(n_r, kAssignThreads * 8) : kNumSMs * 4);
       cell_hist_kernel<<<gh, kAssignThreads, 0, st>>>(b.r_cell, n_r, b.cell_counts);
       CM_LAUNCH_CHECK("cell_hist_kernel");
+    } else if (tc) {
+      PivParams pr = pp;
+      pr.ld = ldr; pr.n = n_r; pr.norms = b.r_norms; pr.n_tiles = ceil_div(n_r, kMmaTile);
+      pr.cell = b.r_cell; pr.counts = b.cell_counts; pr.rad2_bits = b.cell_rad2;
+      rc_a = launch_pivot_tc<T, kPivAssign>(R, pr, st);
     } else {
       rc_a = launch_assign_any<T>(R, ldr, n_r, d, b.mu, b.piv_t, b.piv_norm, nc, b.r_cell, b.cell_counts, b.cell_rad2, st);
     }
     if (rc_a) return rc_a;
-    rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.mu, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, nullptr, st);
+    if (tc) {
+      PivParams pq = pp;
+      pq.ld = ldq; pq.n = n_q; pq.norms = b.q_norms; pq.n_tiles = ceil_div(n_q, kMmaTile);
+      pq.cell = b.q_cell; pq.counts = b.cell_counts + kMaxCells; pq.rad2_bits = nullptr;
+      rc_a = launch_pivot_tc<T, kPivAssign>(Q, pq, st);
+    } else {
+      rc_a = launch_assign_any<T>(Q, ldq, n_q, d, b.mu, b.piv_t, b.piv_norm, nc, b.q_cell, b.cell_counts + kMaxCells, nullptr, st);
+    }
     if (rc_a) return rc_a;
     cell_scan_kernel<<<1, 32, 0, st>>>(b.cell_counts, nc, b.cell_starts, b.cell_cursor);
     CM_LAUNCH_CHECK("cell_scan_kernel");
@@ -2131,7 +2405,14 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     CM_LAUNCH_CHECK("cell_scatter_kernel(Q)");
     home_cell_kernel<<<(unsigned)ceil_div(pl.n_q_tiles, 128), 128, 0, st>>>(b.perm_q, b.q_cell, (int)pl.n_q_tiles, b.home_cell);
     CM_LAUNCH_CHECK("home_cell_kernel");
-    rc_a = launch_tile_bounds_any<T>(Q, ldq, d, b.mu, b.perm_q, pl.n_q_tiles, b.piv_t, b.piv_norm, nc, b.cell_rad2, b.cell_lb2, st);
+    if (tc) {
+      PivParams pb = pp;
+      pb.ld = ldq; pb.n = n_q; pb.norms = b.q_norms; pb.n_tiles = pl.n_q_tiles;
+      pb.perm = b.perm_q; pb.rad2_in = b.cell_rad2; pb.lb2 = b.cell_lb2;
+      rc_a = launch_pivot_tc<T, kPivBounds>(Q, pb, st);
+    } else {
+      rc_a = launch_tile_bounds_any<T>(Q, ldq, d, b.mu, b.perm_q, pl.n_q_tiles, b.piv_t, b.piv_norm, nc, b.cell_rad2, b.cell_lb2, st);
+    }
     if (rc_a) return rc_a;
   } else {
     fill_perm_kernel<<<(unsigned)(ceil_div(pl.n_q_pad, 256) < kNumSMs * 8 ? ceil_div(pl.n_q_pad, 256) : kNumSMs * 8), 256, 0, st>>>(

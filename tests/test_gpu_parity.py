@@ -261,7 +261,10 @@ def test_search_with_precomputed_reference_cells(torch_cuda):
     assert torch.equal(cell, whole[0]) and torch.equal(rad2, whole[1])
     d0, i0, s0 = device.knn_search(qd, rd, 30, return_stats=True)
     d1, i1, s1 = device.knn_search(qd, rd, 30, return_stats=True, ref_cells=(cell, rad2))
-    assert torch.equal(d0, d1) and torch.equal(i0, i1) and int(s0[3]) == int(s1[3])
+    assert torch.equal(d0, d1) and torch.equal(i0, i1)
+    # the in-search assignment runs on the tensor cores, cm_knn_assign_reference in float32: a row between two pivots
+    # may land in either cell, which moves the scan by a few tiles and nothing else
+    assert abs(int(s0[3]) - int(s1[3])) <= 0.02 * int(s0[3])
     assert device.knn_assign_reference(rd[:2000], 30) is None  # small references are searched without cells
 
 
@@ -986,3 +989,33 @@ def test_wide_embeddings_stay_on_the_tensor_path(torch_cuda, d):
             assert neighbours_match(ii, dd, si, sd) == 0
             same = ii == si
             np.testing.assert_array_equal(dd[same], sd[same])
+
+
+@pytest.mark.parametrize("d,offset", [(50, 0.0), (50, 300.0), (24, 2_000.0), (100, 50.0)])
+def test_near_ties_at_rank_k(torch_cuda, d, offset):
+    """Adversarial for the certificate of the tensor-core path: for every query the k-th and (k+1)-th neighbours are
+    planted at distances that differ by 1e-7 .. 1e-4 relative -- below, at and above the error bound of the split-fp16
+    products -- on rows with large norms (un-centred data).  Whatever the certificate decides (accept or fall back),
+    the result must be the float64 brute force's, bit for bit."""
+    torch = torch_cuda
+    from cellmapper_b200 import _lib, device
+
+    rng = np.random.default_rng(int(d + offset))
+    k, n_q, n_far = 30, 400, 20_000
+    q = (rng.standard_normal((n_q, d)) * 2 + offset).astype(np.float32)
+    far = (rng.standard_normal((n_far, d)) * 2 + offset + 40.0 / np.sqrt(d)).astype(np.float32)  # a shell of distant points
+    planted = []
+    for i in range(n_q):
+        dirs = rng.standard_normal((k + 1, d))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        radii = np.sort(rng.random(k + 1) * 0.5 + 0.5)
+        eps = 10.0 ** rng.uniform(-7, -4)
+        radii[k] = radii[k - 1] * (1 + eps)  # the first neighbour that must stay OUT, a hair behind the last one IN
+        planted.append(q[i].astype(np.float64) + dirs * radii[:, None])
+    r = np.concatenate([np.concatenate(planted).astype(np.float32), far])
+    qd, rd = dev(torch, q), dev(torch, r)
+    dd, ii, st = device.knn_search(qd, rd, k, return_stats=True)
+    dx, ix = device.knn_search(qd, rd, k, algo=_lib.KNN_EXACT_F64)
+    dd, ii, dx, ix = (t.cpu().numpy() for t in (dd, ii, dx, ix))
+    np.testing.assert_array_equal(dd, dx)
+    assert neighbours_match(ii, dd, ix, dx, rel=0.0) == 0
