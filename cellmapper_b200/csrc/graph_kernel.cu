@@ -314,23 +314,26 @@ edge_to_csr_small_kernel(const double* __restrict__ dist, const int64_t* __restr
 // ------------------------------------------------------------------------------------------------
 constexpr int kFusedMaxM = 4;
 
-// Two phases per batch of 32 rows and warp.  Phase A, one ROW per step, lane = edge: kernel weight, column sort
+// Two phases per batch of kFusedBatch rows and warp.  Phase A, one ROW per step, lane = edge: kernel weight, column sort
 // ((column, source lane) through the bitonic network, the float64 weight follows once), float64 row sum in numpy's
 // order, normalise, coalesced CSR store; the normalised weights and the gathered payloads of the row are parked in a
 // shared-memory slab.  Phase B, lane = ROW: the inherently serial parts -- class sums and payload products, added in
-// ascending column order like scipy -- run as 32 independent chains, one per lane, reading the slab without bank
-// conflicts (row stride 33).  History: with every lane of a warp executing the serial loop of ONE row (broadcast by
-// shuffles, then by slab reads) the kernel issued ~600 warp instructions per row, 1.4-1.6 ms at 1.5 M rows.
-constexpr int kFusedWarps = 4;
+// ascending column order like scipy -- run as independent chains: four lanes per row, one for the vote and one per
+// payload column, reading the slab without bank conflicts (row stride 33).  History: with every lane of a warp
+// executing the serial loop of ONE row (broadcast by shuffles, then by slab reads) the kernel issued ~600 warp
+// instructions per row, 1.4-1.6 ms at 1.5 M rows; batches of 32 rows made the slab so large (17 KB per warp) that
+// only 12 warps fitted an SM and the row-at-a-time phase A ran at its latency: 2.1 ms.
+constexpr int kFusedWarps = 8;
+constexpr int kFusedBatch = 8;
 constexpr int kSlabStride = 33;
 
 template <typename TB, int M>
 struct FusedSlab {
-  double w[32];                           // phase A: kernel weights of the current row in column order
-  int n_valid[32];                        // per row of the batch
-  float v[32 * kSlabStride];              // [row][edge] normalised float32 weights
-  int cls[32 * kSlabStride];              // [row][edge] class of the edge's reference cell
-  TB b[(M > 0 ? M : 1) * 32 * kSlabStride];  // [payload column][row][edge]
+  double w[32];                                    // phase A: kernel weights of the current row in column order
+  int n_valid[kFusedBatch];                        // per row of the batch
+  float v[kFusedBatch * kSlabStride];              // [row][edge] normalised float32 weights
+  int cls[kFusedBatch * kSlabStride];              // [row][edge] class of the edge's reference cell
+  TB b[(M > 0 ? M : 1) * kFusedBatch * kSlabStride];  // [payload column][row][edge]
 };
 
 template <typename TC, typename TB, int M>
@@ -346,8 +349,9 @@ map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict
   const double p0 = kernel_param(kernel, stats3);
   if (rows_full && blockIdx.x == 0 && threadIdx.x == 0) indptr[0] = 0;
   const bool payloads = codes != nullptr || B != nullptr;
-  for (int64_t row0 = ((int64_t)blockIdx.x * kFusedWarps + warp) * 32; row0 < n_q; row0 += (int64_t)gridDim.x * kFusedWarps * 32) {
-    const int rows_here = (int)min((int64_t)32, n_q - row0);
+  for (int64_t row0 = ((int64_t)blockIdx.x * kFusedWarps + warp) * kFusedBatch; row0 < n_q;
+       row0 += (int64_t)gridDim.x * kFusedWarps * kFusedBatch) {
+    const int rows_here = (int)min((int64_t)kFusedBatch, n_q - row0);
     __syncwarp();  // phase B of the previous batch has read the slab
     // ---------------- phase A: one row per step, lane = edge ----------------
     for (int r = 0; r < rows_here; ++r) {
@@ -432,19 +436,20 @@ map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict
         sl.v[r * kSlabStride + lane] = v;
         sl.cls[r * kSlabStride + lane] = cls;
 #pragma unroll
-        for (int j = 0; j < M; ++j) sl.b[(j * 32 + r) * kSlabStride + lane] = bl[j];
+        for (int j = 0; j < M; ++j) sl.b[(j * kFusedBatch + r) * kSlabStride + lane] = bl[j];
         if (lane == 0) sl.n_valid[r] = n_valid;
       }
     }
     if (!payloads) continue;
     __syncwarp();
-    // ---------------- phase B: lane = row; serial sums in ascending column order (scipy's) ----------------
-    if (lane < rows_here) {
-      const int64_t row = row0 + lane;
-      const int n = sl.n_valid[lane];
-      const float* vrow = sl.v + lane * kSlabStride;
-      if (codes) {
-        const int* crow = sl.cls + lane * kSlabStride;
+    // ---------------- phase B: four lanes per row; serial sums in ascending column order (scipy's) ----------------
+    const int br = lane >> 2, sub = lane & 3;  // sub 0: the vote (+ payload column 3), sub 1..3: payload columns 0..2
+    if (br < rows_here) {
+      const int64_t row = row0 + br;
+      const int n = sl.n_valid[br];
+      const float* vrow = sl.v + br * kSlabStride;
+      if (codes && sub == 0) {
+        const int* crow = sl.cls + br * kSlabStride;
         float best = 0.f;  // an empty row, or weights that all rounded to 0 (csr_matmat drops zero sums, so the row
         int best_c = 0;    // of M @ onehot is empty): scipy's sparse argmax / max return column 0 / 0
         unsigned done = 0u;
@@ -464,22 +469,19 @@ map_rows_fused_kernel(const double* __restrict__ dist, const int64_t* __restrict
         out_conf[row] = best;
       }
       if (B) {
-        TB acc[M > 0 ? M : 1];
 #pragma unroll
-        for (int j = 0; j < M; ++j) acc[j] = (TB)0;
-        for (int t = 0; t < n; ++t) {
-          const float vt = vrow[t];
-#pragma unroll
-          for (int j = 0; j < M; ++j) {
-            const TB bt = sl.b[(j * 32 + lane) * kSlabStride + t];
+        for (int j = 0; j < M; ++j) {
+          if (sub != (j < 3 ? j + 1 : 0)) continue;
+          const TB* brow = sl.b + (j * kFusedBatch + br) * kSlabStride;
+          TB acc = (TB)0;
+          for (int t = 0; t < n; ++t) {
             if constexpr (sizeof(TB) == 4)
-              acc[j] = __fadd_rn(acc[j], __fmul_rn(vt, bt));
+              acc = __fadd_rn(acc, __fmul_rn(vrow[t], brow[t]));
             else
-              acc[j] = __dadd_rn(acc[j], __dmul_rn((double)vt, bt));
+              acc = __dadd_rn(acc, __dmul_rn((double)vrow[t], brow[t]));
           }
+          out_dense[row * ldo + j] = acc;
         }
-#pragma unroll
-        for (int j = 0; j < M; ++j) out_dense[row * ldo + j] = acc[j];
       }
     }
   }
@@ -619,7 +621,7 @@ extern "C" int cm_map_rows_fused(const double* dist, const int64_t* idx, int64_t
     const int rc = inclusive_scan_i32(indptr + 1, n_q, cols, st);
     if (rc) return rc;
   }
-  const int64_t blocks = ceil_div(n_q, kFusedWarps * 32);
+  const int64_t blocks = ceil_div(n_q, kFusedWarps * kFusedBatch);
   const int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
   const bool f64 = B && b_dtype == CM_F64;
 #define CM_GO(TC, TB)                                                                                                            \

@@ -143,6 +143,10 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, const uint4& a) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint4& a, const uint4& b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x),
                "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
@@ -825,7 +829,6 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
   const int quad = warp & 3;                   // TMEM lane quadrant of warps 1..4
   const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
   const uint32_t t_lane_acc = t_lane_a + kMmaTile;
-  const int chunks = p.kp_q >> 3;
   const int k_steps = p.kp_q >> 4;
   const uint32_t idesc = make_idesc_f16(kMmaTile, kMmaTile);
   uint32_t mma_phase = 0;
@@ -846,38 +849,44 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
         xn_up = __double2float_ru(nn);
         xn_dn = __double2float_rd(nn);
       }
+      // Every embedding column is split once (hi, lo) and lands in three segments: chunk ci of segment 0 (-2 hi, plus
+      // the constant c in the three norm columns), of segment 1 (-2 hi) and of segment 2 (-2 lo); one 4-column
+      // tcgen05.st per chunk.  Same arithmetic as prep_kernel, so these rows and the pivot image agree bit for bit.
       const T* xr = X + (row >= 0 ? row : 0) * p.ld;
-      auto make_chunk = [&](int chunk) {
-        const int seg = chunk / p.dc;
-        const int cs0 = (chunk - seg * p.dc) * 8;
-        __half h[8];
+      auto pack = [](const float (&f)[8]) {
+        uint4 v;
+        v.x = (uint32_t)__half_as_ushort(__float2half_rn(f[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[1])) << 16);
+        v.y = (uint32_t)__half_as_ushort(__float2half_rn(f[2])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[3])) << 16);
+        v.z = (uint32_t)__half_as_ushort(__float2half_rn(f[4])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[5])) << 16);
+        v.w = (uint32_t)__half_as_ushort(__float2half_rn(f[6])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[7])) << 16);
+        return v;
+      };
+      for (int ci = 0; ci < p.dc; ++ci) {
+        float s0[8], s1[8], s2[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int cs = cs0 + e;
-          float out = 0.f;
-          if (row >= 0 && seg < 3) {
+          const int cs = ci * 8 + e;
+          float hi2 = 0.f, lo2 = 0.f, nc = 0.f;
+          if (row >= 0) {
             if (cs < p.d) {
               const float xs = (float)(((double)xr[cs] - p.mu[cs]) * (double)scale);
               const __half hi = __float2half_rn(xs);
               const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
-              out = seg == 2 ? -2.f * lo : -2.f * __half2float(hi);
-            } else if (seg == 0 && cs < p.d + 3) {
-              out = kNormColumn;
+              hi2 = -2.f * __half2float(hi);
+              lo2 = -2.f * lo;
+            } else if (cs < p.d + 3) {
+              nc = kNormColumn;
             }
           }
-          h[e] = __float2half_rn(out);
+          s0[e] = cs < p.d ? hi2 : nc;
+          s1[e] = hi2;
+          s2[e] = lo2;
         }
-        uint4 v;
-        v.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-        v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-        v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
-        v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
-        return v;
-      };
-      for (int c = 0; c < chunks; c += 2) {
-        const uint4 a = make_chunk(c), b = make_chunk(c + 1);
-        tmem_st_32x32b_x8(t_lane_a + 4 * c, a, b);
+        tmem_st_32x32b_x4(t_lane_a + 4 * ci, pack(s0));
+        tmem_st_32x32b_x4(t_lane_a + 4 * (p.dc + ci), pack(s1));
+        tmem_st_32x32b_x4(t_lane_a + 4 * (2 * p.dc + ci), pack(s2));
       }
+      if ((3 * p.dc) & 1) tmem_st_32x32b_x4(t_lane_a + 4 * (3 * p.dc), make_uint4(0u, 0u, 0u, 0u));  // the padding chunk
       tmem_st_wait();
       tc_fence_before();
     }
