@@ -827,6 +827,7 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
   const float scale = scale_from_absmax(p.info->absmax_bits);
   const float inv_s2 = 1.f / (scale * scale);  // exact: a power of two
   const int quad = warp & 3;                   // TMEM lane quadrant of warps 1..4
+  const int row_stride = p.d | 1;              // odd: a thread walking its own row hits every bank once per 32 threads
   const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
   const uint32_t t_lane_acc = t_lane_a + kMmaTile;
   const int k_steps = p.kp_q >> 4;
@@ -852,7 +853,18 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
       // Every embedding column is split once (hi, lo) and lands in three segments: chunk ci of segment 0 (-2 hi, plus
       // the constant c in the three norm columns), of segment 1 (-2 hi) and of segment 2 (-2 lo); one 4-column
       // tcgen05.st per chunk.  Same arithmetic as prep_kernel, so these rows and the pivot image agree bit for bit.
-      const T* xr = X + (row >= 0 ? row : 0) * p.ld;
+      // Stage the warp's 32 rows in shared memory first: lane-strided reads of one row at a time, all rows in flight
+      // together.  (Reading the row chunk by chunk from global memory put one memory round trip in front of every
+      // tcgen05.st: 7 dependent trips per tile, 20 us per tile and CTA.)
+      T* stage = reinterpret_cast<T*>(smem + 2 * b_bytes) + (size_t)(quad * 32) * row_stride;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int64_t rr = __shfl_sync(0xffffffffu, row, r);
+        const T* src = X + (rr >= 0 ? rr : 0) * p.ld;
+        for (int c = lane; c < p.d; c += 32) stage[r * row_stride + c] = src[c];
+      }
+      __syncwarp();
+      const T* xr = stage + (size_t)lane * row_stride;
       auto pack = [](const float (&f)[8]) {
         uint4 v;
         v.x = (uint32_t)__half_as_ushort(__float2half_rn(f[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[1])) << 16);
@@ -979,7 +991,7 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
 
 template <typename T, int MODE>
 int launch_pivot_tc(const T* X, PivParams p, cudaStream_t st) {
-  const size_t smem = (size_t)2 * kMmaTile * p.kp_r * 2;
+  const size_t smem = (size_t)2 * kMmaTile * p.kp_r * 2 + (size_t)kMmaTile * (p.d | 1) * sizeof(T);
   CM_CUDA_CHECK(cudaFuncSetAttribute(pivot_tc_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t want = (int64_t)kNumSMs * 2;
   const int grid = (int)(p.n_tiles < want ? p.n_tiles : want);
