@@ -106,6 +106,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// asynchronous global -> shared copy of one element (4 or 8 bytes), no registers in between
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -835,16 +843,37 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
   uint32_t mma_phase = 0;
   bool b_ready = false;
 
+  // The rows of a tile are staged in shared memory by asynchronous copies, every warp its own 32 rows; the copies
+  // for the NEXT tile are issued as soon as this tile's operand sits in tensor memory, so they land while the MMAs and
+  // the epilogue run.  (Reading the rows from global memory chunk by chunk put seven dependent memory round trips in
+  // front of every tile: 20 us per tile and CTA; staging them synchronously still paid four.)
+  T* stage = reinterpret_cast<T*>(smem + 2 * b_bytes) + (size_t)(quad * 32) * row_stride;
+  auto tile_row = [&](int64_t tile) -> int64_t {
+    const int64_t pos = tile * kMmaTile + quad * 32 + lane;
+    if (MODE == kPivBounds) return p.perm[pos];
+    return pos < p.n ? pos : -1;
+  };
+  auto stage_rows = [&](int64_t my_row) {
+    for (int r = 0; r < 32; ++r) {
+      const int64_t rr = __shfl_sync(0xffffffffu, my_row, r);
+      if (rr < 0) continue;  // warp-uniform
+      const T* src = X + rr * p.ld;
+      for (int c = lane; c < p.d; c += 32) cp_async_elem<sizeof(T)>(smem_u32(stage + r * row_stride + c), src + c);
+    }
+    cp_async_commit();
+  };
+  int64_t row_next = -1;
+  if (warp >= 1 && (int64_t)blockIdx.x < p.n_tiles) {
+    row_next = tile_row(blockIdx.x);
+    stage_rows(row_next);
+  }
+
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     int64_t row = -1;
     float xn_up = 0.f, xn_dn = 0.f;
     if (warp >= 1) {
       // this thread's row -> split-fp16 query operand [-2hi, c c c | -2hi | -2lo] -> tensor memory (lane = row)
-      const int64_t pos = tile * kMmaTile + quad * 32 + lane;
-      if (MODE == kPivBounds)
-        row = p.perm[pos];
-      else
-        row = pos < p.n ? pos : -1;
+      row = row_next;
       if (row >= 0) {
         const double nn = p.norms[row];
         xn_up = __double2float_ru(nn);
@@ -853,17 +882,8 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
       // Every embedding column is split once (hi, lo) and lands in three segments: chunk ci of segment 0 (-2 hi, plus
       // the constant c in the three norm columns), of segment 1 (-2 hi) and of segment 2 (-2 lo); one 4-column
       // tcgen05.st per chunk.  Same arithmetic as prep_kernel, so these rows and the pivot image agree bit for bit.
-      // Stage the warp's 32 rows in shared memory first: lane-strided reads of one row at a time, all rows in flight
-      // together.  (Reading the row chunk by chunk from global memory put one memory round trip in front of every
-      // tcgen05.st: 7 dependent trips per tile, 20 us per tile and CTA.)
-      T* stage = reinterpret_cast<T*>(smem + 2 * b_bytes) + (size_t)(quad * 32) * row_stride;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int64_t rr = __shfl_sync(0xffffffffu, row, r);
-        const T* src = X + (rr >= 0 ? rr : 0) * p.ld;
-        for (int c = lane; c < p.d; c += 32) stage[r * row_stride + c] = src[c];
-      }
-      __syncwarp();
+      cp_async_wait_all();
+      __syncwarp();  // the warp's 32 staged rows are complete and visible
       const T* xr = stage + (size_t)lane * row_stride;
       auto pack = [](const float (&f)[8]) {
         uint4 v;
@@ -901,6 +921,11 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
       if ((3 * p.dc) & 1) tmem_st_32x32b_x4(t_lane_a + 4 * (3 * p.dc), make_uint4(0u, 0u, 0u, 0u));  // the padding chunk
       tmem_st_wait();
       tc_fence_before();
+      __syncwarp();  // every lane has read its staged row: the slab can take the next tile
+      if (tile + gridDim.x < p.n_tiles) {
+        row_next = tile_row(tile + gridDim.x);
+        stage_rows(row_next);
+      }
     }
     __syncthreads();  // the operand is in tensor memory; the previous tile's accumulator has been read
     float best = CUDART_INF_F;
