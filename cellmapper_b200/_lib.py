@@ -56,8 +56,9 @@ SIGNATURES = {
     "cm_csr_col_sums": (c_int, [_P, _P, _P, c_int64, _P, _P]),
     "cm_vote_argmax": (c_int, [_P, _P, _P, c_int64, _P, c_int, _P, _P, _P, _P]),
     "cm_spmm_csr_dense": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, c_int, _P, c_int64, _P]),
-    "cm_spgemm_count": (c_int, [_P, _P, c_int64, _P, _P, c_int32, _P, _P]),
-    "cm_spgemm_fill": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int, c_int32, _P, _P, _P, _P]),
+    "cm_spgemm_count": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int32, _P, _P]),
+    "cm_spgemm_fill": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int, _P, c_int32, _P, _P, _P, _P]),
+    "cm_spgemm_partition": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "cm_presence_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
     "cm_presence_scores": (c_int, [_P, _P, c_int64, c_int, _P, c_int64, c_int64, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "cm_select_ranks": (c_int, [_P, c_int, c_int64, c_int64, _P, c_int, _P, _P, c_size_t, _P]),

@@ -342,14 +342,17 @@ class CellMapper(EvaluationMixin):
             if not x.has_sorted_indices:
                 x = x.sorted_indices()
             data = x.data if x.data.dtype in (np.float32, np.float64) else x.data.astype(np.float64)  # scipy: int -> float64 result
-            cache[key] = (_to_device(x.indptr, torch.int64), _to_device(x.indices, torch.int32), _to_device(data), int(x.shape[1]))
+            x_ip, x_cols = _to_device(x.indptr, torch.int64), _to_device(x.indices, torch.int32)
+            # the gene-partition index of the layer (barrier-free CSR x CSR kernel), built once and reused by every call
+            cache[key] = (x_ip, x_cols, _to_device(data), int(x.shape[1]), device.spgemm_partition(x_ip, x_cols, int(x.shape[1])))
         return cache[key]
 
     def _spgemm_layer_chunks(self, key: str, max_chunk_nnz: int = 1 << 27, info: dict | None = None):
         """Device chunks (``device.SpgemmChunk``) of ``mapping_matrix @ layer`` for a sparse reference layer."""
         m = self._require_mapping()
-        x_ip, x_cols, x_vals, n_genes = self._layer_device(key)
-        yield from device.spgemm_chunks(m.indptr, m.cols, m.vals, x_ip, x_cols, x_vals, n_genes, max_chunk_nnz=max_chunk_nnz, info=info)
+        x_ip, x_cols, x_vals, n_genes, x_part = self._layer_device(key)
+        yield from device.spgemm_chunks(m.indptr, m.cols, m.vals, x_ip, x_cols, x_vals, n_genes, max_chunk_nnz=max_chunk_nnz, info=info,
+                                        x_part=x_part)
 
     def map_layers(self, key: str, *, chunk_consumer=None, max_chunk_nnz: int = 1 << 27) -> None:
         """reference: cellmapper.py:346-383.  Sparse layers go through the CSR x CSR kernel, dense layers through

@@ -27,6 +27,7 @@ __all__ = [
     "spmm",
     "spgemm",
     "spgemm_chunks",
+    "spgemm_partition",
     "SpgemmChunk",
     "presence_scores",
     "select_ranks",
@@ -400,9 +401,32 @@ def _layer_values(x_vals: torch.Tensor) -> torch.Tensor:
     return x_vals.contiguous() if x_vals.dtype == torch.float32 else x_vals.to(torch.float64).contiguous()
 
 
-def spgemm_count(indptr, cols, x_indptr, x_cols, n_genes: int) -> torch.Tensor:
+def spgemm_partition(x_indptr: torch.Tensor, x_cols: torch.Tensor, n_genes: int) -> torch.Tensor:
+    """Gene-partition index of a CSR expression matrix for the barrier-free CSR x CSR kernel: int32 (n_rows, 32),
+    entry (row, w) = first position of the row whose gene lies in range w or later.  The 32 gene ranges are cut at
+    the quantiles of the matrix' own column histogram (estimated from a stride sample), so every warp of a CTA gets
+    an equal share of the entries even when a few thousand genes hold most of them.  Built once per layer
+    (~64 MB for 500 k cells); the ranges travel in the last row of the returned tensor."""
+    dev = _check_cuda(x_indptr, x_cols)
+    _expect(x_indptr, torch.int64, "x_indptr")
+    _expect(x_cols, torch.int32, "x_cols")
+    n_rows = x_indptr.numel() - 1
+    with torch.cuda.device(dev):
+        stride = max(1, x_cols.numel() // 8_000_000)
+        hist = torch.bincount(x_cols[::stride].long(), minlength=n_genes) if x_cols.numel() else torch.zeros(n_genes, dtype=torch.int64, device=dev)
+        cum = torch.cumsum(hist, 0)
+        targets = cum[-1] * torch.arange(1, 32, device=dev, dtype=torch.float64) / 32.0
+        cuts = torch.searchsorted(cum.double(), targets).clamp_(max=n_genes - 1) + 1
+        bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cummax(cuts, 0).values]).to(torch.int32)
+        part = torch.empty((n_rows + 1, 32), dtype=torch.int32, device=dev)
+        part[n_rows] = bounds  # kept with the index: the kernels only need the index, the ranges document it
+        _call("cm_spgemm_partition", _ptr(x_indptr), _ptr(x_cols), n_rows, _ptr(bounds), _ptr(part), _stream())
+    return part
+
+
+def spgemm_count(indptr, cols, x_indptr, x_cols, n_genes: int, x_part: torch.Tensor | None = None) -> torch.Tensor:
     """Structural nnz of every row of M @ X (int32 (n_q,)): the first of the two passes of ``spgemm``."""
-    dev = _check_cuda(indptr, cols, x_indptr, x_cols)
+    dev = _check_cuda(indptr, cols, x_indptr, x_cols, x_part)
     _expect(indptr, torch.int32, "indptr")
     _expect(cols, torch.int32, "cols")
     _expect(x_indptr, torch.int64, "x_indptr")
@@ -410,11 +434,12 @@ def spgemm_count(indptr, cols, x_indptr, x_cols, n_genes: int) -> torch.Tensor:
     n_q = indptr.numel() - 1
     with torch.cuda.device(dev):
         row_nnz = torch.empty(n_q, dtype=torch.int32, device=dev)
-        _call("cm_spgemm_count", _ptr(indptr), _ptr(cols), n_q, _ptr(x_indptr), _ptr(x_cols), int(n_genes), _ptr(row_nnz), _stream())
+        _call("cm_spgemm_count", _ptr(indptr), _ptr(cols), n_q, _ptr(x_indptr), _ptr(x_cols), _ptr(x_part), int(n_genes), _ptr(row_nnz), _stream())
     return row_nnz
 
 
-def spgemm(indptr, cols, vals, x_indptr: torch.Tensor, x_cols: torch.Tensor, x_vals: torch.Tensor, n_genes: int):
+def spgemm(indptr, cols, vals, x_indptr: torch.Tensor, x_cols: torch.Tensor, x_vals: torch.Tensor, n_genes: int,
+           x_part: torch.Tensor | None = None):
     """M @ X for CSR X (cellmapper.py:372-373). Two passes (count, fill); one host sync for the output size.
     Returns (out_indptr int64 (n_q+1,), out_cols int32, out_vals), columns sorted per row; out_vals is float32 for a
     float32 layer and float64 otherwise (scipy's promotion).  The whole result is materialised on the device: for
@@ -426,7 +451,9 @@ def spgemm(indptr, cols, vals, x_indptr: torch.Tensor, x_cols: torch.Tensor, x_v
     x_cols = x_cols.to(torch.int32).contiguous()
     x_vals = _layer_values(x_vals)
     with torch.cuda.device(dev):
-        row_nnz = spgemm_count(indptr, cols, x_indptr, x_cols, n_genes)
+        if x_part is None:
+            x_part = spgemm_partition(x_indptr, x_cols, n_genes)
+        row_nnz = spgemm_count(indptr, cols, x_indptr, x_cols, n_genes, x_part)
         out_indptr = torch.zeros(n_q + 1, dtype=torch.int64, device=dev)
         torch.cumsum(row_nnz, 0, out=out_indptr[1:])
         nnz = int(out_indptr[-1].item())
@@ -434,7 +461,7 @@ def spgemm(indptr, cols, vals, x_indptr: torch.Tensor, x_cols: torch.Tensor, x_v
         out_vals = torch.empty(max(nnz, 1), dtype=x_vals.dtype, device=dev)
         _call(
             "cm_spgemm_fill", _ptr(indptr), _ptr(cols), _ptr(vals), n_q, _ptr(x_indptr), _ptr(x_cols), _ptr(x_vals),
-            _dtype_code(x_vals), int(n_genes), _ptr(out_indptr), _ptr(out_cols), _ptr(out_vals), _stream(),
+            _dtype_code(x_vals), _ptr(x_part), int(n_genes), _ptr(out_indptr), _ptr(out_cols), _ptr(out_vals), _stream(),
         )  # fmt: skip
     return out_indptr, out_cols[:nnz], out_vals[:nnz]
 
@@ -455,7 +482,8 @@ class SpgemmChunk:
         return int(self.cols.numel())
 
 
-def spgemm_chunks(indptr, cols, vals, x_indptr, x_cols, x_vals, n_genes: int, max_chunk_nnz: int = 1 << 27, info: dict | None = None):
+def spgemm_chunks(indptr, cols, vals, x_indptr, x_cols, x_vals, n_genes: int, max_chunk_nnz: int = 1 << 27, info: dict | None = None,
+                  x_part: torch.Tensor | None = None):
     """M @ X for CSR X, produced in chunks of consecutive query rows so that the result never has to exist at
     once (BASELINE config 4: 500 k rows x ~15 k nnz = 40-80 GB).  One count pass over all rows and ONE host sync
     (the row pointer of the result, needed to cut the chunks), then per chunk one fill into one of two device
@@ -471,7 +499,9 @@ def spgemm_chunks(indptr, cols, vals, x_indptr, x_cols, x_vals, n_genes: int, ma
     x_cols = x_cols.to(torch.int32).contiguous()
     x_vals = _layer_values(x_vals)
     with torch.cuda.device(dev):
-        row_nnz = spgemm_count(indptr, cols, x_indptr, x_cols, n_genes)
+        if x_part is None:
+            x_part = spgemm_partition(x_indptr, x_cols, n_genes)
+        row_nnz = spgemm_count(indptr, cols, x_indptr, x_cols, n_genes, x_part)
         out_indptr = torch.zeros(n_q + 1, dtype=torch.int64, device=dev)
         torch.cumsum(row_nnz, 0, out=out_indptr[1:])
         ip_host = out_indptr.cpu().numpy()  # the one host sync
@@ -497,7 +527,7 @@ def spgemm_chunks(indptr, cols, vals, x_indptr, x_cols, x_vals, n_genes: int, ma
             rel = out_indptr[lo : hi + 1] - out_indptr[lo]
             _call(
                 "cm_spgemm_fill", indptr[lo:].data_ptr(), _ptr(cols), _ptr(vals), hi - lo, _ptr(x_indptr), _ptr(x_cols),
-                _ptr(x_vals), _dtype_code(x_vals), int(n_genes), _ptr(rel), _ptr(buf_cols[b]), _ptr(buf_vals[b]), _stream(),
+                _ptr(x_vals), _dtype_code(x_vals), _ptr(x_part), int(n_genes), _ptr(rel), _ptr(buf_cols[b]), _ptr(buf_vals[b]), _stream(),
             )  # fmt: skip
             chunk = SpgemmChunk(lo, hi, rel, buf_cols[b][:nnz], buf_vals[b][:nnz])
             in_flight[b] = chunk

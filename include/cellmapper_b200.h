@@ -197,10 +197,17 @@ int cm_spmm_csr_dense(const int32_t* indptr, const int32_t* cols, const float* v
 #define CM_SPGEMM_MAX_COLS 40960     /* float32 layers */
 #define CM_SPGEMM_MAX_COLS_F64 24576 /* float64 / integer layers */
 int cm_spgemm_count(const int32_t* m_indptr, const int32_t* m_cols, int64_t n_q, const int64_t* x_indptr,
-                    const int32_t* x_cols, int32_t n_genes, int32_t* out_row_nnz, void* stream);
+                    const int32_t* x_cols, const int32_t* x_part, int32_t n_genes, int32_t* out_row_nnz, void* stream);
 int cm_spgemm_fill(const int32_t* m_indptr, const int32_t* m_cols, const float* m_vals, int64_t n_q,
-                   const int64_t* x_indptr, const int32_t* x_cols, const void* x_vals, int dtype, int32_t n_genes,
-                   const int64_t* out_indptr, int32_t* out_cols, void* out_vals, void* stream);
+                   const int64_t* x_indptr, const int32_t* x_cols, const void* x_vals, int dtype, const int32_t* x_part,
+                   int32_t n_genes, const int64_t* out_indptr, int32_t* out_cols, void* out_vals, void* stream);
+/* x_part (may be NULL): gene-partition index of X built once per layer by cm_spgemm_partition: x_part[row * 32 + w] =
+ * first position of the row whose gene is >= gene_bounds[w] (gene_bounds: 32 ascending int32 on the device,
+ * gene_bounds[0] = 0, chosen so that the 32 ranges hold equal shares of X's entries).  With it, warp w of a CTA owns the
+ * genes of range w and no barrier is needed between neighbours; without it (or for matrices wider than one accumulator
+ * window) rows are spread over the CTA by position and every neighbour ends in a block barrier.  Same results. */
+int cm_spgemm_partition(const int64_t* x_indptr, const int32_t* x_cols, int64_t n_rows, const int32_t* gene_bounds,
+                        int32_t* x_part, void* stream);
 /* dtype (cm_dtype) is the type of x_vals AND out_vals: CM_F32 for float32 layers; CM_F64 for float64 / integer layers
  * (converted to float64 by the caller), for which scipy promotes the float32 mapping matrix and returns float64.
  * Row chunks: both calls index m_cols / m_vals through the VALUES of m_indptr, so passing m_indptr + row_lo with
