@@ -468,37 +468,43 @@ spgemm_part_kernel(const int32_t* __restrict__ m_indptr, const int32_t* __restri
         }
       }
       __syncthreads();
-      // this warp's slice of every neighbour's row, neighbours in ascending order; the first 32 entries of four
-      // neighbours' slices are loaded before the first of them is accumulated
-      constexpr int kAhead = 4;
+      // this warp's slice of every neighbour's row, neighbours in ascending order.  The first kPerLane * 32 entries of
+      // the slices of kAhead neighbours are loaded before the first of them is accumulated: one memory round trip per
+      // group of neighbours (a load inside the per-neighbour loop put one in front of EVERY neighbour: 69 us per row).
+      constexpr int kAhead = 6, kPerLane = 3;
       for (int j0 = 0; j0 < n_nb; j0 += kAhead) {
-        int32_t gc[kAhead];
-        T gv[kAhead];
-        int32_t a[kAhead], b[kAhead];
+        int32_t gc[kAhead][kPerLane];
+        T gv[kAhead][kPerLane];
 #pragma unroll
         for (int u = 0; u < kAhead; ++u) {
           const int j = j0 + u;
           const bool on = j < n_nb;
-          a[u] = on ? s_part[j][warp] : 0;
-          b[u] = on ? s_part[j][warp + 1] : 0;
-          const int32_t pidx = a[u] + lane;
-          const bool have = pidx < b[u];
+          const int32_t a = on ? s_part[j][warp] : 0, b = on ? s_part[j][warp + 1] : 0;
           const int64_t xs = on ? s_xs[j] : 0;
-          gc[u] = have ? x_cols[xs + pidx] : -1;
-          gv[u] = (kFill && have) ? x_vals[xs + pidx] : (T)0;
+#pragma unroll
+          for (int v = 0; v < kPerLane; ++v) {
+            const int32_t pidx = a + v * 32 + lane;
+            const bool have = pidx < b;
+            gc[u][v] = have ? x_cols[xs + pidx] : -1;
+            gv[u][v] = (kFill && have) ? x_vals[xs + pidx] : (T)0;
+          }
         }
 #pragma unroll
         for (int u = 0; u < kAhead; ++u) {
           const int j = j0 + u;
           if (j >= n_nb) break;
           const T w = s_w[j];
-          if (gc[u] >= 0) {
-            flags[gc[u]] = 1;
-            if (kFill) acc[gc[u]] = mul_add_rn(acc[gc[u]], w, gv[u]);  // columns are unique inside one X row
+#pragma unroll
+          for (int v = 0; v < kPerLane; ++v) {
+            if (gc[u][v] >= 0) {
+              flags[gc[u][v]] = 1;
+              if (kFill) acc[gc[u][v]] = mul_add_rn(acc[gc[u][v]], w, gv[u][v]);  // columns are unique inside one X row
+            }
           }
-          if (a[u] + 32 < b[u]) {  // the rest of a long slice (warp-uniform test)
+          const int32_t a = s_part[j][warp], b = s_part[j][warp + 1];
+          if (a + kPerLane * 32 < b) {  // the rest of a long slice (warp-uniform test)
             const int64_t xs = s_xs[j];
-            for (int32_t pidx = a[u] + 32 + lane; pidx < b[u]; pidx += 32) {
+            for (int32_t pidx = a + kPerLane * 32 + lane; pidx < b; pidx += 32) {
               const int32_t g = x_cols[xs + pidx];
               flags[g] = 1;
               if (kFill) acc[g] = mul_add_rn(acc[g], w, x_vals[xs + pidx]);
