@@ -199,6 +199,7 @@ class CpuPath:
 
         self.shim = reference_shim if reference_shim.available() else None
         self.kind = "reference" if self.shim is not None else "port"
+        self.cores = cpu_threads()
 
     def run(self, name, xr, xq, labels=None, umap=None, layer=None):
         # under torchrun every rank starts with OMP_NUM_THREADS=1; the CPU arm gets the host's cores back
@@ -206,6 +207,7 @@ class CpuPath:
             from threadpoolctl import threadpool_limits
 
             with threadpool_limits(limits=_host_cores()):
+                self.cores = cpu_threads()
                 return self._run(name, xr, xq, labels, umap, layer)
         except ImportError:
             return self._run(name, xr, xq, labels, umap, layer)
@@ -274,7 +276,7 @@ def reference_arm(args):
         "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_text(name, args.data), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cpu_threads(), "kind": cpu.kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -612,7 +614,7 @@ def run_map_workload(ctx, name, data, steps, warmup, with_e2e=True, with_cpu=Tru
         runner = CpuPath()
         runner.run(name, xr, xq[: min(ns, 2000)], labels, umap)  # warm-up, discarded
         dt, ref_out = runner.run(name, xr, xq[:ns], labels, umap)
-        cpu = {"value": ns / dt, "unit": "cells/s", "cores": cpu_threads(), "kind": runner.kind,
+        cpu = {"value": ns / dt, "unit": "cells/s", "cores": runner.cores, "kind": runner.kind,
                "sample": f"first {ns} of {n_q_total} queries x full {n_r} reference, 1 run after warm-up", "phases_s": ref_out["seconds"]}
         got = ii[:ns].cpu().numpy()
         want = ref_out["indices"]
@@ -758,7 +760,7 @@ def run_expr_workload(ctx, name, steps, warmup, with_cpu=True):
         ns = min(cpu_sample_queries(name), n_q)
         runner = CpuPath()
         dt, ref_out = runner.run(name, xr, xq[:ns], layer=x_host)
-        cpu = {"value": ns / dt, "unit": "cells/s", "cores": cpu_threads(), "kind": runner.kind,
+        cpu = {"value": ns / dt, "unit": "cells/s", "cores": runner.cores, "kind": runner.kind,
                "sample": f"first {ns} of {n_q_total} queries x full {n_r} reference, 1 run", "phases_s": ref_out["seconds"]}
         qry_ad = AnnData(X=csr_matrix((ns, 1), dtype=np.float32), obs=pd.DataFrame(index=pd.RangeIndex(ns).astype(str)), obsm={"X_joint": xq[:ns]})
         cm = CellMapper(qry_ad, ref_ad)
@@ -833,9 +835,13 @@ def run_presence_workload(ctx, name, steps, warmup, with_cpu=True):
     dd, ii, scores = r["res"]
     st_host = torch.stack(search_stats[-steps:]).double().mean(0).cpu().numpy()
     # the single-GPU search of the same rows is the reference result of the sharded one: sample check against the f64 kernel
-    n_bad, n_checked = (0, 0)
+    # every rank checks a sample of ITS shard's lists (before the exchange) against the float64 brute force over the shard
     if world == 1:
         n_bad, n_checked = verify_sample_exact(ctx, xq_d, xr_d, dd, ii, mode)
+    else:
+        dl, il = device.knn_search(xq_d, xr_d, K, r_index_offset=r_lo, dist_mode=mode)
+        n_bad, n_checked = verify_sample_exact(ctx, xq_d, xr_d, dl, il, mode, r_offset=r_lo)
+        del dl, il
     out = {
         "value": n_q * steps / t_dev,
         "ms_per_step": 1e3 * t_dev / steps,
@@ -882,7 +888,7 @@ def run_presence_workload(ctx, name, steps, warmup, with_cpu=True):
         if rank == 0:
             runner = CpuPath()
             dt, ref_out = runner.run(name, xr, xq[:ns])
-            cpu = {"value": ns / dt, "unit": "cells/s", "cores": cpu_threads(), "kind": runner.kind,
+            cpu = {"value": ns / dt, "unit": "cells/s", "cores": runner.cores, "kind": runner.kind,
                    "sample": f"first {ns} of {n_q} queries x the full {n_r} reference, 1 run", "phases_s": ref_out["seconds"]}
             got = ii_s.cpu().numpy()
             hits = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(got, ref_out["indices"]))
