@@ -59,18 +59,19 @@ def sources() -> list[str]:
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def build(force: bool = False, verbose: bool = False, dev_probes: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, dev_probes: bool = False, variant: str = "", defines: tuple = ()) -> str:
     """``dev_probes``: a separate library (lib/libcellmapper_b200_probes.so, -DCM_DEV_PROBES) that also exports
     the development probes cm_debug_probe_flags / cm_debug_probe_prof; tools/ load it through CM_LIBPATH.  The
     shipping library never contains them."""
     from concurrent.futures import ThreadPoolExecutor
 
     os.makedirs(LIBDIR, exist_ok=True)
-    tag = "_probes" if dev_probes else ""
+    # variant / defines: tuning builds (tools/ab_search.py): lib/libcellmapper_b200_<variant>.so with extra -D flags
+    tag = ("_probes" if dev_probes else "") + (f"_{variant}" if variant else "")
     libpath = LIBPATH.replace(".so", f"{tag}.so")
     stamp = STAMP + tag
-    flags = NVCC_FLAGS + (["-DCM_DEV_PROBES"] if dev_probes else [])
-    fp = _fingerprint() + tag
+    flags = NVCC_FLAGS + (["-DCM_DEV_PROBES"] if dev_probes else []) + [f"-D{d}" for d in defines]
+    fp = _fingerprint() + tag + " ".join(defines)
     if not force and os.path.exists(libpath) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
         return libpath
 

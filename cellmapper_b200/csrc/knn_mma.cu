@@ -792,6 +792,7 @@ struct PivParams {
   int32_t* counts;
   unsigned int* rad2_bits;    // null on the query side
   // kPivBounds
+  const unsigned char* q_img; // the query operand image in scan order (prep_kernel): rows are copied, not rebuilt
   const int32_t* perm;        // scan position -> row, -1 = padding
   const unsigned int* rad2_in;
   float* lb2;                 // [n_tiles][kMaxCells]
@@ -865,7 +866,7 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
   int64_t row_next = -1;
   if (warp >= 1 && (int64_t)blockIdx.x < p.n_tiles) {
     row_next = tile_row(blockIdx.x);
-    stage_rows(row_next);
+    if (MODE == kPivAssign) stage_rows(row_next);
   }
 
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -882,6 +883,11 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
       // Every embedding column is split once (hi, lo) and lands in three segments: chunk ci of segment 0 (-2 hi, plus
       // the constant c in the three norm columns), of segment 1 (-2 hi) and of segment 2 (-2 lo); one 4-column
       // tcgen05.st per chunk.  Same arithmetic as prep_kernel, so these rows and the pivot image agree bit for bit.
+      if (MODE == kPivBounds) {
+        // the operand rows of the sorted queries already exist (the image mma_topk will read): copy, do not rebuild
+        const uint4* src = reinterpret_cast<const uint4*>(p.q_img) + (tile * kMmaTile + quad * 32 + lane) * (int64_t)(p.kp_q >> 3);
+        for (int c = 0; c < (p.kp_q >> 4); ++c) tmem_st_32x32b_x8(t_lane_a + 8 * c, src[2 * c], src[2 * c + 1]);
+      } else {
       cp_async_wait_all();
       __syncwarp();  // the warp's 32 staged rows are complete and visible
       const T* xr = stage + (size_t)lane * row_stride;
@@ -919,12 +925,13 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
         tmem_st_32x32b_x4(t_lane_a + 4 * (2 * p.dc + ci), pack(s2));
       }
       if ((3 * p.dc) & 1) tmem_st_32x32b_x4(t_lane_a + 4 * (3 * p.dc), make_uint4(0u, 0u, 0u, 0u));  // the padding chunk
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();  // every lane has read its staged row: the slab can take the next tile
       if (tile + gridDim.x < p.n_tiles) {
         row_next = tile_row(tile + gridDim.x);
-        stage_rows(row_next);
+        if (MODE == kPivAssign) stage_rows(row_next);
       }
     }
     __syncthreads();  // the operand is in tensor memory; the previous tile's accumulator has been read
@@ -1502,31 +1509,43 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     // wait for the store still reading it, and the slot as popc(mine & below) cost 16 POPCs per half tile
     // on a pipe that issues one warp instruction every 8 cycles.
     uint32_t a16 = cur0, a4 = ccur0;
+#ifdef CM_PUSH_GROUPS
+    // A half tile holds ~1.6 passing elements over the warp's 32 rows, so most of the 16 leaves are flagged by NO
+    // lane: the union of the lanes' masks (one REDUX) lets the warp skip whole groups of four leaves with a branch
+    // that is uniform by construction (it cannot diverge, unlike a per-lane test of the own mask).
+    const uint32_t mask_union = __reduce_or_sync(0xffffffffu, mine);
+#endif
 #pragma unroll
-    for (int T = 0; T < 16; ++T) {
-      // bit = 0 or 2^B; next address = address + 16 (4) * [bit set] as ONE multiply-add on the FMA pipe
-      // (mad.hi with 2^(36-B) for B >= 5: bit * 2^(36-B) >> 32 = 16; mad.lo with 16 >> B below), leaving the compare/logic pipe to the screening
-      const int B = 15 - T;  // bit position of leaf T
-      const uint32_t bit = mine & (1u << B);
-      uint32_t n16, n4;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "setp.ne.u32 p, %2, 0;\n\t"
-          "@p st.shared.v4.u32 [%0], {%3, %4, %5, %6};\n\t"
-          "@p st.shared.u32 [%1], %7;\n\t}"
-          ::"r"(a16), "r"(a4), "r"(bit), "r"(v[4 * T]), "r"(v[4 * T + 1]), "r"(v[4 * T + 2]), "r"(v[4 * T + 3]),
-            "r"(c0 + (uint32_t)(4 * T))
-          : "memory");
-      if (B >= 5)
-        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(1u << ((36 - B) & 31)), "r"(a16));
-      else
-        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(16u >> B), "r"(a16));
-      if (B >= 3)
-        asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(1u << ((34 - B) & 31)), "r"(a4));
-      else
-        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(4u >> B), "r"(a4));
-      a16 = n16;
-      a4 = n4;
+    for (int G = 0; G < 4; ++G) {
+#ifdef CM_PUSH_GROUPS
+      if (!(mask_union & (0xF000u >> (4 * G)))) continue;  // warp-uniform
+#endif
+#pragma unroll
+      for (int T = 4 * G; T < 4 * G + 4; ++T) {
+        // bit = 0 or 2^B; next address = address + 16 (4) * [bit set] as ONE multiply-add on the FMA pipe
+        // (mad.hi with 2^(36-B) for B >= 5: bit * 2^(36-B) >> 32 = 16; mad.lo with 16 >> B below), leaving the compare/logic pipe to the screening
+        const int B = 15 - T;  // bit position of leaf T
+        const uint32_t bit = mine & (1u << B);
+        uint32_t n16, n4;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.u32 p, %2, 0;\n\t"
+            "@p st.shared.v4.u32 [%0], {%3, %4, %5, %6};\n\t"
+            "@p st.shared.u32 [%1], %7;\n\t}"
+            ::"r"(a16), "r"(a4), "r"(bit), "r"(v[4 * T]), "r"(v[4 * T + 1]), "r"(v[4 * T + 2]), "r"(v[4 * T + 3]),
+              "r"(c0 + (uint32_t)(4 * T))
+            : "memory");
+        if (B >= 5)
+          asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(1u << ((36 - B) & 31)), "r"(a16));
+        else
+          asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n16) : "r"(bit), "r"(16u >> B), "r"(a16));
+        if (B >= 3)
+          asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(1u << ((34 - B) & 31)), "r"(a4));
+        else
+          asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n4) : "r"(bit), "r"(4u >> B), "r"(a4));
+        a16 = n16;
+        a4 = n4;
+      }
     }
     rc.qn += n_mine;
     CM_PROBE(rc.c_slow += clock64() - t_slow0;)
@@ -2379,6 +2398,7 @@ template <typename T>
 int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int64_t ldr, int d, const MmaPlan& pl,
              const MmaBuffers& b, cudaStream_t st, const uint8_t* ref_cell = nullptr, const uint32_t* ref_rad2 = nullptr) {
   CM_CUDA_CHECK(cudaMemsetAsync(b.info, 0, sizeof(ScaleInfo), st));
+  bool q_img_done = false;
   const int wpb = 8;
   int gq = (int)(ceil_div(n_q, wpb) < kNumSMs * 8 ? ceil_div(n_q, wpb) : kNumSMs * 8);
   int gr = (int)(ceil_div(n_r, wpb) < kNumSMs * 8 ? ceil_div(n_r, wpb) : kNumSMs * 8);
@@ -2454,9 +2474,16 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
     home_cell_kernel<<<(unsigned)ceil_div(pl.n_q_tiles, 128), 128, 0, st>>>(b.perm_q, b.q_cell, (int)pl.n_q_tiles, b.home_cell);
     CM_LAUNCH_CHECK("home_cell_kernel");
     if (tc) {
+      // the sorted query operand rows are needed by the bounds pass: build the query image first
+      const int64_t tq0 = pl.n_q_pad * (pl.kp_q / 8);
+      const int bq0 = (int)(ceil_div(tq0, 256) < kNumSMs * 16 ? ceil_div(tq0, 256) : kNumSMs * 16);
+      prep_kernel<T><<<bq0, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q / pl.parts / 8, pl.dc, pl.parts, b.mu, b.q_norms, b.info, 1,
+                                          b.perm_q, reinterpret_cast<uint4*>(b.q_img));
+      CM_LAUNCH_CHECK("prep_kernel(Q)");
+      q_img_done = true;
       PivParams pb = pp;
       pb.ld = ldq; pb.n = n_q; pb.norms = b.q_norms; pb.n_tiles = pl.n_q_tiles;
-      pb.perm = b.perm_q; pb.rad2_in = b.cell_rad2; pb.lb2 = b.cell_lb2;
+      pb.perm = b.perm_q; pb.rad2_in = b.cell_rad2; pb.lb2 = b.cell_lb2; pb.q_img = b.q_img;
       rc_a = launch_pivot_tc<T, kPivBounds>(Q, pb, st);
     } else {
       rc_a = launch_tile_bounds_any<T>(Q, ldq, d, b.mu, b.perm_q, pl.n_q_tiles, b.piv_t, b.piv_norm, nc, b.cell_rad2, b.cell_lb2, st);
@@ -2473,9 +2500,11 @@ int run_prep(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int6
   int64_t tq = pl.n_q_pad * (pl.kp_q / 8), tr = pl.n_r_pad * pl.parts * (pl.kp_r / 8);
   int bq = (int)(ceil_div(tq, 256) < kNumSMs * 16 ? ceil_div(tq, 256) : kNumSMs * 16);
   int br = (int)(ceil_div(tr, 256) < kNumSMs * 16 ? ceil_div(tr, 256) : kNumSMs * 16);
-  prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q / pl.parts / 8, pl.dc, pl.parts, b.mu, b.q_norms, b.info, 1,
-                                     b.perm_q, reinterpret_cast<uint4*>(b.q_img));
-  CM_LAUNCH_CHECK("prep_kernel(Q)");
+  if (!q_img_done) {
+    prep_kernel<T><<<bq, 256, 0, st>>>(Q, ldq, n_q, pl.n_q_pad, d, pl.kp_q / pl.parts / 8, pl.dc, pl.parts, b.mu, b.q_norms, b.info, 1,
+                                       b.perm_q, reinterpret_cast<uint4*>(b.q_img));
+    CM_LAUNCH_CHECK("prep_kernel(Q)");
+  }
   prep_kernel<T><<<br, 256, 0, st>>>(R, ldr, n_r, pl.n_r_pad, d, pl.kp_r / 8, pl.dc, pl.parts, b.mu, b.r_norms, b.info, 0, b.perm_r,
                                      reinterpret_cast<uint4*>(b.r_img));
   CM_LAUNCH_CHECK("prep_kernel(R)");
