@@ -549,13 +549,13 @@ class CellMapper(EvaluationMixin):
             lut = _to_device(np.ascontiguousarray(to_orig.astype(code_dtype)))
             pred_codes = lut[code_dev.long()].cpu().numpy()
             conf = conf_dev.cpu().numpy()
-            pred = pd.Series(pd.Categorical.from_codes(pred_codes, dtype=ref_col.dtype, validate=False), index=self.query.obs_names)
+            pred = pd.Series(pd.Categorical.from_codes(pred_codes, dtype=ref_col.dtype, validate=False), index=self.query.obs_names, copy=False)
         else:
             pred_codes = code_dev.cpu().numpy()
             conf = conf_dev.cpu().numpy()
             pred = pd.Series(data=np.array(cats)[pred_codes], index=self.query.obs_names, dtype=ref_col.dtype)
         self.query.obs[f"{key}_{prediction_postfix}"] = pred
-        self.query.obs[f"{key}_{confidence_postfix}"] = pd.Series(conf, index=self.query.obs_names)
+        self.query.obs[f"{key}_{confidence_postfix}"] = pd.Series(conf, index=self.query.obs_names, copy=False)  # a fresh array: no defensive copy
         if f"{key}_colors" in self.reference.uns:  # cellmapper.py:611-617
             color_lookup = dict(zip(self.reference.obs[key].cat.categories, self.reference.uns[f"{key}_colors"], strict=True))
             self.query.uns[f"{key}_{prediction_postfix}_colors"] = [
@@ -568,7 +568,7 @@ class CellMapper(EvaluationMixin):
         m = self._require_mapping()
         values = np.array(self.reference.obs[key])
         out = device.spmm(m.indptr, m.cols, m.vals, _to_device(values))
-        self.query.obs[f"{key}_{prediction_postfix}"] = pd.Series(data=out.cpu().numpy().ravel(), index=self.query.obs_names)
+        self.query.obs[f"{key}_{prediction_postfix}"] = pd.Series(data=out.cpu().numpy().ravel(), index=self.query.obs_names, copy=False)
         logger.info("Numerical data mapped and stored in query.obs['%s'].", f"{key}_{prediction_postfix}")
 
     def map(

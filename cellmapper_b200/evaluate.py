@@ -150,7 +150,8 @@ class EvaluationMixin:
             codes_dev = _to_device(codes)
         all_dev, groups_dev = self.presence_scores_device(codes_dev, len(groups) if groups is not None else 0)
         _process_column(all_dev, log, tuple(percentile))
-        self.reference.obs[key_added] = pd.Series(all_dev.cpu().numpy(), index=self.reference.obs_names)
+        # a fresh array owned by nobody else: pandas' defensive copy of 10 M float64 (31 ms) is not needed
+        self.reference.obs[key_added] = pd.Series(all_dev.cpu().numpy(), index=self.reference.obs_names, copy=False)
         logger.info("Presence score across all query cells computed and stored in `reference.obs['%s']`", key_added)
         if groupby is not None:
             for g in range(len(groups)):
