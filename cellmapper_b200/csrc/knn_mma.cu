@@ -807,7 +807,9 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
   __shared__ int hist[kMaxCells];
   __shared__ unsigned int rad[kMaxCells];
   __shared__ uint32_t wmin[4][MODE == kPivBounds ? kMaxCells : 1];
+  __shared__ double smu[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 64) smu[threadIdx.x] = (int)threadIdx.x < p.d ? p.mu[threadIdx.x] : 0.0;
   const uint32_t b_bytes = (uint32_t)kMmaTile * p.kp_r * 2;
   const uint32_t bar_b = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
   for (int i = threadIdx.x; i < kMaxCells; i += kPivThreads) {
@@ -891,38 +893,38 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
       cp_async_wait_all();
       __syncwarp();  // the warp's 32 staged rows are complete and visible
       const T* xr = stage + (size_t)lane * row_stride;
-      auto pack = [](const float (&f)[8]) {
-        uint4 v;
-        v.x = (uint32_t)__half_as_ushort(__float2half_rn(f[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[1])) << 16);
-        v.y = (uint32_t)__half_as_ushort(__float2half_rn(f[2])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[3])) << 16);
-        v.z = (uint32_t)__half_as_ushort(__float2half_rn(f[4])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[5])) << 16);
-        v.w = (uint32_t)__half_as_ushort(__float2half_rn(f[6])) | ((uint32_t)__half_as_ushort(__float2half_rn(f[7])) << 16);
-        return v;
-      };
+      // per pair of columns: one split (hi, lo) per element, the factor -2 as one half2 multiply per segment word
+      const __half2 minus2 = __floats2half2_rn(-2.f, -2.f);
       for (int ci = 0; ci < p.dc; ++ci) {
-        float s0[8], s1[8], s2[8];
+        uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int cs = ci * 8 + e;
-          float hi2 = 0.f, lo2 = 0.f, nc = 0.f;
-          if (row >= 0) {
-            if (cs < p.d) {
-              const float xs = (float)(((double)xr[cs] - p.mu[cs]) * (double)scale);
-              const __half hi = __float2half_rn(xs);
-              const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
-              hi2 = -2.f * __half2float(hi);
-              lo2 = -2.f * lo;
-            } else if (cs < p.d + 3) {
-              nc = kNormColumn;
+        for (int pr = 0; pr < 4; ++pr) {
+          __half hi[2], lo[2];
+          uint32_t norm_bits = 0u;
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int cs = ci * 8 + pr * 2 + e2;
+            hi[e2] = __float2half_rn(0.f);
+            lo[e2] = hi[e2];
+            if (row >= 0) {
+              if (cs < p.d) {
+                const float xs = (float)((double)xr[cs] - smu[cs]) * scale;  // scale is a power of two: the same value as prep_kernel's
+                hi[e2] = __float2half_rn(xs);
+                lo[e2] = __float2half_rn(xs - __half2float(hi[e2]));
+              } else if (cs < p.d + 3) {
+                norm_bits |= 0x5C00u << (16 * e2);  // fp16 256.0: the constant of the three norm columns
+              }
             }
           }
-          s0[e] = cs < p.d ? hi2 : nc;
-          s1[e] = hi2;
-          s2[e] = lo2;
+          const __half2 h2 = __hmul2(__halves2half2(hi[0], hi[1]), minus2);
+          const __half2 l2 = __hmul2(__halves2half2(lo[0], lo[1]), minus2);
+          w1[pr] = *reinterpret_cast<const uint32_t*>(&h2);
+          w2[pr] = *reinterpret_cast<const uint32_t*>(&l2);
+          w0[pr] = w1[pr] | norm_bits;  // hi is zero where the norm columns sit
         }
-        tmem_st_32x32b_x4(t_lane_a + 4 * ci, pack(s0));
-        tmem_st_32x32b_x4(t_lane_a + 4 * (p.dc + ci), pack(s1));
-        tmem_st_32x32b_x4(t_lane_a + 4 * (2 * p.dc + ci), pack(s2));
+        tmem_st_32x32b_x4(t_lane_a + 4 * ci, make_uint4(w0[0], w0[1], w0[2], w0[3]));
+        tmem_st_32x32b_x4(t_lane_a + 4 * (p.dc + ci), make_uint4(w1[0], w1[1], w1[2], w1[3]));
+        tmem_st_32x32b_x4(t_lane_a + 4 * (2 * p.dc + ci), make_uint4(w2[0], w2[1], w2[2], w2[3]));
       }
       if ((3 * p.dc) & 1) tmem_st_32x32b_x4(t_lane_a + 4 * (3 * p.dc), make_uint4(0u, 0u, 0u, 0u));  // the padding chunk
       }
