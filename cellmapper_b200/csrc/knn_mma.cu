@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
 #pragma unroll
         for (int pr = 0; pr < 4; ++pr) {
           __half hi[2], lo[2];
-          uint32_t norm_bits = 0u;
+          uint32_t norm_bits = 0u, norm_mask = 0u;
 #pragma unroll
           for (int e2 = 0; e2 < 2; ++e2) {
             const int cs = ci * 8 + pr * 2 + e2;
@@ -913,6 +913,7 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
                 lo[e2] = __float2half_rn(xs - __half2float(hi[e2]));
               } else if (cs < p.d + 3) {
                 norm_bits |= 0x5C00u << (16 * e2);  // fp16 256.0: the constant of the three norm columns
+                norm_mask |= 0xFFFFu << (16 * e2);
               }
             }
           }
@@ -920,7 +921,7 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
           const __half2 l2 = __hmul2(__halves2half2(lo[0], lo[1]), minus2);
           w1[pr] = *reinterpret_cast<const uint32_t*>(&h2);
           w2[pr] = *reinterpret_cast<const uint32_t*>(&l2);
-          w0[pr] = w1[pr] | norm_bits;  // hi is zero where the norm columns sit
+          w0[pr] = (w1[pr] & ~norm_mask) | norm_bits;  // (-2 * 0 is -0: the sign bit must not leak into the constant)
         }
         tmem_st_32x32b_x4(t_lane_a + 4 * ci, make_uint4(w0[0], w0[1], w0[2], w0[3]));
         tmem_st_32x32b_x4(t_lane_a + 4 * (p.dc + ci), make_uint4(w1[0], w1[1], w1[2], w1[3]));
