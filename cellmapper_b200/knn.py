@@ -326,8 +326,21 @@ class Neighbors:
         if metric != "euclidean":
             raise ValueError(f"method='b200' supports metric='euclidean' only (got {metric!r}).")
         logger.info("Using %s to compute %d neighbors.", method, n_neighbors)
-        x = self._upload_reference(self.xrep) if self._upload_reference is not None else _to_device(self.xrep)
-        y = x if self.yrep is self.xrep else _to_device(self.yrep)
+        if self._upload_reference is not None and self.yrep is not self.xrep and not isinstance(self.yrep, torch.Tensor):
+            # multi-GPU: the query block goes up on a side stream (PCIe) while the replicated reference is uploaded
+            # 1/world per rank and all-gathered over NVLink on the main stream
+            main = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                y = _to_device(self.yrep)
+                y_ready = torch.cuda.Event()
+                y_ready.record(side)
+            x = self._upload_reference(self.xrep)
+            main.wait_event(y_ready)
+            y.record_stream(main)
+        else:
+            x = self._upload_reference(self.xrep) if self._upload_reference is not None else _to_device(self.xrep)
+            y = x if self.yrep is self.xrep else _to_device(self.yrep)
         np_dtype = np.result_type(
             np.float32 if x.dtype == torch.float32 else np.float64, np.float32 if y.dtype == torch.float32 else np.float64
         )
