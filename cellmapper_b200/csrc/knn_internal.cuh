@@ -38,8 +38,19 @@ static inline int mma_kp_q_part(int d) { return 8 * ((3 * mma_seg_chunks(d) + 1)
 static inline int mma_kp_q(int d) { return mma_parts(d) * mma_kp_q_part(d); }  // fp16 columns of a whole query row
 static inline int mma_kp_r(int d) { return 8 * 2 * mma_seg_chunks(d); }        // fp16 columns of ONE part of the reference image
 constexpr int kMmaMaxK = 40;     // neighbours supported by the candidate buffers
+// CM_SPLIT_EPI=1 (experiment, off): per TMEM lane quadrant one SCANNING epilogue warp and one DRAINING warp
+// (knn_mma.cu: SplitCtx).  Exact and green on the search tests, but 13-20 % slower than the one-warp epilogue on
+// B200 (profiles/r2z_split_epilogue_ab.txt), so the shipping build keeps one warp per quadrant.  The scanner's two
+// hand-over queues per row take 6 KB more shared memory; eight candidate slots per row pay for it.
+#ifndef CM_SPLIT_EPI
+#define CM_SPLIT_EPI 0
+#endif
 #ifndef CM_CAND_CAP
+#if CM_SPLIT_EPI
+#define CM_CAND_CAP 108
+#else
 #define CM_CAND_CAP 116
+#endif
 #endif
 constexpr int kCandCap = CM_CAND_CAP;    // per-row candidate slots in shared memory
 constexpr int kKeepLo = 44;      // after compaction a row keeps between kKeepLo ..

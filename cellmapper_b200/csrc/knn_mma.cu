@@ -1322,11 +1322,20 @@ constexpr int kCandTrigger = kCandCap - kCandSlack;
 constexpr int kQueueCap = CM_QUEUE_CAP;
 constexpr uint32_t kDumpStride = 20 * kQueueCap + 16;
 constexpr size_t kDumpBytes = 4 * 32 * kDumpStride;
+// Split epilogue (CM_SPLIT_EPI, single-part tiles): every row has TWO queues of 5 leaves which the scanning warp fills
+// in turn and hands to the draining warp.  112 bytes = 7 x 16 keeps the 16-byte leaf stores of a quarter warp on distinct
+// banks; bytes 100..103 of a queue hold its length at hand-over.
+constexpr int kQueueCapSplit = 5;
+constexpr uint32_t kDumpStrideSplit = 112;
+constexpr uint32_t kDumpLenOffset = 100;
+constexpr size_t kDumpBytesSplit = 2 * 4 * 32 * kDumpStrideSplit;
+static_assert(20 * kQueueCapSplit <= kDumpLenOffset && kDumpLenOffset + 4 <= kDumpStrideSplit, "split queue does not fit its stride");
 
 // ------------------------------------------------------------------------------------------------
 // the tensor-core kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kMmaThreads = 224;  // warp 0 producer, warps 1 and 6 MMA issue (even / odd tiles), warps 2..5 epilogue
+constexpr int kMmaThreadsSplit = 352;  // + warps 7..10: the draining warps of the split epilogue (quadrant = warp % 4)
 // TMEM (512 columns): the query operand first, then the accumulators.  d <= 53 (one part): 128 columns for the
 // operand (kp_q/2 <= 88 used) + three accumulators, the MMA warps run up to 2 tiles ahead.  Wide rows (several parts,
 // kp_q/2 up to 216 columns): 256 + two accumulators; their tiles are MMA-bound, so the third buffer is not missed.
@@ -1375,6 +1384,104 @@ struct MmaParams {
   ScaleInfo* info;
 };
 
+// ---- split epilogue: a scanning and a draining warp per TMEM lane quadrant (kSplit) ----
+// A query row then has TWO threads (the same lane of the quadrant's two warps).  The SCANNER reads every accumulator
+// tile (fast path, mask, pushes of flagged leaves) and touches no shared row state except for a read of the row's
+// threshold -- a stale, larger threshold only queues more.  When one of its queues cannot take a half tile's leaves it
+// hands the queue to the DRAINER and goes on with the row's other queue; the drainer moves the leaves into the
+// candidate buffer, compacts (~10 k cycles, a third of the one-warp epilogue's time on clustered data) and publishes
+// the tighter threshold, all while the scanner keeps scanning.  The row's candidate buffer and bookkeeping (count,
+// threshold, compaction model) live in shared memory under a lock per quadrant: the scanner takes it only for the
+// straight-line appends of a scan's first tiles (every leaf passes while the thresholds are infinite).
+// What did NOT work (measured, round 2): two symmetric epilogue warps claiming alternate tiles.  Correct, but 17 %
+// slower than one warp: a warp that sleeps on an accumulator barrier sees the tcgen05.commit ~1 000 cycles late, which
+// the one-warp design never notices because its MMA warps run two tiles ahead; and two lessons are kept here --
+// (1) a loop that only lane 0 executes (lock spin) leaves the warp split in two groups once lane 0 has slept in it
+// (bar.warp.sync synchronises, it does not re-merge): .aligned instructions and converged reductions then run on partial
+// warps, so every spin below is executed by the whole warp on a broadcast value; (2) parity waits are only unambiguous
+// while the waiter is at most one phase behind, which out-of-order buffer releases break for the MMA warps.
+constexpr uint32_t kStateField = 4 * 32 * 4;  // bytes between the fields of the shared row state
+struct SplitCtx {
+  uint32_t st;        // shared address of this row's count; threshold key, threshold, smallest key, gain follow at kStateField steps
+  uint32_t lock;      // shared address of the quadrant's lock word
+  uint32_t ncomp;     // shared address of the quadrant's compaction counter
+  uint32_t thr_pub;   // shared address of the quadrant's published threshold for the producer's cell pruning (0: none)
+  uint32_t qfull;     // shared address of the quadrant's two queue flags (0: the scanner may fill, 1: the drainer must drain)
+  uint32_t dump0;     // shared address of this row's queue 0; queue 1 follows 128 rows further
+  int cur;            // scanner: the queue being filled
+  float inv_s2, qn;   // score -> squared-distance units
+  int n_compact0;     // the counter at the last acquire
+};
+constexpr uint32_t kQueueSetBytes = 128 * kDumpStrideSplit;  // queue 1 of a row lies this far behind its queue 0
+
+__device__ __forceinline__ uint32_t lds_acquire_bcast(uint32_t addr) {  // one lane's view of a flag, warp-uniform
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return __shfl_sync(0xffffffffu, v, 0);
+}
+__device__ __forceinline__ void sts_release_lane0(uint32_t addr, uint32_t v) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __noinline__ void split_timeout(const char* what) {
+  printf("cellmapper_b200: %s timed out (block %d warp %d)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5));
+  __trap();
+}
+// spin until the flag has the wanted value (the whole warp runs the loop on a broadcast value)
+__device__ __forceinline__ void split_wait_flag(uint32_t addr, uint32_t want, const char* what) {
+  if (lds_acquire_bcast(addr) == want) return;
+  const long long t0 = clock64();
+  while (lds_acquire_bcast(addr) != want) {
+    __nanosleep(100);
+    if (clock64() - t0 > 20000000000LL) split_timeout(what);  // ~10 s: a protocol bug must trap, not hang the GPU
+  }
+}
+__device__ __forceinline__ void split_acquire(RowCand& rc, SplitCtx& sx) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t old = 1u;
+    if ((threadIdx.x & 31) == 0)
+      asm volatile("atom.acquire.cta.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "r"(sx.lock) : "memory");
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == 0u) break;  // warp-uniform
+    __nanosleep(100);
+    if (clock64() - t0 > 20000000000LL) split_timeout("epilogue lock");
+  }
+  rc.cnt = (int)lds_u32_volatile(sx.st);
+  rc.thr_key = lds_u32_volatile(sx.st + kStateField);
+  rc.thr = __uint_as_float(lds_u32_volatile(sx.st + 2 * kStateField));
+  rc.kmin = lds_u32_volatile(sx.st + 3 * kStateField);
+  rc.gain = lds_u32_volatile(sx.st + 4 * kStateField);
+  rc.n_compact = (int)lds_u32_volatile(sx.ncomp);
+  sx.n_compact0 = rc.n_compact;
+}
+__device__ __forceinline__ void split_release(RowCand& rc, SplitCtx& sx) {
+  sts_u32(sx.st, (uint32_t)rc.cnt);
+  sts_u32(sx.st + kStateField, rc.thr_key);
+  sts_u32(sx.st + 2 * kStateField, __float_as_uint(rc.thr));
+  sts_u32(sx.st + 3 * kStateField, rc.kmin);
+  sts_u32(sx.st + 4 * kStateField, rc.gain);
+  if (rc.n_compact != sx.n_compact0) {  // warp-uniform: thresholds only move in compactions
+    if ((threadIdx.x & 31) == 0) sts_u32(sx.ncomp, (uint32_t)rc.n_compact);
+    if (sx.thr_pub) {
+      const float t2 = sx.qn >= 0.f ? (rc.thr * sx.inv_s2 + sx.qn) * (1.f + 1e-6f) : -CUDART_INF_F;  // rounded up
+      const uint32_t m = __reduce_max_sync(0xffffffffu, float_to_ordered(t2));
+      if ((threadIdx.x & 31) == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sx.thr_pub), "r"(m) : "memory");
+    }
+  }
+  sts_release_lane0(sx.lock, 0u);
+}
+// scanner: hand the current queue to the drainer and continue with the row's other queue (waits for the drainer only
+// when that one has not been emptied yet, i.e. when the drainer is a whole queue behind)
+__device__ __forceinline__ void split_hand_over(RowCand& rc, SplitCtx& sx) {
+  sts_u32(rc.dump + kDumpLenOffset, (uint32_t)rc.qn);
+  sts_release_lane0(sx.qfull + 4u * (uint32_t)sx.cur, 1u);
+  sx.cur ^= 1;
+  split_wait_flag(sx.qfull + 4u * (uint32_t)sx.cur, 0u, "queue hand-over");
+  rc.dump = sx.dump0 + (uint32_t)sx.cur * kQueueSetBytes;
+  rc.qn = 0;
+}
+
 // Append the elements of one leaf (<= 3 consecutive columns) that are below the row's threshold:
 // predicated stores, no branches.
 template <int N>
@@ -1400,6 +1507,7 @@ __device__ __forceinline__ void append_leaf(const uint32_t* v, uint32_t c0, RowC
 
 // Drain the per-lane leaf queues into the candidate buffers: iteration j handles entry j of every lane
 // that has one, so the trip count is the longest queue of the warp.
+template <int QC>
 __device__ __forceinline__ void drain_queue(RowCand& rc, int k) {
   CM_PROBE(const long long t_d0 = clock64();)
   const int n_max = (int)__reduce_max_sync(0xffffffffu, (unsigned)rc.qn);
@@ -1410,7 +1518,7 @@ __device__ __forceinline__ void drain_queue(RowCand& rc, int k) {
     if (j < rc.qn) {
       uint32_t x0, x1, x2, x3;
       lds_v4(rc.dump + 16u * (uint32_t)j, x0, x1, x2, x3);
-      const uint32_t col = lds_u32(rc.dump + 16u * kQueueCap + 4u * (uint32_t)j);
+      const uint32_t col = lds_u32(rc.dump + 16u * QC + 4u * (uint32_t)j);
       const float thr = rc.thr;
       const bool p0 = __uint_as_float(x0) < thr, p1 = __uint_as_float(x1) < thr, p2 = __uint_as_float(x2) < thr,
                  p3 = __uint_as_float(x3) < thr;
@@ -1450,7 +1558,10 @@ __device__ __forceinline__ void drain_queue(RowCand& rc, int k) {
 // threshold is in the buffer or in the queue" holds.  Halves in which one lane alone has more than a
 // queue of flagged leaves (the first tiles of a scan, before the thresholds are finite) take the
 // straight-line path: predicated appends of all 64 columns.
-__device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c0, RowCand& rc, int k, int flags) {
+template <bool kSplit>
+__device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c0, RowCand& rc, int k, int flags, SplitCtx& sx) {
+  constexpr int QC = kSplit ? kQueueCapSplit : kQueueCap;
+  if (kSplit) rc.thr = __uint_as_float(lds_u32_volatile(sx.st + 2 * kStateField));  // possibly stale (larger): only queues more
   float t[16];
 #pragma unroll
   for (int g = 0; g < 16; ++g)
@@ -1474,9 +1585,14 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     for (int T = 8; T < 16; ++T) mb = __funnelshift_l(__float_as_uint(t[T] - thr0), mb, 1);
     const uint32_t mine = (ma << 8) | mb;
     const int n_mine = __popc(mine);
-    if (__any_sync(0xffffffffu, rc.qn + n_mine > kQueueCap)) {
-      drain_queue(rc, k);
-      if (__any_sync(0xffffffffu, n_mine > kQueueCap)) {
+    if (__any_sync(0xffffffffu, rc.qn + n_mine > QC)) {
+      if (kSplit) {
+        if (__any_sync(0xffffffffu, rc.qn > 0)) split_hand_over(rc, sx);
+      } else {
+        drain_queue<QC>(rc, k);
+      }
+      if (__any_sync(0xffffffffu, n_mine > QC)) {
+        if (kSplit) split_acquire(rc, sx);
         // straight-line predicated appends of all 64 columns, a compaction check every kCandSlack columns
         const uint32_t idx_off = rc.idx - rc.keys;
 #pragma unroll
@@ -1496,6 +1612,7 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
           }
         }
         CM_PROBE(rc.n_leaf += 16; rc.c_slow += clock64() - t_slow0;)
+        if (kSplit) split_release(rc, sx);
         return;
       }
     }
@@ -1505,7 +1622,7 @@ __device__ __forceinline__ void process_half(const uint32_t (&v)[64], uint32_t c
     // on the memory pipe's scoreboard after every store (ncu r1c: 80 % short-scoreboard stalls on the
     // cursor increments, a quarter of the epilogue's time).
     const uint32_t cur0 = rc.dump + 16u * (uint32_t)rc.qn;
-    const uint32_t ccur0 = rc.dump + 16u * kQueueCap + 4u * (uint32_t)rc.qn;
+    const uint32_t ccur0 = rc.dump + 16u * QC + 4u * (uint32_t)rc.qn;
     // Predicated, not branched: the flagged leaves differ from lane to lane, so a branch per leaf diverges
     // on nearly every one of them (ncu r1e: instruction-fetch and branch-resolution stalls on the 16 tests).
     // The two store addresses advance through a chain of fresh registers: a cursor updated in place would
@@ -1659,8 +1776,20 @@ __device__ __forceinline__ void mma_issue_loop(const MmaIssueArgs& a) {
   }
 }
 
-template <bool kDebug, bool kWide>
-__global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParams p) {
+// shared row state of the split epilogue (see SplitCtx); empty without it
+template <bool kSplit> struct SplitShared {};
+template <> struct SplitShared<true> {
+  uint32_t row[5][4][32];  // count, threshold key, threshold (float bits), smallest key, gain: [field][quadrant][lane]
+  uint32_t lock[4];
+  uint32_t n_compact[4];
+  uint32_t qfull[4][2];    // per quadrant and queue: 0 = the scanner may fill it, 1 = handed to the drainer
+  uint32_t scan_done[4];   // the quadrant's scanner has handed over its last queue
+};
+
+template <bool kDebug, bool kWide, bool kSplit>
+__global__ void __launch_bounds__(kSplit ? kMmaThreadsSplit : kMmaThreads, 1) mma_topk_kernel(const MmaParams p) {
+  static_assert(!(kSplit && (kWide || kDebug)), "the split epilogue serves single-part tiles of the shipping kernel");
+  __shared__ SplitShared<kSplit> split;
   constexpr int kAccBufs = TmemLayout<kWide>::kAccBufs;
   constexpr int kTmemACols = TmemLayout<kWide>::kACols;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -1713,6 +1842,22 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     }
     for (int i = 0; i < 4; ++i) thr_pub[i] = 0xFFFFFFFFu;  // +inf: nothing can be pruned yet
     fence_barrier_init();
+  }
+  if constexpr (kSplit) {
+    if (threadIdx.x < 128) {
+      const int q = threadIdx.x >> 5, l = threadIdx.x & 31;
+      split.row[0][q][l] = 0u;           // count
+      split.row[1][q][l] = 0xFFFFFFFFu;  // threshold key: nothing seen yet
+      split.row[2][q][l] = kInfBits;     // threshold
+      split.row[3][q][l] = kInfBits;     // smallest key
+      split.row[4][q][l] = 0x3f800000u;  // gain 1.0f
+    }
+    if (threadIdx.x < 4) {
+      split.lock[threadIdx.x] = 0u;
+      split.n_compact[threadIdx.x] = 0u;
+      split.qfull[threadIdx.x][0] = split.qfull[threadIdx.x][1] = 0u;
+      split.scan_done[threadIdx.x] = 0u;
+    }
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
@@ -1817,14 +1962,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       case 6: mma_issue_loop<6>(a); break;
       default: mma_issue_loop<7>(a); break;
     }
-  } else if (warp >= 2 && warp <= 5) {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4, one query row per thread =====
+  } else if ((warp >= 2 && warp <= 5) || (kSplit && warp >= 7)) {
+    // ===== epilogue: warps 2..5 (scanners) and, kSplit, 7..10 (drainers); quadrant = warp % 4, one query row per thread =====
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane;
+    const bool drainer = kSplit && warp >= 7;
     RowCand rc;
     rc.keys = smem_u32(cand_keys + quad * kCandCap * 32 + lane);
     rc.idx = smem_u32(cand_idx + quad * kCandCap * 32 + lane);
-    rc.dump = smem_u32(dump_base + (size_t)(quad * 32 + lane) * kDumpStride);
+    rc.dump = kSplit ? smem_u32(dump_base + (size_t)(quad * 32 + lane) * kDumpStrideSplit)
+                     : smem_u32(dump_base + (size_t)(quad * 32 + lane) * kDumpStride);
     rc.cnt = 0;
     rc.qn = 0;
     rc.thr_key = 0xFFFFFFFFu;
@@ -1836,7 +1983,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     const int64_t q_row = (int64_t)q_tile * kMmaTile + row_in_tile;
     const uint32_t t_lane_a = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t t_lane = t_lane_a + kTmemACols;
-    {
+    if (!drainer) {
       // query operand: this thread's row of Q' (kp_q fp16, row-major) -> TMEM columns [0, kp_q/2)
       const uint4* src = reinterpret_cast<const uint4*>(p.q_img + (size_t)q_row * p.kp_q * 2);
       for (int c = 0; c < (p.kp_q >> 4); ++c) tmem_st_32x32b_x8(t_lane_a + 8 * c, src[2 * c], src[2 * c + 1]);
@@ -1856,6 +2003,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     }
     int published = 0;
     auto publish = [&]() {
+      if (kSplit) return;  // published by whoever compacts (split_release)
       if (p.cell_lb2 && rc.n_compact != published) {  // thresholds only move in compactions (warp-uniform counter)
         published = rc.n_compact;
         const float t2 = qn >= 0.f ? (rc.thr * inv_s2 + qn) * (1.f + 1e-6f) : -CUDART_INF_F;  // rounded up
@@ -1864,6 +2012,87 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       }
     };
 
+    SplitCtx sx;
+    sx.st = sx.lock = sx.ncomp = sx.thr_pub = sx.qfull = sx.dump0 = 0u;
+    sx.cur = 0;
+    sx.inv_s2 = inv_s2;
+    sx.qn = qn;
+    sx.n_compact0 = 0;
+    if constexpr (kSplit) {
+      sx.st = smem_u32(&split.row[0][quad][lane]);
+      sx.lock = smem_u32(&split.lock[quad]);
+      sx.ncomp = smem_u32(&split.n_compact[quad]);
+      sx.thr_pub = p.cell_lb2 ? thr_pub_addr + 4u * quad : 0u;
+      sx.qfull = smem_u32(&split.qfull[quad][0]);
+      sx.dump0 = rc.dump;
+    }
+    if (drainer) {
+      if constexpr (kSplit) {
+        // ===== drainer: empties the queues the quadrant's scanner hands over, in hand-over order =====
+        const uint32_t done_addr = smem_u32(&split.scan_done[quad]);
+        int next = 0, idle = 0;
+        const long long t0 = clock64();
+#pragma unroll 1
+        for (;;) {
+          const uint32_t flag_addr = sx.qfull + 4u * (uint32_t)next;
+          // Idle polling must stay out of the scanner's way (both warps issue through the same scheduler; the first
+          // version polled with three acquire loads and a clock read every 200 ns: 30 % of the kernel's instructions):
+          // one plain load per ~1.5 us -- a hand-over is not urgent, the scanner has the row's other queue.
+          if (__shfl_sync(0xffffffffu, lds_u32_volatile(flag_addr), 0) == 0u) {
+            // nothing handed over: finished if the scanner is (its last hand-over precedes the flag: look again)
+            if (lds_acquire_bcast(done_addr) != 0u && lds_acquire_bcast(flag_addr) == 0u) break;
+            __nanosleep(1500);
+            if ((++idle & 1023) == 0 && clock64() - t0 > 40000000000LL) split_timeout("drainer");  // ~20 s
+            continue;
+          }
+          (void)lds_acquire_bcast(flag_addr);  // acquire: the queue's contents are visible
+          rc.dump = sx.dump0 + (uint32_t)next * kQueueSetBytes;
+          rc.qn = (int)lds_u32_volatile(rc.dump + kDumpLenOffset);
+          split_acquire(rc, sx);
+          drain_queue<kQueueCapSplit>(rc, p.k);
+          split_release(rc, sx);
+          sts_release_lane0(flag_addr, 0u);
+          next ^= 1;
+        }
+        // the scan is over and every queue is empty: final compaction and write-out (nobody else touches the rows now)
+        split_acquire(rc, sx);
+        compact_row(rc, p.k);  // leave at most kCandOut entries
+        const int64_t o = (int64_t)blockIdx.x * kMmaTile + row_in_tile;
+        for (int e = 0; e < rc.cnt; ++e) {
+          p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
+          p.cand_i[o * kCandOut + e] = (int32_t)lds_u32(rc.idx + e * kCandStride);
+        }
+        p.cand_cnt[o] = rc.cnt;
+        p.cand_thr[o] = rc.thr;
+      }
+    } else if constexpr (kSplit) {
+      // ===== scanner: every accumulator tile, one half tile in registers at a time (352 threads leave 168 registers;
+      // the ~50 exposed cycles of each tcgen05.ld are cheaper than spilling the second register set) =====
+      uint32_t va[64];
+#pragma unroll 1
+      for (int it = 0;; ++it) {
+        const int buf = it % kAccBufs;
+        mbar_wait(bar_acc_full(buf), (uint32_t)(it / kAccBufs) & 1u);
+        const int tcur = (int)lds_u32_volatile(ring_addr + 4u * (uint32_t)(it & (kTileRing - 1)));
+        if (tcur < 0) break;
+        tc_fence_after();
+        const uint32_t t_buf = t_lane + (uint32_t)buf * kMmaTile;
+        const uint32_t col_base = (uint32_t)tcur * kMmaTile;
+        tmem_ld_32x32b_x64(t_buf, va);
+        tmem_ld_wait();
+        process_half<true>(va, col_base, rc, p.k, 0, sx);
+        tmem_ld_32x32b_x64(t_buf + 64, va);
+        tmem_ld_wait();
+        // this warp has read the whole buffer: hand it back before the second half's math
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+        process_half<true>(va, col_base + 64, rc, p.k, 0, sx);
+      }
+      // the last queue goes to the drainer, which also does the final compaction and the write-out
+      if (__any_sync(0xffffffffu, rc.qn > 0)) split_hand_over(rc, sx);
+      sts_release_lane0(smem_u32(&split.scan_done[quad]), 1u);
+    } else {
     uint32_t va[64], vb[64];  // two register sets: the next half tile's tcgen05.ld overlaps this half's math
     mbar_wait(bar_acc_full(0), 0);
     CM_PROBE(if (tl) tl[2] = clock64() - tl0;)
@@ -1890,7 +2119,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
       tmem_ld_wait();                          // columns 0..63 in va
       tmem_ld_32x32b_x64(t_buf + 64, vb);      // columns 64..127 in flight
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[j] = __uint_as_float(va[j]);
-      if (!(CM_FLAGS(p.flags) & 1)) process_half(va, col_base, rc, p.k, CM_FLAGS(p.flags));
+      if (!(CM_FLAGS(p.flags) & 1)) process_half<false>(va, col_base, rc, p.k, CM_FLAGS(p.flags), sx);
 
       tmem_ld_wait();                          // columns 64..127 in vb
       // this warp has read the whole buffer: hand it back, then start on the next tile
@@ -1907,12 +2136,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
         }
       }
       if (kDebug) for (int j = 0; j < 64; ++j) dbg[64 + j] = __uint_as_float(vb[j]);
-      if (!(CM_FLAGS(p.flags) & 1)) process_half(vb, col_base + 64, rc, p.k, CM_FLAGS(p.flags));
+      if (!(CM_FLAGS(p.flags) & 1)) process_half<false>(vb, col_base + 64, rc, p.k, CM_FLAGS(p.flags), sx);
       publish();
       CM_PROBE(++n_epi_tiles;)
     }
     CM_PROBE(if (tl) tl[3] = clock64() - tl0;)
-    drain_queue(rc, p.k);
+    drain_queue<kQueueCap>(rc, p.k);
     compact_row(rc, p.k);  // leave at most kCandOut entries
     CM_PROBE(if (tl) tl[4] = clock64() - tl0;)
 #ifdef CM_DEV_PROBES
@@ -1932,6 +2161,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) mma_topk_kernel(const MmaParam
     p.cand_cnt[o] = rc.cnt;
     p.cand_thr[o] = rc.thr;
     CM_PROBE(if (tl) { tl[5] = clock64() - tl0; tl[6] = n_epi_tiles; })
+    }  // one-warp epilogue
   }
 
   tc_fence_before();
@@ -2314,8 +2544,10 @@ MmaPlan make_plan(int64_t n_q, int64_t n_r, int d, bool exhaustive) {
   pl.perm_mul = scramble_multiplier(pl.n_r_pad);
   pl.n_cells = n_r >= kMinRefsForCells ? kMaxCells : 0;
   const size_t b_bytes = (size_t)kMmaTile * pl.kp_r * 2;
-  const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2 + kDumpBytes;
-  const size_t budget = 227 * 1024 - 4096;  // 4 KB of static shared memory (barriers, TMEM slot, tile ring, cell tables)
+  // the queues of the split epilogue are the larger ones; every launch uses the same layout
+  const size_t cand_bytes = (size_t)4 * kCandCap * 32 * 4 * 2 + (CM_SPLIT_EPI ? kDumpBytesSplit : kDumpBytes);
+  // static shared memory (barriers, TMEM slot, tile ring, cell tables): 4 KB, + 2 KB of split row state
+  const size_t budget = 227 * 1024 - (CM_SPLIT_EPI ? 6144 : 4096);
   int stages = (int)((budget - cand_bytes) / b_bytes);
   pl.stages = stages > kMaxStages ? kMaxStages : stages;
   pl.smem_bytes = b_bytes * pl.stages + cand_bytes;
@@ -2543,15 +2775,19 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.perm_q = b.perm_q;
   p.info = b.info;
   const int64_t grid = pl.n_items;
-#define CM_LAUNCH_MMA(DBG, WIDE)                                                                                                  \
-  do {                                                                                                                            \
-    CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<DBG, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)); \
-    mma_topk_kernel<DBG, WIDE><<<(unsigned)grid, kMmaThreads, pl.smem_bytes, st>>>(p);                                             \
+#define CM_LAUNCH_MMA(DBG, WIDE, SPLIT)                                                                                                    \
+  do {                                                                                                                                   \
+    CM_CUDA_CHECK(cudaFuncSetAttribute(mma_topk_kernel<DBG, WIDE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)); \
+    mma_topk_kernel<DBG, WIDE, SPLIT><<<(unsigned)grid, SPLIT ? kMmaThreadsSplit : kMmaThreads, pl.smem_bytes, st>>>(p);                   \
   } while (0)
   if (debug_out) {
-    if (pl.wide) CM_LAUNCH_MMA(true, true); else CM_LAUNCH_MMA(true, false);
+    if (pl.wide) CM_LAUNCH_MMA(true, true, false); else CM_LAUNCH_MMA(true, false, false);
+  } else if (pl.wide) {
+    CM_LAUNCH_MMA(false, true, false);
+  } else if (CM_SPLIT_EPI && pl.parts == 1) {
+    CM_LAUNCH_MMA(false, false, true);
   } else {
-    if (pl.wide) CM_LAUNCH_MMA(false, true); else CM_LAUNCH_MMA(false, false);
+    CM_LAUNCH_MMA(false, false, false);  // several parts, narrow operand (54 <= d <= 61)
   }
 #undef CM_LAUNCH_MMA
   CM_LAUNCH_CHECK("mma_topk_kernel");

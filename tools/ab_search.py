@@ -8,11 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "base": (),
-    "pg4": ("CM_PUSH_GROUPS=4",),
-    "q12": ("CM_QUEUE_CAP=12",),
-    "pg4q12": ("CM_PUSH_GROUPS=4", "CM_QUEUE_CAP=12"),
-    "kh26": ("CM_KEEP_HI=26",),
-    "kh18": ("CM_KEEP_HI=18",),
+    "split": ("CM_SPLIT_EPI=1",),
 }
 
 if sys.argv[1] == "build":
