@@ -109,11 +109,13 @@ def knn_search(
     algo: int = _lib.KNN_AUTO,
     return_stats: bool = False,
     ref_cells: tuple[torch.Tensor, torch.Tensor] | None = None,
+    out: tuple[torch.Tensor, torch.Tensor] | None = None,
 ):
     """Exact Euclidean k-NN of every row of ``q`` in ``r`` (reference call site knn.py:428-440).
 
     ``ref_cells``: optional (cell uint8 (n_r,), rad2 int32 (256,)) from ``knn_assign_reference`` over all rows of
     ``r`` (assembled from the ranks' blocks in a multi-GPU run); the search then skips that part of its preparation.
+    ``out``: optional (float64 (n_q,k), int64 (n_q,k)) contiguous device tensors to write into (row blocks of one result).
     Returns (distances float64 (n_q,k), indices int64 (n_q,k)[, stats int64 (4,)]) on the device.
     """
     dev = _check_cuda(q, r)
@@ -130,8 +132,16 @@ def knn_search(
         raise ValueError(f"query and reference have different dimensions: {d} vs {r.shape[1]}")
     lib = _lib.load()
     with torch.cuda.device(dev):
-        out_d = torch.empty((n_q, k), dtype=torch.float64, device=dev)
-        out_i = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+        if out is None:
+            out_d = torch.empty((n_q, k), dtype=torch.float64, device=dev)
+            out_i = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+        else:
+            out_d, out_i = out
+            _check_cuda(out_d, out_i)
+            _expect(out_d, torch.float64, "out[0]")
+            _expect(out_i, torch.int64, "out[1]")
+            if tuple(out_d.shape) != (n_q, k) or tuple(out_i.shape) != (n_q, k) or not (out_d.is_contiguous() and out_i.is_contiguous()):
+                raise ValueError(f"out tensors must be contiguous ({n_q}, {k}) tensors")
         stats = torch.zeros(4, dtype=torch.int64, device=dev)
         ws_bytes = int(lib.cm_knn_workspace_bytes(n_q, n_r, d, k, algo))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

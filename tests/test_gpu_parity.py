@@ -1019,3 +1019,25 @@ def test_near_ties_at_rank_k(torch_cuda, d, offset):
     dd, ii, dx, ix = (t.cpu().numpy() for t in (dd, ii, dx, ix))
     np.testing.assert_array_equal(dd, dx)
     assert neighbours_match(ii, dd, ix, dx, rel=0.0) == 0
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_pipelined_query_upload_matches_plain_search(torch_cuda, monkeypatch, pinned):
+    """The end-to-end path uploads large host query sets in two blocks and searches the first while the second is on
+    its way (knn.Neighbors._compute_yx_pipelined): same neighbours and distances as one search, bit for bit."""
+    torch = torch_cuda
+    from cellmapper_b200 import _lib, device, synth
+    from cellmapper_b200.knn import Neighbors, sklearn_like_dist_mode
+
+    centres = synth.mixture_centres(8, 32)
+    xr, _ = synth.mixture_embedding(20000, centres, seed=3)
+    xq, _ = synth.mixture_embedding(5001, centres, seed=4)
+    monkeypatch.setattr(Neighbors, "_PIPELINE_MIN_BYTES", 0)
+    yrep = torch.from_numpy(xq).pin_memory() if pinned else xq
+    nb = Neighbors(xr, yrep)
+    assert nb._pipelined_query_blocks(15) == [(0, 1152), (1152, 5001)]
+    nb.compute_neighbors(n_neighbors=15, only_yx=True)
+    mode = sklearn_like_dist_mode(np.float32, 32, 15, 20000)
+    d, i = device.knn_search(dev(torch, xq), dev(torch, xr), 15, dist_mode=mode)
+    assert torch.equal(nb.yx.indices_device, i) and torch.equal(nb.yx.distances_device, d)
+    assert nb.yx.rows_full and int(nb.search_stats["yx"][0]) == 0
