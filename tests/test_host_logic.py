@@ -161,3 +161,22 @@ def test_metric_from_sums_matches_reference(method):
     ok = ~np.isnan(want)
     # the reference evaluates scipy's formulas in float32 (both inputs are float32 arrays): 1e-4 absolute
     np.testing.assert_allclose(got[ok], want[ok], atol=2e-4 if method != "js" else 5e-4)
+
+
+def test_pipelined_query_blocks_decision():
+    """Which searches upload their query rows in two blocks (knn.Neighbors._pipelined_query_blocks): large host-resident
+    query sets whose dtype matches the reference and that run on the tensor-core path; everything else takes one upload."""
+    import torch
+
+    from cellmapper_b200.knn import Neighbors
+
+    ref = np.zeros((1000, 50), np.float32)
+    big = np.zeros((400_000, 50), np.float32)  # 80 MB
+    assert Neighbors(ref, big)._pipelined_query_blocks(30) == [(0, 99_968), (99_968, 400_000)]
+    assert Neighbors(ref, torch.from_numpy(big))._pipelined_query_blocks(30) == [(0, 99_968), (99_968, 400_000)]
+    assert Neighbors(ref, big[:1000])._pipelined_query_blocks(30) is None  # small: one upload
+    assert Neighbors(ref, big.astype(np.float64))._pipelined_query_blocks(30) is None  # mixed dtypes are promoted on the device
+    assert Neighbors(ref, big)._pipelined_query_blocks(64) is None  # k outside the tensor-core path
+    assert Neighbors(big, None)._pipelined_query_blocks(30) is None  # self mapping
+    wide = np.zeros((200_000, 200), np.float32)
+    assert Neighbors(np.zeros((1000, 200), np.float32), wide)._pipelined_query_blocks(30) is None  # d > 128
