@@ -22,7 +22,7 @@ KNN_AUTO, KNN_EXACT_F64, KNN_TENSOR_EXHAUSTIVE = 0, 1, 2
 EDGE_STATS_WORKSPACE_BYTES = 32768
 KNN_ASSIGN_WORKSPACE_BYTES = 262144
 SPGEMM_MAX_COLS = 40960
-MMA_MAX_D, MMA_MAX_K = 128, 40  # limits of the tensor-core search (csrc/knn_internal.cuh)
+MMA_MAX_D, MMA_MAX_K = 128, 64  # limits of the tensor-core search (csrc/knn_internal.cuh)
 SELECT_WORKSPACE_BYTES = 16384
 MOMENTS = 8
 

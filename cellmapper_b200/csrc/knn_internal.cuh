@@ -37,7 +37,6 @@ static inline int mma_seg_chunks(int d) { return (mma_ext_chunks(d) + mma_parts(
 static inline int mma_kp_q_part(int d) { return 8 * ((3 * mma_seg_chunks(d) + 1) / 2 * 2); }  // even chunk count
 static inline int mma_kp_q(int d) { return mma_parts(d) * mma_kp_q_part(d); }  // fp16 columns of a whole query row
 static inline int mma_kp_r(int d) { return 8 * 2 * mma_seg_chunks(d); }        // fp16 columns of ONE part of the reference image
-constexpr int kMmaMaxK = 40;     // neighbours supported by the candidate buffers
 // CM_SPLIT_EPI=1 (experiment, off): per TMEM lane quadrant one SCANNING epilogue warp and one DRAINING warp
 // (knn_mma.cu: SplitCtx).  Exact and green on the search tests, but 13-20 % slower than the one-warp epilogue on
 // B200 (profiles/r2z_split_epilogue_ab.txt), so the shipping build keeps one warp per quadrant.  The scanner's two
@@ -53,10 +52,17 @@ constexpr int kMmaMaxK = 40;     // neighbours supported by the candidate buffer
 #endif
 #endif
 constexpr int kCandCap = CM_CAND_CAP;    // per-row candidate slots in shared memory
-constexpr int kKeepLo = 44;      // after compaction a row keeps between kKeepLo ..
-constexpr int kKeepHi = 60;      // .. and kKeepHi candidates
-constexpr int kCandOut = kKeepHi;
+// neighbours supported by the candidate buffers: after a compaction a row keeps between k + 6 and k + 22 candidates
+// (knn_mma.cu: keep_window), which has to stay below the compaction trigger (kCandCap - 22) and inside the kCandOut
+// slots of the row's output list.  Up to 42 neighbours the <= 64 candidates of a query are re-ranked in registers
+// (rerank64_kernel), above that by the shared-memory kernel.
+constexpr int kMmaMaxK = CM_SPLIT_EPI ? 40 : 64;
+constexpr int kKeepSpan = 22;
+constexpr int kCandOut = 96;     // slots per query and scanning CTA in the candidate lists
 constexpr int kMaxSplits = 8;
+static_assert(kMmaMaxK + kKeepSpan + 2 <= kCandOut, "candidate lists too short for kMmaMaxK");
+static_assert(kMmaMaxK + kKeepSpan < kCandCap - 22, "a compaction must free slots: raise kCandCap or lower kMmaMaxK");
+static inline int mma_cand_max(int k) { return k + kKeepSpan < kCandOut - 2 ? k + kKeepSpan : kCandOut - 2; }
 
 static inline bool mma_supported(int d, int k) { return d <= kMmaMaxD && k <= kMmaMaxK; }
 

@@ -40,6 +40,7 @@
 #ifndef CM_KEEP_HI
 #define CM_KEEP_HI 22  // upper end of the keep window above k (tuning builds override it; 14 fails certificates on inputs with many duplicated points)
 #endif
+static_assert(CM_KEEP_HI <= cm::kKeepSpan, "the candidate lists are sized for a keep window of k + kKeepSpan");
 #ifdef CM_DEV_PROBES
 #define CM_PROBE(...) __VA_ARGS__
 #else
@@ -2177,7 +2178,7 @@ __global__ void __launch_bounds__(kSplit ? kMmaThreadsSplit : kMmaThreads, 1) mm
 // exact re-rank + certificate: one warp per query
 // ------------------------------------------------------------------------------------------------
 constexpr int kRerankWarps = 8;
-constexpr int kRerankNp = 512;  // >= kMaxSplits * kCandOut = 480 candidates per query (the launch uses less when it can)
+constexpr int kRerankNp = 1024;  // >= kMaxSplits * kCandOut = 768 candidates per query (the launch uses less when it can)
 constexpr int kStageRows = 16;  // candidate rows staged per batch
 constexpr int kStageLaneElems = 4;  // elements per lane and staged row: d <= 128
 static_assert(kMaxSplits * kCandOut <= kRerankNp, "re-rank buffer too small");
@@ -2325,7 +2326,7 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
 }
 
 // Register-resident re-rank for queries with at most 64 candidates (every query whose tile was scanned
-// by ONE CTA: <= kCandOut = 60).  Lane l owns candidates l and l + 32: it reads its two candidate rows
+// by ONE CTA and k <= 42: <= k + 22 candidates).  Lane l owns candidates l and l + 32: it reads its two candidate rows
 // itself (no staging, all lanes busy), the query row is broadcast from shared memory, and the 64
 // (d2, index) pairs are sorted by a bitonic network over shuffles -- no shared-memory round trips, no
 // index arithmetic with divisions.  Same outputs and the same certificate as rerank_kernel.
@@ -2798,8 +2799,8 @@ template <typename T>
 int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, int64_t ldr, int d, int k,
                const MmaPlan& pl, const MmaBuffers& b, int64_t r_off, int dist_mode, double* out_dist,
                int64_t* out_idx, cudaStream_t st) {
-  if (pl.n_items == pl.n_q_tiles) {
-    // every query tile was scanned by one CTA: at most kCandOut <= 64 candidates per query
+  if (pl.n_items == pl.n_q_tiles && mma_cand_max(k) <= 64) {
+    // every query tile was scanned by one CTA and k <= 42: at most 64 candidates per query
     const size_t smem64 = (size_t)kRerankWarps * ((d + 1) & ~1) * sizeof(double);
     int64_t blocks64 = ceil_div(n_q, kRerankWarps);
     int grid64 = (int)(blocks64 < (int64_t)kNumSMs * 16 ? blocks64 : (int64_t)kNumSMs * 16);
@@ -2815,7 +2816,7 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
     return CM_OK;
   }
   int np_max = 64;  // power of two >= the candidates one query can have and >= kMmaMaxK
-  while (np_max < (pl.n_items > pl.n_full ? pl.splits : 1) * kCandOut) np_max <<= 1;
+  while (np_max < (pl.n_items > pl.n_full ? pl.splits : 1) * mma_cand_max(k)) np_max <<= 1;
   size_t smem = (size_t)kRerankWarps * (np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double) +
                                        (size_t)kStageRows * (d | 1) * sizeof(T));
   CM_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

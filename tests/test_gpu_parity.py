@@ -99,7 +99,8 @@ def test_search_matches_reference_golden(torch_cuda, name, algo):
     assert (np.diff(d, axis=1) >= 0).all()
 
 
-@pytest.mark.parametrize("n_q,n_r,d,k", [(5000, 5000, 30, 30), (3000, 20000, 50, 30), (1000, 4000, 16, 5), (513, 1000, 50, 40)])
+@pytest.mark.parametrize("n_q,n_r,d,k", [(5000, 5000, 30, 30), (3000, 20000, 50, 30), (1000, 4000, 16, 5), (513, 1000, 50, 40),
+                                        (700, 30000, 50, 50), (300, 2000, 100, 64)])
 def test_search_matches_sklearn_live(torch_cuda, n_q, n_r, d, k):
     """BASELINE config 1 (5k x 5k x 30) and friends against sklearn run on the box's CPU."""
     torch = torch_cuda
@@ -217,7 +218,7 @@ def test_pruned_search_is_exact(torch_cuda, name):
 
 @pytest.mark.parametrize("seed", [1, 2])
 def test_search_randomised_shapes(torch_cuda, seed):
-    """Randomised d (2..53), k (1..40), sizes, dtypes and data kinds (mixtures, uniform, integer lattices full of exact
+    """Randomised d (2..53), k (1..64), sizes, dtypes and data kinds (mixtures, uniform, integer lattices full of exact
     ties, duplicated rows, a 3-d manifold, offset + constant column; tools/stress_search.py): the tensor-core path
     must return the float64 SIMT kernel's distances bit for bit and its neighbours outside exact ties."""
     torch = torch_cuda
@@ -230,7 +231,7 @@ def test_search_randomised_shapes(torch_cuda, seed):
     kinds = ["mixture", "uniform", "lattice", "duplicates", "manifold", "offset_const"]
     for case in range(12):
         kind = kinds[case % len(kinds)]
-        d, k = int(rng.integers(2, 54)), int(rng.integers(1, 41))
+        d, k = int(rng.integers(2, 54)), int(rng.integers(1, 65))
         n_r = int(rng.integers(16_384, 80_000))
         n_q = int(rng.integers(64, 3_000))
         dt = np.float32 if rng.random() < 0.7 else np.float64
@@ -1041,3 +1042,24 @@ def test_pipelined_query_upload_matches_plain_search(torch_cuda, monkeypatch, pi
     d, i = device.knn_search(dev(torch, xq), dev(torch, xr), 15, dist_mode=mode)
     assert torch.equal(nb.yx.indices_device, i) and torch.equal(nb.yx.distances_device, d)
     assert nb.yx.rows_full and int(nb.search_stats["yx"][0]) == 0
+
+
+def test_more_than_42_neighbours_stay_on_the_tensor_path(torch_cuda):
+    """k = 43..64 (round 2: the limit was 40): the candidate lists hold up to k + 22 entries per query and the
+    shared-memory re-rank kernel takes over from the register one.  Exact, no fallback rows, and the tensor-core kernel
+    did the scan (it counts its tile pairs; the float64 brute-force kernel does not)."""
+    torch = torch_cuda
+    from cellmapper_b200 import _lib, device, synth
+
+    centres = synth.mixture_centres(16, 50)
+    xr, _ = synth.mixture_embedding(60_000, centres, seed=1)
+    xq, _ = synth.mixture_embedding(4_000, centres, seed=2)
+    qd, rd = dev(torch, xq), dev(torch, xr)
+    for k in (43, 64):
+        dd, ii, st = device.knn_search(qd, rd, k, return_stats=True)
+        dx, ix = device.knn_search(qd, rd, k, algo=_lib.KNN_EXACT_F64)
+        assert torch.equal(dd, dx) and torch.equal(ii, ix)
+        st = st.cpu().numpy()
+        assert st[0] == 0
+        exhaustive_tiles = -(-4_000 // 128) * -(-60_000 // 128)
+        assert 0 < st[3] <= exhaustive_tiles, st  # stats[3] = tile pairs of the tensor-core kernel (0 on the brute-force path)

@@ -176,7 +176,7 @@ def test_pipelined_query_blocks_decision():
     assert Neighbors(ref, torch.from_numpy(big))._pipelined_query_blocks(30) == [(0, 99_968), (99_968, 400_000)]
     assert Neighbors(ref, big[:1000])._pipelined_query_blocks(30) is None  # small: one upload
     assert Neighbors(ref, big.astype(np.float64))._pipelined_query_blocks(30) is None  # mixed dtypes are promoted on the device
-    assert Neighbors(ref, big)._pipelined_query_blocks(64) is None  # k outside the tensor-core path
+    assert Neighbors(ref, big)._pipelined_query_blocks(65) is None  # k outside the tensor-core path (k <= 64)
     assert Neighbors(big, None)._pipelined_query_blocks(30) is None  # self mapping
     wide = np.zeros((200_000, 200), np.float32)
     assert Neighbors(np.zeros((1000, 200), np.float32), wide)._pipelined_query_blocks(30) is None  # d > 128
