@@ -23,7 +23,7 @@ from scipy.sparse import coo_matrix, csc_matrix, csr_matrix, issparse
 from . import _lib, device
 from ._anndata import AnnData
 from .evaluate import EvaluationMixin, process_presence_scores
-from .knn import Neighbors, NeighborsResults, _to_device
+from .knn import Neighbors, NeighborsResults, _to_device, _to_host
 from .logging import logger
 
 __all__ = ["CellMapper", "PackageConstants", "get_n_comps", "sorted_category_codes", "process_presence_scores"]
@@ -328,7 +328,7 @@ class CellMapper(EvaluationMixin):
                 emb_dev = _to_device(np.asarray(self.reference.obsm[key]))
             out = device.spmm(m.indptr, m.cols, m.vals, emb_dev)
         output_key = f"{key}_{prediction_postfix}"
-        self.query.obsm[output_key] = out.cpu().numpy()
+        self.query.obsm[output_key] = _to_host(out)
         logger.info("Embeddings mapped and stored in query.obsm['%s'].", output_key)
 
     def _layer_device(self, key: str):
@@ -373,7 +373,7 @@ class CellMapper(EvaluationMixin):
         if not issparse(layer):
             dense = device.spmm(m.indptr, m.cols, m.vals, _to_device(np.asarray(layer)))
             self.imputed_device = dense
-            out = dense.cpu().numpy()
+            out = _to_host(dense)
             if chunk_consumer is not None:
                 chunk_consumer(0, self.query.n_obs, out)
                 return
@@ -548,11 +548,11 @@ class CellMapper(EvaluationMixin):
             code_dtype = ref_col.cat.codes.dtype  # int8 up to 127 categories, int16, ...
             lut = _to_device(np.ascontiguousarray(to_orig.astype(code_dtype)))
             pred_codes = lut[code_dev.long()].cpu().numpy()
-            conf = conf_dev.cpu().numpy()
+            conf = _to_host(conf_dev)
             pred = pd.Series(pd.Categorical.from_codes(pred_codes, dtype=ref_col.dtype, validate=False), index=self.query.obs_names, copy=False)
         else:
             pred_codes = code_dev.cpu().numpy()
-            conf = conf_dev.cpu().numpy()
+            conf = _to_host(conf_dev)
             pred = pd.Series(data=np.array(cats)[pred_codes], index=self.query.obs_names, dtype=ref_col.dtype)
         self.query.obs[f"{key}_{prediction_postfix}"] = pred
         self.query.obs[f"{key}_{confidence_postfix}"] = pd.Series(conf, index=self.query.obs_names, copy=False)  # a fresh array: no defensive copy

@@ -26,7 +26,7 @@ import torch
 from scipy.sparse import csr_matrix, issparse
 
 from . import _lib, device
-from .knn import _to_device
+from .knn import _to_device, _to_host
 from .logging import logger
 
 __all__ = ["EvaluationMixin", "process_presence_scores", "percentile_plan", "percentile_from_order_stats"]
@@ -151,12 +151,12 @@ class EvaluationMixin:
         all_dev, groups_dev = self.presence_scores_device(codes_dev, len(groups) if groups is not None else 0)
         _process_column(all_dev, log, tuple(percentile))
         # a fresh array owned by nobody else: pandas' defensive copy of 10 M float64 (31 ms) is not needed
-        self.reference.obs[key_added] = pd.Series(all_dev.cpu().numpy(), index=self.reference.obs_names, copy=False)
+        self.reference.obs[key_added] = pd.Series(_to_host(all_dev), index=self.reference.obs_names, copy=False)
         logger.info("Presence score across all query cells computed and stored in `reference.obs['%s']`", key_added)
         if groupby is not None:
             for g in range(len(groups)):
                 _process_column(groups_dev[:, g], log, tuple(percentile))
-            self.reference.obsm[key_added] = pd.DataFrame(groups_dev.cpu().numpy(), index=self.reference.obs_names, columns=groups)
+            self.reference.obsm[key_added] = pd.DataFrame(_to_host(groups_dev), index=self.reference.obs_names, columns=groups)
             logger.info(
                 "Presence scores per group defined in `query.obs['%s']` computed and stored in `reference.obsm['%s']`",
                 groupby,

@@ -70,6 +70,44 @@ def _staged_upload(src: torch.Tensor, dev: torch.device) -> torch.Tensor:
     return out
 
 
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> numpy array.  Large results (10 M presence scores, 1.5 M x 30 neighbour lists) come down through
+    the same kind of page-locked ring as the uploads: the DMA of chunk i+1 overlaps the host copy of chunk i into an
+    ordinary numpy array.  torch's ``.cpu()`` into pageable memory measured 4.4 GB/s on the GPU box (80 MB: 18 ms)."""
+    if not t.is_cuda:
+        return t.numpy()
+    t = t.contiguous()
+    n = t.numel() * t.element_size()
+    if n < _STAGE_MIN_BYTES:
+        return t.cpu().numpy()
+    dev = t.device
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, "down")
+    bufs = _stage_ring.get(key)
+    if bufs is None:
+        bufs = _stage_ring[key] = [torch.empty(_STAGE_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(_STAGE_SLOTS)]
+    out = torch.empty(t.shape, dtype=t.dtype)
+    s8, d8 = t.reshape(-1).view(torch.uint8), out.reshape(-1).view(torch.uint8)
+    pending: list = []  # (slot, offset, bytes, event) of chunks whose DMA has been enqueued
+
+    def land():
+        slot, off, m, ev = pending.pop(0)
+        ev.synchronize()
+        d8[off : off + m].copy_(bufs[slot][:m])
+
+    for i, off in enumerate(range(0, n, _STAGE_CHUNK_BYTES)):
+        if len(pending) == _STAGE_SLOTS:
+            land()  # frees the slot this chunk is about to use
+        slot = i % _STAGE_SLOTS
+        m = min(_STAGE_CHUNK_BYTES, n - off)
+        bufs[slot][:m].copy_(s8[off : off + m], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append((slot, off, m, ev))
+    while pending:
+        land()
+    return out.numpy()
+
+
 def _to_device(a, dtype=None) -> torch.Tensor:
     if isinstance(a, torch.Tensor) and a.is_cuda:
         t = a
@@ -125,13 +163,13 @@ class NeighborsResults:
     @property
     def distances(self) -> np.ndarray:
         if self._dist_host is None:
-            self._dist_host = self._dist_dev.cpu().numpy()
+            self._dist_host = _to_host(self._dist_dev)
         return self._dist_host
 
     @property
     def indices(self) -> np.ndarray:
         if self._idx_host is None:
-            self._idx_host = self._idx_dev.cpu().numpy()
+            self._idx_host = _to_host(self._idx_dev)
         return self._idx_host
 
     # -- device views --------------------------------------------------------------------------

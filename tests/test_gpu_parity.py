@@ -1063,3 +1063,18 @@ def test_more_than_42_neighbours_stay_on_the_tensor_path(torch_cuda):
         assert st[0] == 0
         exhaustive_tiles = -(-4_000 // 128) * -(-60_000 // 128)
         assert 0 < st[3] <= exhaustive_tiles, st  # stats[3] = tile pairs of the tensor-core kernel (0 on the brute-force path)
+
+
+def test_staged_download_is_a_plain_copy(torch_cuda):
+    """knn._to_host: large device results come down through a ring of page-locked buffers; same bytes as .cpu()."""
+    torch = torch_cuda
+    from cellmapper_b200 import knn
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for shape, dtype in [((3_000_001,), torch.float64), ((700_000, 7), torch.float32), ((5,), torch.int64), ((9_000_000,), torch.int8)]:
+        t = (torch.rand(shape, device="cuda", generator=g) * 100).to(dtype)
+        got = knn._to_host(t)
+        assert isinstance(got, np.ndarray) and got.shape == tuple(shape)
+        np.testing.assert_array_equal(got, t.cpu().numpy())
+    view = torch.arange(6_000_000, device="cuda", dtype=torch.float32).reshape(2_000_000, 3)[:, 1]  # non-contiguous
+    np.testing.assert_array_equal(knn._to_host(view), view.cpu().numpy())
