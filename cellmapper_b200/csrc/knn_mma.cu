@@ -242,25 +242,48 @@ __global__ void centre_kernel(const T* __restrict__ R, int64_t ldr, int64_t n_r,
   }
 }
 
+// ||x - mu||^2 per row (float64) and max |x - mu| over all rows.  One warp per row, kRowstatsUnroll rows per warp and
+// pass with all their loads in flight before the first use: with one row per pass a warp had 200 bytes outstanding and
+// the kernel ran at 0.2 of the HBM rate (1.45 ms for 10 M x 50 float32).  Per row the arithmetic and its order are
+// unchanged (lane partial sums over columns lane, lane + 32, ..., then the xor-shuffle tree).
+constexpr int kRowstatsUnroll = 4;
 template <typename T>
 __global__ void rowstats_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, const double* __restrict__ mu,
                                 double* __restrict__ norms, ScaleInfo* info, int is_ref) {
+  constexpr int U = kRowstatsUnroll;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   float amax = 0.f;
   double nmax = 0.0;
-  for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n;
-       row += (int64_t)gridDim.x * warps_per_block) {
-    double s = 0.0;
+  for (int64_t row0 = ((int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * U; row0 < n;
+       row0 += (int64_t)gridDim.x * warps_per_block * U) {
+    double s[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] = 0.0;
     for (int c = lane; c < d; c += 32) {
-      const double v = (double)X[row * ld + c] - mu[c];
-      s = fma(v, v, s);
-      amax = fmaxf(amax, fabsf((float)v));
+      T x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) x[u] = row0 + u < n ? X[(row0 + u) * ld + c] : (T)0;
+      const double m = mu[c];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double v = row0 + u < n ? (double)x[u] - m : 0.0;
+        s[u] = fma(v, v, s[u]);
+        amax = fmaxf(amax, fabsf((float)v));
+      }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) norms[row] = s;
-    nmax = fmax(nmax, s);
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (row0 + u < n) {
+        if (lane == 0) norms[row0 + u] = s[u];
+        nmax = fmax(nmax, s[u]);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -281,77 +304,94 @@ __device__ __forceinline__ float scale_from_absmax(unsigned int bits) {
 
 constexpr float kNormColumn = 256.f;  // the constant c in the three norm columns of Q'
 
-// One thread per (row, 8-column chunk): one 16-byte store into the operand image.
+// One thread per (row, 8 source columns): the hi / lo split of the 8 values is computed ONCE and written to every
+// segment that holds it (two 16-byte stores for a reference row, three for a query row; the first version ran one thread
+// per OUTPUT chunk and redid the float64 centring and the split for each: 2.4 ms for 10 M reference rows, issue-bound).
 // image byte offset of (row, col) = (row/8) * (kp*16) + (col/8) * 128 + (row%8) * 16 + (col%8) * 2
 // Column meaning (dc = chunks per segment, cs = column inside the segment):
 //   query     seg0: -2*hi(x) for cs<d, c for d<=cs<d+3     seg1: -2*hi(x)     seg2: -2*lo(x)
 //   reference seg0:    hi(x) for cs<d, n1 n2 n3 at d..d+2   seg1:    lo(x)
+__device__ __forceinline__ uint4 pack_half8(const __half (&h)[8]) {
+  uint4 v;
+  v.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+  v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+  v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
+  v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
+  return v;
+}
 template <typename T>
 __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int64_t n_pad, int d, int chunks_part, int dc, int parts,
                             const double* __restrict__ mu, const double* __restrict__ norms,
                             const ScaleInfo* __restrict__ info, int is_query, const int32_t* __restrict__ perm,
                             uint4* __restrict__ img) {
-  // chunks_part: 8-column chunks of one part of a row (query: 3 segments of dc, padded to an even count; reference:
-  // 2 segments of dc); a row has parts * chunks_part chunks.  Extended column of (part, segment, cs) = part*dc*8 + cs.
+  // chunks_part: 8-column chunks of one part of an image row (query: 3 segments of dc, padded to an even count;
+  // reference: 2 segments of dc); an image row has parts * chunks_part chunks.  Extended column of (part, cs) =
+  // part*dc*8 + cs: [0, d) embedding, [d, d+3) norm columns.
   const int chunks = parts * chunks_part;
+  const int src_chunks = parts * dc;  // 8-column groups of the extended source row
   const float scale = scale_from_absmax(info->absmax_bits);
-  const int64_t total = n_pad * chunks;
+  const int64_t total = n_pad * src_chunks;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    // consecutive threads: 8 rows of a group, then the next chunk -> 128 contiguous bytes per 8 lanes
-    const int64_t group = t / (8 * chunks);
-    const int rem = (int)(t - group * 8 * chunks);
-    const int chunk_all = rem >> 3, r8 = rem & 7;
-    const int part = chunk_all / chunks_part, chunk = chunk_all - part * chunks_part;
+    // consecutive threads: 8 rows of a group, then the next chunk -> 128 contiguous bytes per 8 lanes and store
+    const int64_t group = t / (8 * src_chunks);
+    const int rem = (int)(t - group * 8 * src_chunks);
+    const int cc = rem >> 3, r8 = rem & 7;
+    const int part = cc / dc, c = cc - part * dc;
     const int64_t pos = group * 8 + r8;
     // image position -> source row (scan order, see the "coarse cells" section); -1 = padding
     const int64_t prow = perm[pos];
     const int64_t row = prow < 0 ? n : prow;
-    const int seg = chunk / dc;
-    const int n_seg = is_query ? 3 : 2;
-    __half h[8];
+    __half s0[8], s1[8], s2[8];  // the chunk's values in segment 0, 1 and (query) 2
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int cs = part * dc * 8 + (chunk - seg * dc) * 8 + e;  // extended column: [0, d) embedding, [d, d+3) norms
-      float out = 0.f;
-      if (seg < n_seg) {
-        if (row < n) {
-          if (cs < d) {
-            const float xs = (float)(((double)X[row * ld + cs] - mu[cs]) * (double)scale);
-            const __half hi = __float2half_rn(xs);
-            const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
-            if (is_query)
-              out = seg == 2 ? -2.f * lo : -2.f * __half2float(hi);
-            else
-              out = seg == 1 ? lo : __half2float(hi);
-          } else if (seg == 0 && cs < d + 3) {
-            if (is_query) {
-              out = kNormColumn;
-            } else {
-              const double nn = norms[row] * (double)scale * (double)scale / (double)kNormColumn;
-              const float n1 = __half2float(__float2half_rn((float)nn));
-              const float n2 = __half2float(__float2half_rn((float)(nn - (double)n1)));
-              const float n3 = __half2float(__float2half_rn((float)(nn - (double)n1 - (double)n2)));
-              out = cs == d ? n1 : (cs == d + 1 ? n2 : n3);
-            }
+      const int cs = part * dc * 8 + c * 8 + e;
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+      if (row < n) {
+        if (cs < d) {
+          const float xs = (float)(((double)X[row * ld + cs] - mu[cs]) * (double)scale);
+          const __half hi = __float2half_rn(xs);
+          const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
+          if (is_query) {
+            v0 = v1 = -2.f * __half2float(hi);
+            v2 = -2.f * lo;
+          } else {
+            v0 = __half2float(hi);
+            v1 = lo;
           }
-        } else if (!is_query && seg == 0 && cs == d) {
-          out = 65504.f;  // padded reference rows: "infinitely far"
+        } else if (cs < d + 3) {
+          if (is_query) {
+            v0 = kNormColumn;
+          } else {
+            const double nn = norms[row] * (double)scale * (double)scale / (double)kNormColumn;
+            const float n1 = __half2float(__float2half_rn((float)nn));
+            const float n2 = __half2float(__float2half_rn((float)(nn - (double)n1)));
+            const float n3 = __half2float(__float2half_rn((float)(nn - (double)n1 - (double)n2)));
+            v0 = cs == d ? n1 : (cs == d + 1 ? n2 : n3);
+          }
         }
+      } else if (!is_query && cs == d) {
+        v0 = 65504.f;  // padded reference rows: "infinitely far"
       }
-      h[e] = __float2half_rn(out);
+      s0[e] = __float2half_rn(v0);
+      s1[e] = __float2half_rn(v1);
+      s2[e] = __float2half_rn(v2);
     }
-    uint4 v;
-    v.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-    v.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-    v.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
-    v.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
-    if (is_query) {
-      img[pos * chunks + chunk_all] = v;  // row-major, part after part: the epilogue threads copy their own row into TMEM
-    } else {
-      // [tile][part][16 groups of 8 rows][chunk][row in group]: every (tile, part) is one contiguous operand image
-      const int64_t tile = group >> 4;
-      const int g16 = (int)(group & 15);
-      img[((tile * parts + part) * 16 + g16) * (int64_t)(chunks_part * 8) + chunk * 8 + r8] = v;
+    const int n_seg = is_query ? 3 : 2;
+    for (int seg = 0; seg <= n_seg; ++seg) {
+      // seg == n_seg: the zero chunk that pads a query part to an even chunk count (written by the thread of column group 0)
+      if (seg == n_seg && !(c == 0 && chunks_part > n_seg * dc)) break;
+      const int chunk = seg * dc + c;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (seg < n_seg) v = pack_half8(seg == 0 ? s0 : (seg == 1 ? s1 : s2));
+      const int chunk_all = part * chunks_part + chunk;
+      if (is_query) {
+        img[pos * chunks + chunk_all] = v;  // row-major, part after part: the epilogue threads copy their own row into TMEM
+      } else {
+        // [tile][part][16 groups of 8 rows][chunk][row in group]: every (tile, part) is one contiguous operand image
+        const int64_t tile = group >> 4;
+        const int g16 = (int)(group & 15);
+        img[((tile * parts + part) * 16 + g16) * (int64_t)(chunks_part * 8) + chunk * 8 + r8] = v;
+      }
     }
   }
 }
