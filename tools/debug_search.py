@@ -1,4 +1,4 @@
-"""Development helper: one small tensor-core search, all device printf output kept (deadlock diagnosis)."""
+"""Development helper: one search of a given shape or golden file checked against the float64 kernel, all device printf output kept."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
