@@ -2233,18 +2233,19 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
               double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = blockDim.x >> 5;  // <= kRerankWarps: fewer when the per-warp buffers of wide rows / many candidates would not fit
   double* keys = reinterpret_cast<double*>(smem_raw) + (size_t)warp * np_max;
-  int* vals = reinterpret_cast<int*>(smem_raw + (size_t)kRerankWarps * np_max * sizeof(double)) + (size_t)warp * np_max;
-  double* qrow = reinterpret_cast<double*>(smem_raw + (size_t)kRerankWarps * np_max * (sizeof(double) + sizeof(int))) +
+  int* vals = reinterpret_cast<int*>(smem_raw + (size_t)n_warps * np_max * sizeof(double)) + (size_t)warp * np_max;
+  double* qrow = reinterpret_cast<double*>(smem_raw + (size_t)n_warps * np_max * (sizeof(double) + sizeof(int))) +
                  (size_t)warp * d;
   const int ds = d | 1;  // odd row stride of the staging slab: conflict-free column walks
-  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)kRerankWarps * (np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double))) +
+  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)n_warps * (np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double))) +
              (size_t)warp * kStageRows * ds;
   const double scale = (double)scale_from_absmax(info->absmax_bits);
   const double max_rnorm = __longlong_as_double((long long)info->max_rnorm_bits);
 
   // qs = position of the query in the (cell-sorted) scan order, q = its row in the caller's arrays
-  for (int64_t qs = (int64_t)blockIdx.x * kRerankWarps + warp; qs < n_q; qs += (int64_t)gridDim.x * kRerankWarps) {
+  for (int64_t qs = (int64_t)blockIdx.x * n_warps + warp; qs < n_q; qs += (int64_t)gridDim.x * n_warps) {
     const int64_t q = perm_q[qs];
     for (int c = lane; c < d; c += 32) qrow[c] = (double)Q[q * ldq + c];
     __syncwarp();
@@ -2857,12 +2858,14 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
   }
   int np_max = 64;  // power of two >= the candidates one query can have and >= kMmaMaxK
   while (np_max < (pl.n_items > pl.n_full ? pl.splits : 1) * mma_cand_max(k)) np_max <<= 1;
-  size_t smem = (size_t)kRerankWarps * (np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double) +
-                                       (size_t)kStageRows * (d | 1) * sizeof(T));
+  const size_t per_warp = np_max * (sizeof(double) + sizeof(int)) + (size_t)d * sizeof(double) + (size_t)kStageRows * (d | 1) * sizeof(T);
+  int n_warps = kRerankWarps;  // wide float64 rows with 1024 candidate slots need 30 KB per warp: 8 warps would not fit
+  while (n_warps > 1 && (size_t)n_warps * per_warp > 200 * 1024) n_warps >>= 1;
+  const size_t smem = (size_t)n_warps * per_warp;
   CM_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t blocks = ceil_div(n_q, kRerankWarps);
+  int64_t blocks = ceil_div(n_q, n_warps);
   int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
-  rerank_kernel<T><<<grid, kRerankWarps * 32, smem, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, (int)pl.n_full, pl.splits, np_max, b.q_norms,
+  rerank_kernel<T><<<grid, n_warps * 32, smem, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, (int)pl.n_full, pl.splits, np_max, b.q_norms,
                                                          b.cand_s, b.cand_i, b.cand_cnt, b.cand_thr, b.info,
                                                          b.perm_q, b.perm_r, r_off, dist_mode, pl.err_exp, out_dist, out_idx,
                                                          b.fail_rows);

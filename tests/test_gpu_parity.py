@@ -1063,6 +1063,16 @@ def test_more_than_42_neighbours_stay_on_the_tensor_path(torch_cuda):
         assert st[0] == 0
         exhaustive_tiles = -(-4_000 // 128) * -(-60_000 // 128)
         assert 0 < st[3] <= exhaustive_tiles, st  # stats[3] = tile pairs of the tensor-core kernel (0 on the brute-force path)
+    # few queries: the tile is cut into 8 reference ranges, each with its own list of up to k + 22 candidates -> 1024
+    # re-rank slots per query; with wide float64 rows the re-rank kernel's per-warp buffers only fit 4 warps per block
+    # (found by tools/stress_search.py: the launch asked for 238 KB of shared memory)
+    rng = np.random.default_rng(11)
+    xr64 = rng.standard_normal((70_000, 128))
+    xq64 = rng.standard_normal((100, 128))
+    qd, rd = dev(torch, xq64), dev(torch, xr64)
+    dd, ii, st = device.knn_search(qd, rd, 64, return_stats=True)
+    dx, ix = device.knn_search(qd, rd, 64, algo=_lib.KNN_EXACT_F64)
+    assert torch.equal(dd, dx) and torch.equal(ii, ix) and int(st[3]) > 0
 
 
 def test_staged_download_is_a_plain_copy(torch_cuda):

@@ -39,7 +39,7 @@ def main():
     bad_total = 0
     for case in range(n_cases):
         kind = kinds[case % len(kinds)]
-        d = int(rng.integers(2, 54)); k = int(rng.integers(1, 41))
+        d = int(rng.integers(2, 129)); k = int(rng.integers(1, 65))  # the whole tensor-core range (d <= 128, k <= 64)
         n_r = int(rng.integers(16_384, 120_000)); n_q = int(rng.integers(64, min(20_000, 1_500_000_000 // (n_r * max(d, 8)))))
         dt = np.float32 if rng.random() < 0.7 else np.float64
         q, r = make(kind, rng, n_q, n_r, d)
