@@ -50,7 +50,8 @@ enum cm_dist_mode {
 /* search algorithm selector for cm_knn_search */
 enum cm_knn_algo {
   CM_KNN_AUTO = 0,             /* tcgen05 split-fp16 GEMM + exact re-rank, exact f64 fallback per row; reference
-                                  cells that a triangle-inequality bound rules out are skipped (still exact)  */
+                                  cells that a triangle-inequality bound rules out are skipped (still exact).
+                                  Covers d <= 128 and k <= 64; beyond that AUTO is CM_KNN_EXACT_F64            */
   CM_KNN_EXACT_F64 = 1,        /* SIMT float64 brute force only (ground truth / fallback kernel)             */
   CM_KNN_TENSOR_EXHAUSTIVE = 2 /* the tensor-core path with the pruning switched off: every (query tile,
                                   reference tile) pair is multiplied.  Same results as CM_KNN_AUTO; it is the
