@@ -105,6 +105,55 @@ def process_presence_scores(scores: pd.DataFrame, log: bool = False, percentile:
     return pd.DataFrame(out, index=scores.index, columns=scores.columns)
 
 
+def _dense_columns(indptr, cols, vals, row_lo, row_hi, col_map, n_out, out):
+    """Rows [row_lo, row_hi) of a device CSR (``indptr`` relative to the block) as dense columns ``col_map[col]`` (-1: drop)."""
+    n_rows = row_hi - row_lo
+    if out is None:
+        out = torch.zeros((n_rows, n_out), dtype=vals.dtype, device=vals.device)
+        row_lo = 0
+    counts = (indptr[1:] - indptr[:-1]).long()
+    nnz = int(counts.sum())
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=vals.device), counts) + row_lo
+    m = col_map.long()[cols[:nnz].long()]
+    keep = m >= 0
+    out[rows[keep], m[keep]] = vals[:nnz][keep].to(out.dtype)
+    return out
+
+
+def _average_ranks(x: torch.Tensor) -> torch.Tensor:
+    """Column-wise ``scipy.stats.rankdata(method="average")`` of a dense (n, g) block; float64."""
+    n, g = x.shape
+    s, idx = torch.sort(x, dim=0, stable=True)
+    pos = torch.arange(n, device=x.device, dtype=torch.float64).unsqueeze(1).expand(n, g)
+    new = torch.ones((n, g), dtype=torch.bool, device=x.device)
+    new[1:] = s[1:] != s[:-1]  # first element of a group of equal values
+    end = torch.ones_like(new)
+    end[:-1] = new[1:]  # last element of a group
+    first = torch.cummax(torch.where(new, pos, torch.full_like(pos, -1.0)), dim=0).values
+    last = torch.flip(torch.cummin(torch.flip(torch.where(end, pos, torch.full_like(pos, float(n))), [0]), dim=0).values, [0])
+    ranks = torch.empty((n, g), dtype=torch.float64, device=x.device)
+    ranks.scatter_(0, idx, (first + last) * 0.5 + 1.0)
+    return ranks
+
+
+def _spearman_columns(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Spearman correlation of every column pair of two dense (n, g) blocks (NaN for a constant column), in column
+    chunks that keep the temporaries below ~1 GB."""
+    n, g = a.shape
+    out = torch.full((g,), float("nan"), dtype=torch.float64, device=a.device)
+    if n < 2:
+        return out
+    step = max(1, int(1e9 // (max(n, 1) * 96)))
+    for c0 in range(0, g, step):
+        ra, rb = _average_ranks(a[:, c0 : c0 + step]), _average_ranks(b[:, c0 : c0 + step])
+        ra -= ra.mean(dim=0, keepdim=True)
+        rb -= rb.mean(dim=0, keepdim=True)
+        den = torch.sqrt((ra * ra).sum(0) * (rb * rb).sum(0))
+        r = (ra * rb).sum(0) / den
+        out[c0 : c0 + step] = torch.where(den > 0, r, torch.full_like(r, float("nan")))
+    return out
+
+
 def _group_codes(labels: pd.Series):
     """(groups in order of first appearance -- ``Series.unique()``, evaluate.py:465 --, int32 code per row; missing
     values get -1 and belong to no group, as ``group_labels == group`` is False for them)."""
@@ -214,16 +263,13 @@ class EvaluationMixin:
         ``impute_key`` (keyword-only, not in the reference): evaluate the transfer of ``reference.X`` /
         ``reference.layers[impute_key]`` WITHOUT materialising the imputed matrix: the chunks of ``M @ X`` are
         consumed on the device as they are produced.  Otherwise ``query_imputed`` is used, like the reference.
-        Supported: "pearson", "rmse" (one sweep), "js" (two sweeps).  "spearman" needs per-gene ranks over all
-        cells, i.e. the densified columns: not available on the streamed path."""
+        "pearson", "rmse" (one sweep) and "js" (two sweeps) never densify anything.  "spearman" needs per-gene ranks
+        over all cells (of a group), i.e. whole columns: both matrices are densified ON THE DEVICE for the shared genes
+        (float32 / float64 like the reference's arrays) and ranked with average ranks for ties, which bounds it to
+        ``n_cells * n_shared_genes <= 2**30`` -- the reference, which densifies on the host, has the same kind of limit."""
         if method in ("jensen-shannon",):
             method = "js"
-        if method == "spearman":
-            raise NotImplementedError(
-                "method='spearman' is not implemented by the b200 backend (per-gene ranks need the densified matrix); "
-                "use 'pearson', 'rmse' or 'js'."
-            )
-        if method not in ("pearson", "js", "rmse"):
+        if method not in ("pearson", "spearman", "js", "rmse"):
             raise NotImplementedError(f"Method '{method}' is not implemented.")
         if impute_key is None and self.query_imputed is None:
             raise ValueError("Imputed query data not found. Either run map_layers() first or set query_imputed manually.")
@@ -253,6 +299,10 @@ class EvaluationMixin:
         n_sets = 1 + (len(groups) if groups is not None else 0)
         o_ip, o_cols, o_vals = self._original_expression_device(layer_key)
         dev = o_ip.device
+        if method == "spearman":
+            values = self._spearman_values(impute_key, max_chunk_nnz, (o_ip, o_cols, o_vals), maps, codes_dev, n_sets, n_shared)
+            self._finish_expression_metric(method, values, shared_genes, groups, groupby, test_var_key)
+            return
         moments = torch.zeros((n_sets, _lib.MOMENTS, n_shared), dtype=torch.float64, device=dev)
         for ch in self._imputed_chunks(impute_key, max_chunk_nnz):
             device.expr_gene_sums(False, ch.indptr, ch.cols, ch.vals, ch.row_lo, o_ip, o_cols, o_vals, maps, codes_dev, n_shared, moments)
@@ -265,6 +315,39 @@ class EvaluationMixin:
         counts = np.array([self.query.n_obs] + ([int((codes == g).sum()) for g in range(len(groups))] if groups is not None else []), dtype=np.float64)
         values = _metric_from_sums(method, mom, counts, js_sums.cpu().numpy() if js_sums is not None else None)
 
+        self._finish_expression_metric(method, values, shared_genes, groups, groupby, test_var_key)
+
+    # Spearman: Pearson correlation of per-gene average ranks (scipy.stats.spearmanr, evaluate.py:276-277).  Not on the hot
+    # path and bounded by the dense columns it needs, so it is written with torch tensor operations on the device
+    # (sort + tie groups), not with a hand-written kernel.
+    _SPEARMAN_MAX_ELEMS = 1 << 30
+
+    def _spearman_values(self, impute_key, max_chunk_nnz, original, maps, codes_dev, n_sets, n_shared) -> np.ndarray:
+        imp_to_shared, orig_to_shared = maps[0], maps[1]
+        n = self.query.n_obs
+        if n * n_shared > self._SPEARMAN_MAX_ELEMS:
+            raise NotImplementedError(
+                f"method='spearman' ranks whole gene columns and densifies {n} cells x {n_shared} genes on the device; "
+                f"the limit is {self._SPEARMAN_MAX_ELEMS} elements. Use 'pearson', 'rmse' or 'js' (streamed), or pass fewer genes."
+            )
+        o_ip, o_cols, o_vals = original
+        dense_o = _dense_columns(o_ip, o_cols, o_vals, 0, n, orig_to_shared, n_shared, None)
+        dense_i = None
+        for ch in self._imputed_chunks(impute_key, max_chunk_nnz):
+            if dense_i is None:
+                dense_i = torch.zeros((n, n_shared), dtype=ch.vals.dtype, device=ch.vals.device)
+            _dense_columns(ch.indptr, ch.cols, ch.vals, ch.row_lo, ch.row_hi, imp_to_shared, n_shared, dense_i)
+        out = np.empty((n_sets, n_shared), dtype=np.float32)
+        for si in range(n_sets):
+            if si == 0:
+                a, b = dense_o, dense_i
+            else:
+                rows = torch.nonzero(codes_dev == si - 1).ravel()
+                a, b = dense_o[rows], dense_i[rows]
+            out[si] = _spearman_columns(a, b).cpu().numpy().astype(np.float32)
+        return out
+
+    def _finish_expression_metric(self, method, values, shared_genes, groups, groupby, test_var_key) -> None:
         self._store_expression_metric(shared_genes, values[0], method, test_var_key)
         if groupby is not None:
             metrics_df = pd.DataFrame(

@@ -367,7 +367,7 @@ def expression_transfer_metrics(imputed, original, method: str = "pearson", mask
     import warnings
 
     from scipy.spatial.distance import jensenshannon
-    from scipy.stats import pearsonr
+    from scipy.stats import pearsonr, spearmanr
 
     a = original.toarray() if issparse(original) else np.asarray(original)
     b = imputed.toarray() if issparse(imputed) else np.asarray(imputed)
@@ -387,7 +387,7 @@ def expression_transfer_metrics(imputed, original, method: str = "pearson", mask
 
         return np.sqrt(np.mean((z(x) - z(y)) ** 2))
 
-    fn = {"pearson": lambda x, y: pearsonr(x, y)[0], "js": js, "rmse": rmse}[method]
+    fn = {"pearson": lambda x, y: pearsonr(x, y)[0], "spearman": lambda x, y: spearmanr(x, y)[0], "js": js, "rmse": rmse}[method]
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return np.array([fn(a[:, i], b[:, i]) for i in range(a.shape[1])], dtype=np.float32)

@@ -216,7 +216,7 @@ def case_reference_unit_fixtures(name):
 
 def case_evaluate(name, n_q, n_r, d, k, n_comp, n_genes):
     """Consumers of the path: evaluate_expression_transfer (evaluate.py:236-424: pearson / rmse / js, groupby,
-    test_var_key), estimate_presence_score with groupby / log / percentile (evaluate.py:426-521), and an
+    test_var_key; round 2 also spearman), estimate_presence_score with groupby / log / percentile (evaluate.py:426-521), and an
     integer-valued layer (scipy promotes M @ X to float64)."""
     CellMapper, Neighbors, NeighborsResults, AnnData = reference_shim.load()
     xr, xq, cr, cq, labels, umap, score, expr = build_pair(n_q, n_r, d, n_comp, n_genes)
@@ -265,7 +265,7 @@ def case_evaluate(name, n_q, n_r, d, k, n_comp, n_genes):
     out.update(csr_parts("imputed", cm.query_imputed.X))
     import warnings
 
-    for method in ("pearson", "rmse", "js"):
+    for method in ("pearson", "rmse", "js", "spearman"):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             cm.evaluate_expression_transfer(layer_key="X", method=method, groupby="batch", test_var_key="is_test")

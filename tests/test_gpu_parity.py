@@ -780,7 +780,7 @@ def pd_codes(series):
     return pd.factorize(series)[0].astype(np.int32)
 
 
-@pytest.mark.parametrize("method", ["pearson", "rmse", "js"])
+@pytest.mark.parametrize("method", ["pearson", "rmse", "js", "spearman"])
 @pytest.mark.parametrize("streamed", [False, True])
 def test_evaluate_expression_transfer_matches_reference(torch_cuda, method, streamed):
     """Per-gene agreement of imputed and original expression from sums accumulated on the device -- from
@@ -815,7 +815,11 @@ def test_evaluate_expression_transfer_matches_reference(torch_cuda, method, stre
     assert m["method"] == method and m["n_test_genes"] == int(g[f"n_test_{method}"])
     np.testing.assert_allclose(m["average"], float(g[f"average_{method}"]), atol=tol)
     with pytest.raises(NotImplementedError):
-        cm.evaluate_expression_transfer(method="spearman", impute_key="X")
+        cm.evaluate_expression_transfer(method="kendall", impute_key="X")
+    if method == "spearman":  # dense columns on the device: bounded, and the bound is an error, not a silent fallback
+        cm._SPEARMAN_MAX_ELEMS = 1000
+        with pytest.raises(NotImplementedError, match="densifies"):
+            cm.evaluate_expression_transfer(method="spearman", impute_key="X")
 
 
 def test_integer_layer_gives_float64_like_scipy(torch_cuda):

@@ -180,3 +180,34 @@ def test_pipelined_query_blocks_decision():
     assert Neighbors(big, None)._pipelined_query_blocks(30) is None  # self mapping
     wide = np.zeros((200_000, 200), np.float32)
     assert Neighbors(np.zeros((1000, 200), np.float32), wide)._pipelined_query_blocks(30) is None  # d > 128
+
+
+def test_average_ranks_and_spearman_match_scipy():
+    """The tensor-operation restatement of scipy.stats.rankdata(method="average") / spearmanr used by
+    evaluate_expression_transfer(method="spearman") -- checked on the CPU (the same code runs on the device)."""
+    import warnings
+
+    import torch
+    from scipy.stats import rankdata, spearmanr
+
+    from cellmapper_b200.evaluate import _average_ranks, _dense_columns, _spearman_columns
+
+    rng = np.random.default_rng(0)
+    a = (rng.random((257, 9)) * (rng.random((257, 9)) < 0.4)).astype(np.float32)  # sparse-like: most entries tie at zero
+    b = (rng.integers(0, 4, (257, 9)) * (rng.random((257, 9)) < 0.6)).astype(np.float64)  # integer ties
+    a[:, 3] = 0.0  # a constant column: NaN
+    ra = _average_ranks(torch.from_numpy(a)).numpy()
+    np.testing.assert_array_equal(ra, np.stack([rankdata(a[:, j]) for j in range(9)], 1))
+    got = _spearman_columns(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.array([spearmanr(a[:, j], b[:, j])[0] for j in range(9)])
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got[~np.isnan(want)], want[~np.isnan(want)], rtol=0, atol=1e-14)
+    # CSR rows -> dense columns of selected genes
+    from scipy.sparse import csr_matrix
+
+    m = csr_matrix(a)
+    col_map = torch.tensor([2, -1, 0, -1, -1, 1, -1, -1, -1], dtype=torch.int32)
+    dense = _dense_columns(torch.from_numpy(m.indptr.astype(np.int64)), torch.from_numpy(m.indices), torch.from_numpy(m.data), 0, 257, col_map, 3, None)
+    np.testing.assert_array_equal(dense.numpy(), a[:, [2, 5, 0]])

@@ -196,7 +196,7 @@ def _aligned_evaluate_matrices(g):
     return imp, orig, shared, q_genes
 
 
-@pytest.mark.parametrize("method", ["pearson", "rmse", "js"])
+@pytest.mark.parametrize("method", ["pearson", "rmse", "js", "spearman"])
 def test_expression_transfer_metrics_match_reference(method):
     g = load_golden("evaluate")
     imp, orig, shared, q_genes = _aligned_evaluate_matrices(g)
