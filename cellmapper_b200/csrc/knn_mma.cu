@@ -238,7 +238,9 @@ __global__ void centre_kernel(const T* __restrict__ R, int64_t ldr, int64_t n_r,
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     double s = 0.0;
     for (int64_t j = 0; j < n_s; ++j) s += (double)R[j * stride * ldr + c];
-    mu[c] = s / (double)n_s;
+    // rounded to float: the origin is arbitrary (distances do not depend on it), and with a float-representable origin
+    // float32 inputs can be centred in float32 -- (x - mu) * scale is then the same value the float64 path returns
+    mu[c] = (double)(float)(s / (double)n_s);
   }
 }
 
@@ -311,6 +313,16 @@ constexpr float kNormColumn = 256.f;  // the constant c in the three norm column
 // Column meaning (dc = chunks per segment, cs = column inside the segment):
 //   query     seg0: -2*hi(x) for cs<d, c for d<=cs<d+3     seg1: -2*hi(x)     seg2: -2*lo(x)
 //   reference seg0:    hi(x) for cs<d, n1 n2 n3 at d..d+2   seg1:    lo(x)
+// (x - mu) * scale as a float.  float32 input: mu is float-representable (centre_kernel) and scale a power of two, so one
+// float subtraction gives the correctly rounded difference -- what the float64 route returns after its final rounding --
+// without the two conversions and the float64 add per element that bounded the operand builds.
+template <typename T>
+__device__ __forceinline__ float centred_scaled(T x, double mu, float mu_f, float scale) {  // mu_f == (float)mu == mu
+  if constexpr (sizeof(T) == 4)
+    return (x - mu_f) * scale;
+  else
+    return (float)(((double)x - mu) * (double)scale);
+}
 __device__ __forceinline__ uint4 pack_half8(const __half (&h)[8]) {
   uint4 v;
   v.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
@@ -348,7 +360,8 @@ __global__ void prep_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int6
       float v0 = 0.f, v1 = 0.f, v2 = 0.f;
       if (row < n) {
         if (cs < d) {
-          const float xs = (float)(((double)X[row * ld + cs] - mu[cs]) * (double)scale);
+          const double m = mu[cs];
+          const float xs = centred_scaled<T>(X[row * ld + cs], m, (float)m, scale);
           const __half hi = __float2half_rn(xs);
           const float lo = __half2float(__float2half_rn(xs - __half2float(hi)));
           if (is_query) {
@@ -849,8 +862,12 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
   __shared__ unsigned int rad[kMaxCells];
   __shared__ uint32_t wmin[4][MODE == kPivBounds ? kMaxCells : 1];
   __shared__ double smu[64];
+  __shared__ float smu_f[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 64) smu[threadIdx.x] = (int)threadIdx.x < p.d ? p.mu[threadIdx.x] : 0.0;
+  if (threadIdx.x < 64) {
+    smu[threadIdx.x] = (int)threadIdx.x < p.d ? p.mu[threadIdx.x] : 0.0;
+    smu_f[threadIdx.x] = (float)smu[threadIdx.x];
+  }
   const uint32_t b_bytes = (uint32_t)kMmaTile * p.kp_r * 2;
   const uint32_t bar_b = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
   for (int i = threadIdx.x; i < kMaxCells; i += kPivThreads) {
@@ -949,7 +966,7 @@ __global__ void __launch_bounds__(kPivThreads, 2) pivot_tc_kernel(const T* __res
             lo[e2] = hi[e2];
             if (row >= 0) {
               if (cs < p.d) {
-                const float xs = (float)((double)xr[cs] - smu[cs]) * scale;  // scale is a power of two: the same value as prep_kernel's
+                const float xs = centred_scaled<T>(xr[cs], smu[cs], smu_f[cs], scale);  // the same value as prep_kernel's
                 hi[e2] = __float2half_rn(xs);
                 lo[e2] = __float2half_rn(xs - __half2float(hi[e2]));
               } else if (cs < p.d + 3) {
