@@ -63,6 +63,8 @@ constexpr int kMaxSplits = 8;
 static_assert(kMmaMaxK + kKeepSpan + 2 <= kCandOut, "candidate lists too short for kMmaMaxK");
 static_assert(kMmaMaxK + kKeepSpan < kCandCap - 22, "a compaction must free slots: raise kCandCap or lower kMmaMaxK");
 static inline int mma_cand_max(int k) { return k + kKeepSpan < kCandOut - 2 ? k + kKeepSpan : kCandOut - 2; }
+// slots between consecutive queries' lists: 64 while a list fits (k <= 42), else all kCandOut (the workspace is sized for that)
+static inline int mma_cand_stride(int k) { return mma_cand_max(k) <= 64 ? 64 : kCandOut; }
 
 static inline bool mma_supported(int d, int k) { return d <= kMmaMaxD && k <= kMmaMaxK; }
 

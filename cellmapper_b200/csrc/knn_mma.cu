@@ -1424,7 +1424,8 @@ struct MmaParams {
   const unsigned char* r_img;  // n_r_tiles tiles of 128 x kp_r fp16
   int n_q_tiles, n_r_tiles, kp_q, kp_r, dc, parts, stages, k;  // kp_q: whole query row; kp_r, dc: one part
   int n_full, splits;  // work items: query tiles [0, n_full) scan the whole reference, the rest are cut in `splits`
-  float* cand_s;      // [n_items * 128][kCandOut], item = blockIdx.x
+  int cand_stride;    // slots per query in cand_s / cand_i (mma_cand_stride(k))
+  float* cand_s;      // [n_items * 128][cand_stride], item = blockIdx.x
   int32_t* cand_i;    // same
   int32_t* cand_cnt;  // [n_items * 128]
   float* cand_thr;    // [n_items * 128]
@@ -2117,8 +2118,8 @@ __global__ void __launch_bounds__(kSplit ? kMmaThreadsSplit : kMmaThreads, 1) mm
         compact_row(rc, p.k);  // leave at most kCandOut entries
         const int64_t o = (int64_t)blockIdx.x * kMmaTile + row_in_tile;
         for (int e = 0; e < rc.cnt; ++e) {
-          p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
-          p.cand_i[o * kCandOut + e] = (int32_t)lds_u32(rc.idx + e * kCandStride);
+          p.cand_s[o * p.cand_stride + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
+          p.cand_i[o * p.cand_stride + e] = (int32_t)lds_u32(rc.idx + e * kCandStride);
         }
         p.cand_cnt[o] = rc.cnt;
         p.cand_thr[o] = rc.thr;
@@ -2213,8 +2214,8 @@ __global__ void __launch_bounds__(kSplit ? kMmaThreadsSplit : kMmaThreads, 1) mm
 #endif
     const int64_t o = (int64_t)blockIdx.x * kMmaTile + row_in_tile;
     for (int e = 0; e < rc.cnt; ++e) {
-      p.cand_s[o * kCandOut + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
-      p.cand_i[o * kCandOut + e] = (int32_t)lds_u32(rc.idx + e * kCandStride);
+      p.cand_s[o * p.cand_stride + e] = __uint_as_float(lds_u32(rc.keys + e * kCandStride));
+      p.cand_i[o * p.cand_stride + e] = (int32_t)lds_u32(rc.idx + e * kCandStride);
     }
     p.cand_cnt[o] = rc.cnt;
     p.cand_thr[o] = rc.thr;
@@ -2246,7 +2247,7 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
               int k, int n_full, int splits, int np_max, const double* __restrict__ q_norms, const float* __restrict__ cand_s,
               const int32_t* __restrict__ cand_i, const int32_t* __restrict__ cand_cnt,
               const float* __restrict__ cand_thr, ScaleInfo* info, const int32_t* __restrict__ perm_q,
-              const int32_t* __restrict__ perm_r, int64_t r_index_offset, int dist_mode, int err_exp,
+              const int32_t* __restrict__ perm_r, int64_t r_index_offset, int dist_mode, int err_exp, int cand_stride,
               double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2282,7 +2283,7 @@ rerank_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, int
     int filled = 0;
     for (int s = 0; s < n_it; ++s) {
       const int c_s = cand_cnt[(item0 + s) * kMmaTile + qr];
-      const int64_t o = ((item0 + s) * kMmaTile + qr) * kCandOut;
+      const int64_t o = ((item0 + s) * kMmaTile + qr) * cand_stride;
       for (int e = lane; e < c_s; e += 32) vals[filled + e] = perm_r[cand_i[o + e]];
       filled += c_s;
     }
@@ -2404,7 +2405,8 @@ rerank64_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, i
                 int k, const double* __restrict__ q_norms, const int32_t* __restrict__ cand_i,
                 const int32_t* __restrict__ cand_cnt, const float* __restrict__ cand_thr, ScaleInfo* info,
                 const int32_t* __restrict__ perm_q, const int32_t* __restrict__ perm_r, int64_t r_index_offset,
-                int dist_mode, int err_exp, double* __restrict__ out_dist, int64_t* __restrict__ out_idx, int32_t* __restrict__ fail_rows) {
+                int dist_mode, int err_exp, int cand_stride, double* __restrict__ out_dist, int64_t* __restrict__ out_idx,
+                int32_t* __restrict__ fail_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dp = (d + 1) & ~1;
@@ -2418,8 +2420,8 @@ rerank64_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ R, i
     const int total = cand_cnt[qs];  // item == query tile: candidate row index == scan position
     const float thr = cand_thr[qs];
     int id0 = -1, id1 = -1;
-    if (lane < total) id0 = perm_r[cand_i[qs * kCandOut + lane]];
-    if (lane + 32 < total) id1 = perm_r[cand_i[qs * kCandOut + lane + 32]];
+    if (lane < total) id0 = perm_r[cand_i[qs * cand_stride + lane]];
+    if (lane + 32 < total) id1 = perm_r[cand_i[qs * cand_stride + lane + 32]];
     __syncwarp();  // the previous query's reads of qrow are done
     for (int c = lane; c < dp; c += 32) qrow[c] = c < d ? (double)Q[q * ldq + c] : 0.0;
     __syncwarp();
@@ -2819,6 +2821,7 @@ int run_mma(const MmaPlan& pl, const MmaBuffers& b, int k, float* debug_out, cud
   p.parts = pl.parts;
   p.stages = pl.stages;
   p.k = k;
+  p.cand_stride = mma_cand_stride(k);
   p.cand_s = b.cand_s;
   p.cand_i = b.cand_i;
   p.cand_cnt = b.cand_cnt;
@@ -2865,11 +2868,11 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
     if (d <= 56)
       rerank64_kernel<T, 7><<<grid64, kRerankWarps * 32, smem64, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, b.q_norms, b.cand_i, b.cand_cnt,
                                                                       b.cand_thr, b.info, b.perm_q, b.perm_r, r_off, dist_mode,
-                                                                      pl.err_exp, out_dist, out_idx, b.fail_rows);
+                                                                      pl.err_exp, mma_cand_stride(k), out_dist, out_idx, b.fail_rows);
     else
       rerank64_kernel<T, 16><<<grid64, kRerankWarps * 32, smem64, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, b.q_norms, b.cand_i, b.cand_cnt,
                                                                        b.cand_thr, b.info, b.perm_q, b.perm_r, r_off, dist_mode,
-                                                                       pl.err_exp, out_dist, out_idx, b.fail_rows);
+                                                                       pl.err_exp, mma_cand_stride(k), out_dist, out_idx, b.fail_rows);
     CM_LAUNCH_CHECK("rerank64_kernel");
     return CM_OK;
   }
@@ -2884,7 +2887,7 @@ int run_rerank(const T* Q, int64_t n_q, int64_t ldq, const T* R, int64_t n_r, in
   int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
   rerank_kernel<T><<<grid, n_warps * 32, smem, st>>>(Q, ldq, R, ldr, n_q, n_r, d, k, (int)pl.n_full, pl.splits, np_max, b.q_norms,
                                                          b.cand_s, b.cand_i, b.cand_cnt, b.cand_thr, b.info,
-                                                         b.perm_q, b.perm_r, r_off, dist_mode, pl.err_exp, out_dist, out_idx,
+                                                         b.perm_q, b.perm_r, r_off, dist_mode, pl.err_exp, mma_cand_stride(k), out_dist, out_idx,
                                                          b.fail_rows);
   CM_LAUNCH_CHECK("rerank_kernel");
   return CM_OK;
