@@ -81,7 +81,8 @@ def _to_host(t: torch.Tensor) -> np.ndarray:
     if n < _STAGE_MIN_BYTES:
         return t.cpu().numpy()
     dev = t.device
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, "down")
+    stream = torch.cuda.current_stream(dev)  # the tensor's device, which need not be the current one
+    key = (dev.index, stream.cuda_stream, "down")
     bufs = _stage_ring.get(key)
     if bufs is None:
         bufs = _stage_ring[key] = [torch.empty(_STAGE_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(_STAGE_SLOTS)]
@@ -94,17 +95,18 @@ def _to_host(t: torch.Tensor) -> np.ndarray:
         ev.synchronize()
         d8[off : off + m].copy_(bufs[slot][:m])
 
-    for i, off in enumerate(range(0, n, _STAGE_CHUNK_BYTES)):
-        if len(pending) == _STAGE_SLOTS:
-            land()  # frees the slot this chunk is about to use
-        slot = i % _STAGE_SLOTS
-        m = min(_STAGE_CHUNK_BYTES, n - off)
-        bufs[slot][:m].copy_(s8[off : off + m], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        pending.append((slot, off, m, ev))
-    while pending:
-        land()
+    with torch.cuda.device(dev), torch.cuda.stream(stream):
+        for i, off in enumerate(range(0, n, _STAGE_CHUNK_BYTES)):
+            if len(pending) == _STAGE_SLOTS:
+                land()  # frees the slot this chunk is about to use
+            slot = i % _STAGE_SLOTS
+            m = min(_STAGE_CHUNK_BYTES, n - off)
+            bufs[slot][:m].copy_(s8[off : off + m], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            pending.append((slot, off, m, ev))
+        while pending:
+            land()
     return out.numpy()
 
 
